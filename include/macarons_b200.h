@@ -1,0 +1,98 @@
+/*
+ * macarons_b200 -- C ABI of the Blackwell (sm_100a) next-best-view scoring path.
+ *
+ * The reference (Anttwo/MACARONS, pure Python) has no FFI layer of its own; its boundary for this
+ * path is the Python module API.  Each entry point below is the native
+ * replacement for the body of one reference function and is bound with ctypes from the
+ * reference-shaped Python classes in macarons_b200/networks and macarons_b200/utility (see
+ * INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; all tensors are caller-owned, dense, row-major fp32;
+ *   - `*_f32` entry points take DEVICE pointers and enqueue asynchronously on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - `*_host` entry points take HOST pointers, copy in/out themselves and return after the
+ *     result is in host memory;
+ *   - return value 0 = success, negative = error (mac_last_error() gives the message of the last
+ *     failure on the calling thread);
+ *   - no entry point allocates or frees caller memory; workspaces are sized by the matching
+ *     `*_workspace_bytes` query and must be zero-filled ONCE by the caller before first use
+ *     (every successful call leaves them zero-filled again).
+ */
+#ifndef MACARONS_B200_H
+#define MACARONS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAC_OK 0
+#define MAC_ERR_INVALID_ARGUMENT (-1)
+#define MAC_ERR_CUDA (-2)
+#define MAC_ERR_WORKSPACE (-3)
+#define MAC_ERR_UNSUPPORTED (-4)
+
+#define MAC_ACT_RELU 0    /* use_sigmoid=False branch, networks/SconeVis.py:245-246 */
+#define MAC_ACT_SIGMOID 1 /* use_sigmoid=True  branch, networks/SconeVis.py:243-244 */
+
+#define MAC_N_HARMONICS 64 /* l < 8; hard-coded 64 at networks/SconeVis.py:241 */
+
+/* Library version: major*10000 + minor*100 + patch. */
+int mac_version(void);
+/* Message of the last error raised on this thread ("" if none). */
+const char *mac_last_error(void);
+/* Compute capability the device code was built for (100 for sm_100a). */
+int mac_built_for_sm(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Coverage gain  --  replaces the bodies of
+ *     SconeVis.compute_coverage_gain      /root/reference/macarons/networks/SconeVis.py:210-252
+ *     SconeVis.compute_visibilities       /root/reference/macarons/networks/SconeVis.py:164-208
+ *     Macarons.compute_visibility_gains   /root/reference/macarons/networks/Macarons.py:138-178
+ * (and with them get_spherical_coords, utility/CustomGeometry.py:27-45, and
+ *  get_spherical_harmonics, utility/spherical_harmonics.py:143-156, on the ray tensor).
+ *
+ *   pts        (B, P, pts_dim) fp32, only [..., :3] is read; pts_dim >= 3
+ *   harmonics  (B, P, 64) fp32, coefficient k = l*l + l + m of each point's visibility-gain function
+ *   cams       (B, C, 3)  fp32 camera centres
+ *   cam_begin, cam_end    this call scores cameras [cam_begin, cam_end) of every cloud
+ *                         (the multi-GPU partition: rank r passes its own slice)
+ *   act        MAC_ACT_SIGMOID / MAC_ACT_RELU
+ *
+ * mac_covgain_f32:      out (B, C) fp32; only columns [cam_begin, cam_end) are written:
+ *                       out[b,c] = (1/P) sum_p act( sum_k Y_k(cam_c - pt_p) * harmonics[b,p,k] )
+ * mac_visibility_f32:   out (B, C, P) fp32; only rows [cam_begin, cam_end) are written (no mean).
+ *
+ * Workspace (mac_covgain_f32 only): mac_covgain_workspace_bytes(B, C) bytes of device memory,
+ * zero-filled once by the caller.  Results are bitwise independent of the launch configuration,
+ * of scheduling and of how the camera axis is partitioned across calls / GPUs.
+ * ------------------------------------------------------------------------------------------- */
+size_t mac_covgain_workspace_bytes(int B, int C);
+
+int mac_covgain_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams,
+                    float *out, int B, int P, int C, int cam_begin, int cam_end, int act,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+int mac_visibility_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams,
+                       float *out, int B, int P, int C, int cam_begin, int cam_end, int act,
+                       void *stream);
+
+/* Host-buffer form of mac_covgain_f32 (the call a non-torch caller makes): copies pts/harmonics/
+ * cams to the device `device` (pinned staging is the caller's business), runs the kernel, copies
+ * the [cam_begin, cam_end) columns of `out` back and synchronises.  Device buffers are cached per
+ * thread between calls and released by mac_host_release(). */
+int mac_covgain_host(const float *pts, int pts_dim, const float *harmonics, const float *cams,
+                     float *out, int B, int P, int C, int cam_begin, int cam_end, int act,
+                     int device);
+void mac_host_release(void);
+
+/* Number of kernel launches the library has enqueued since load (for bench.py's gpu_launches). */
+unsigned long long mac_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACARONS_B200_H */

@@ -1,0 +1,68 @@
+"""ctypes binding of libmacarons_b200.so (the C ABI declared in include/macarons_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, an exception is
+raised.  The library is built in-tree by `macarons_b200.build.build()` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_LIB = None
+
+_c_float_p = ctypes.c_void_p  # device or host address passed as an integer
+
+# name -> (restype, argtypes); must list every symbol of include/macarons_b200.h
+SYMBOLS = {
+    "mac_version": (ctypes.c_int, []),
+    "mac_last_error": (ctypes.c_char_p, []),
+    "mac_built_for_sm": (ctypes.c_int, []),
+    "mac_launch_count": (ctypes.c_ulonglong, []),
+    "mac_host_release": (None, []),
+    "mac_covgain_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "mac_covgain_f32": (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "mac_visibility_f32": (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_void_p]),
+    "mac_covgain_host": (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int]),
+}
+
+
+class MacaronsB200Error(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.lib_path()
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises if the library has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise MacaronsB200Error(
+            "%s is missing: run `python -m macarons_b200.build` (needs nvcc). "
+            "macarons_b200 has no CPU or PyTorch fallback." % path)
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI and the header drifted apart
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _LIB = lib
+    return lib
+
+
+def check(rc):
+    """Turn a negative return code into an exception carrying mac_last_error()."""
+    if rc != 0:
+        msg = load().mac_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError("macarons_b200: " + msg)
+        raise MacaronsB200Error("macarons_b200 (code %d): %s" % (rc, msg))

@@ -1,0 +1,112 @@
+// C-ABI plumbing: version / error reporting / launch counter, and the host-buffer entry points.
+#include <atomic>
+#include <string.h>
+
+#include "mac_common.h"
+
+namespace mac {
+
+namespace {
+thread_local char g_error[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+struct HostCache {  // per-thread device staging for the *_host entry points
+    int device = -1;
+    void *buf = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+thread_local HostCache g_cache;
+}  // namespace
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count(int device)
+{
+    static int cached[64] = {0};
+    if (device < 0 || device >= 64) return 148;
+    if (cached[device] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+        cached[device] = n;
+    }
+    return cached[device];
+}
+
+}  // namespace mac
+
+extern "C" int mac_version(void) { return 100; /* 0.1.0 */ }
+
+extern "C" const char *mac_last_error(void) { return mac::g_error; }
+
+extern "C" int mac_built_for_sm(void) { return 100; }
+
+extern "C" unsigned long long mac_launch_count(void) { return mac::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" void mac_host_release(void)
+{
+    mac::HostCache &c = mac::g_cache;
+    if (c.buf) {
+        cudaSetDevice(c.device);
+        cudaFree(c.buf);
+    }
+    if (c.stream) cudaStreamDestroy(c.stream);
+    c = mac::HostCache();
+}
+
+extern "C" int mac_covgain_host(const float *pts, int pts_dim, const float *harmonics, const float *cams, float *out,
+                                int B, int P, int C, int cam_begin, int cam_end, int act, int device)
+{
+    using namespace mac;
+    MAC_REQUIRE(pts && harmonics && cams && out, "null host pointer");
+    MAC_REQUIRE(B > 0 && P > 0 && C > 0 && pts_dim >= 3, "bad shape B=%d P=%d C=%d pts_dim=%d", B, P, C, pts_dim);
+    MAC_REQUIRE(0 <= cam_begin && cam_begin <= cam_end && cam_end <= C, "bad camera range [%d, %d) for C=%d",
+                cam_begin, cam_end, C);
+    MAC_CUDA(cudaSetDevice(device));
+    HostCache &c = g_cache;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t n_pts = up(sizeof(float) * B * static_cast<size_t>(P) * pts_dim);
+    const size_t n_harm = up(sizeof(float) * B * static_cast<size_t>(P) * MAC_N_HARMONICS);
+    const size_t n_cams = up(sizeof(float) * B * static_cast<size_t>(C) * 3);
+    const size_t n_out = up(sizeof(float) * B * static_cast<size_t>(C));
+    const size_t n_ws = up(mac_covgain_workspace_bytes(B, C));
+    const size_t need = n_pts + n_harm + n_cams + n_out + n_ws;
+    if (c.device != device || c.bytes < need) {
+        mac_host_release();
+        MAC_CUDA(cudaSetDevice(device));
+        MAC_CUDA(cudaMalloc(&c.buf, need));
+        MAC_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        c.device = device;
+        c.bytes = need;
+    }
+    unsigned char *base = static_cast<unsigned char *>(c.buf);
+    float *d_pts = reinterpret_cast<float *>(base);
+    float *d_harm = reinterpret_cast<float *>(base + n_pts);
+    float *d_cams = reinterpret_cast<float *>(base + n_pts + n_harm);
+    float *d_out = reinterpret_cast<float *>(base + n_pts + n_harm + n_cams);
+    void *d_ws = base + n_pts + n_harm + n_cams + n_out;
+    MAC_CUDA(cudaMemsetAsync(d_ws, 0, n_ws, c.stream));
+    MAC_CUDA(cudaMemcpyAsync(d_pts, pts, sizeof(float) * B * static_cast<size_t>(P) * pts_dim, cudaMemcpyHostToDevice,
+                             c.stream));
+    MAC_CUDA(cudaMemcpyAsync(d_harm, harmonics, sizeof(float) * B * static_cast<size_t>(P) * MAC_N_HARMONICS,
+                             cudaMemcpyHostToDevice, c.stream));
+    MAC_CUDA(cudaMemcpyAsync(d_cams, cams, sizeof(float) * B * static_cast<size_t>(C) * 3, cudaMemcpyHostToDevice,
+                             c.stream));
+    const int rc = mac_covgain_f32(d_pts, pts_dim, d_harm, d_cams, d_out, B, P, C, cam_begin, cam_end, act, d_ws, n_ws,
+                                   c.stream);
+    if (rc != MAC_OK) return rc;
+    if (cam_end > cam_begin) {
+        MAC_CUDA(cudaMemcpy2DAsync(out + cam_begin, sizeof(float) * C, d_out + cam_begin, sizeof(float) * C,
+                                   sizeof(float) * (cam_end - cam_begin), B, cudaMemcpyDeviceToHost, c.stream));
+    }
+    MAC_CUDA(cudaStreamSynchronize(c.stream));
+    return MAC_OK;
+}

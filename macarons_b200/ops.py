@@ -1,0 +1,122 @@
+"""Tensor-level wrappers over the C ABI.  Inputs must be CUDA fp32 tensors; outputs and workspaces
+are allocated here with torch (the C side never allocates caller-visible memory) and kernels are
+enqueued on torch's current stream."""
+import torch
+
+from . import _lib
+
+ACT_RELU, ACT_SIGMOID = 0, 1
+N_HARMONICS = 64
+
+_workspaces = {}
+
+
+def _require_cuda_f32(name, t):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise _lib.MacaronsB200Error(
+            "%s is on %s: macarons_b200 runs on CUDA (sm_100a) only and has no CPU fallback" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (got %s)" % (name, t.dtype))
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(device, B, C):
+    stream = _stream_ptr(device)
+    key = (device.index, B, C, stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = _lib.load().mac_covgain_workspace_bytes(B, C)
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)  # zero-filled once; kernels keep it zeroed
+        _workspaces[key] = ws
+    return ws
+
+
+def _prep(pts, harmonics, X_cam):
+    _require_cuda_f32("pts", pts)
+    _require_cuda_f32("harmonics", harmonics)
+    _require_cuda_f32("X_cam", X_cam)
+    if pts.dim() != 3 or pts.shape[-1] < 3:
+        raise ValueError("pts must have shape (n_clouds, seq_len, >=3), got %s" % (tuple(pts.shape),))
+    B, P, D = pts.shape
+    if tuple(harmonics.shape) != (B, P, N_HARMONICS):
+        raise ValueError("harmonics must have shape (%d, %d, %d), got %s" % (B, P, N_HARMONICS, tuple(harmonics.shape)))
+    if X_cam.dim() != 3 or X_cam.shape[0] != B or X_cam.shape[2] != 3:
+        raise ValueError("X_cam must have shape (%d, n_camera_candidates, 3), got %s" % (B, tuple(X_cam.shape)))
+    if not (pts.device == harmonics.device == X_cam.device):
+        raise ValueError("pts, harmonics and X_cam must be on the same device")
+    return pts.contiguous(), harmonics.contiguous(), X_cam.contiguous(), B, P, D, X_cam.shape[1]
+
+
+def coverage_gain(pts, harmonics, X_cam, use_sigmoid=True, cam_range=None, out=None):
+    """(B,P,>=3), (B,P,64), (B,C,3) -> (B,C) mean activated SH projection per camera.
+    `cam_range=(c0, c1)` scores only that slice of cameras (other columns of `out` untouched)."""
+    pts, harmonics, X_cam, B, P, D, C = _prep(pts, harmonics, X_cam)
+    c0, c1 = (0, C) if cam_range is None else (int(cam_range[0]), int(cam_range[1]))
+    if out is None:
+        out = (torch.empty if cam_range is None else torch.zeros)((B, C), dtype=torch.float32, device=pts.device)
+    else:
+        _require_cuda_f32("out", out)
+        if tuple(out.shape) != (B, C) or not out.is_contiguous():
+            raise ValueError("out must be a contiguous (%d, %d) tensor" % (B, C))
+    if P == 0 or C == 0:
+        return out
+    lib = _lib.load()
+    with torch.cuda.device(pts.device):
+        ws = _workspace(pts.device, B, C)
+        _lib.check(lib.mac_covgain_f32(pts.data_ptr(), D, harmonics.data_ptr(), X_cam.data_ptr(), out.data_ptr(),
+                                       B, P, C, c0, c1, ACT_SIGMOID if use_sigmoid else ACT_RELU,
+                                       ws.data_ptr(), ws.numel(), _stream_ptr(pts.device)))
+    return out
+
+
+def visibility_gains(pts, harmonics, X_cam, use_sigmoid=True, cam_range=None, out=None):
+    """Same inputs -> (B,C,P) per-point activated SH projection (no mean)."""
+    pts, harmonics, X_cam, B, P, D, C = _prep(pts, harmonics, X_cam)
+    c0, c1 = (0, C) if cam_range is None else (int(cam_range[0]), int(cam_range[1]))
+    if out is None:
+        out = (torch.empty if cam_range is None else torch.zeros)((B, C, P), dtype=torch.float32, device=pts.device)
+    else:
+        _require_cuda_f32("out", out)
+        if tuple(out.shape) != (B, C, P) or not out.is_contiguous():
+            raise ValueError("out must be a contiguous (%d, %d, %d) tensor" % (B, C, P))
+    if P == 0 or C == 0:
+        return out
+    lib = _lib.load()
+    with torch.cuda.device(pts.device):
+        _lib.check(lib.mac_visibility_f32(pts.data_ptr(), D, harmonics.data_ptr(), X_cam.data_ptr(), out.data_ptr(),
+                                          B, P, C, c0, c1, ACT_SIGMOID if use_sigmoid else ACT_RELU,
+                                          _stream_ptr(pts.device)))
+    return out
+
+
+def coverage_gain_host(pts, harmonics, X_cam, use_sigmoid=True, cam_range=None, device=0, out=None):
+    """Host-buffer entry point (numpy float32 arrays or CPU tensors in, numpy out): what a caller
+    without torch-on-GPU uses; copies are done inside the C call."""
+    import numpy as np
+
+    def as_np(x):
+        if isinstance(x, torch.Tensor):
+            x = x.numpy()
+        return np.ascontiguousarray(x, dtype=np.float32)
+
+    pts, harmonics, X_cam = as_np(pts), as_np(harmonics), as_np(X_cam)
+    B, P, D = pts.shape
+    C = X_cam.shape[1]
+    if harmonics.shape != (B, P, N_HARMONICS) or X_cam.shape != (B, C, 3):
+        raise ValueError("inconsistent shapes")
+    c0, c1 = (0, C) if cam_range is None else (int(cam_range[0]), int(cam_range[1]))
+    if out is None:
+        out = np.zeros((B, C), dtype=np.float32)
+    lib = _lib.load()
+    _lib.check(lib.mac_covgain_host(pts.ctypes.data, D, harmonics.ctypes.data, X_cam.ctypes.data, out.ctypes.data,
+                                    B, P, C, c0, c1, ACT_SIGMOID if use_sigmoid else ACT_RELU, int(device)))
+    return out
+
+
+def launch_count():
+    return int(_lib.load().mac_launch_count())

@@ -1,0 +1,142 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (Anttwo/MACARONS at /root/reference).
+
+Run in the build container only (the reference does not travel to the GPU box):
+    python tests/golden/make_golden.py
+For every case the reference's own function is executed on seeded inputs (tests/synth.py), the
+result is stored next to the inputs' seed + a checksum of the inputs, and the oracle (oracle/*.py)
+is asserted to reproduce the reference BIT FOR BIT on this machine.  The reference has no tests or
+golden vectors of its own, so these files are the pin.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+import synth  # noqa: E402
+from macarons.networks.SconeVis import SconeVis  # noqa: E402  (the reference's)
+from macarons.networks.Macarons import Macarons  # noqa: E402
+from macarons.utility import scone_utils as ref_su  # noqa: E402
+from oracle import sampling as o_sampling  # noqa: E402
+from oracle import sh_cov as o_cov  # noqa: E402
+from oracle import view_state as o_vs  # noqa: E402
+
+
+def digest(*tensors):
+    h = hashlib.sha256()
+    for t in tensors:
+        h.update(np.ascontiguousarray(t.numpy()).tobytes())
+    return h.hexdigest()[:16]
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: (v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
+                                 for k, v in arrays.items()})
+    print("wrote %-28s %7.1f KB" % (name + ".npz", os.path.getsize(path) / 1024))
+
+
+def must_equal(a, b, what):
+    if not torch.equal(a, b):
+        raise SystemExit("oracle != reference for %s (max diff %g)" % (what, (a - b).abs().max().item()))
+
+
+# (name, B, P, C, pts_dim, seed, coef_scale, use_sigmoid)
+COVGAIN_CASES = [
+    ("covgain_ragged_sigmoid", 2, 300, 7, 4, 101, 0.5, True),
+    ("covgain_cfg2_sigmoid", 1, 2048, 64, 4, 102, 0.5, True),
+    ("covgain_ragged_relu", 1, 257, 33, 3, 103, 0.5, False),
+    ("covgain_bigcoef_sigmoid", 3, 96, 130, 4, 104, 3.0, True),
+    ("covgain_single_cam", 1, 2048, 1, 4, 105, 1.0, True),
+]
+
+
+def covgain_goldens():
+    torch.manual_seed(5)
+    vis = SconeVis()
+    for name, B, P, C, D, seed, scale, sig in COVGAIN_CASES:
+        pts, harm, cams = synth.covgain_inputs(B, P, C, seed, pts_dim=D, coef_scale=scale)
+        vis.use_sigmoid = sig
+        cov = vis.compute_coverage_gain(pts, harm, cams)
+        per_point = vis.compute_visibilities(pts, harm, cams)
+        must_equal(cov, o_cov.coverage_gain(pts, harm, cams, use_sigmoid=sig), name + " coverage")
+        must_equal(per_point, o_cov.visibility_gains(pts, harm, cams, use_sigmoid=sig, cam_chunk=16), name + " vis")
+        if sig:  # Macarons.compute_visibility_gains is the same arithmetic behind another class
+            mac = Macarons(None, None, vis)
+            must_equal(mac.compute_visibility_gains(pts, harm, cams), per_point, name + " macarons")
+        save(name, B=B, P=P, C=C, pts_dim=D, seed=seed, coef_scale=scale, use_sigmoid=int(sig),
+             input_digest=digest(pts, harm, cams), coverage=cov, visibility=per_point.to(torch.float32),
+             argmax=np.argmax(cov.numpy(), axis=-1))
+    vis.use_sigmoid = True
+    # n-tuple coverage (tiny: C^n tuples)
+    pts, harm, cams = synth.covgain_inputs(1, 128, 5, 106)
+    for n_cam in (2, 3):
+        val, tuples = vis.compute_coverage_gain_multiple(pts, harm, cams, n_cam)
+        v2, t2 = o_cov.coverage_gain_multiple(pts, harm, cams, n_cam)
+        must_equal(val, v2, "coverage_gain_multiple")
+        must_equal(tuples, t2, "coverage_gain_multiple idx")
+        save("covgain_multiple_n%d" % n_cam, seed=106, B=1, P=128, C=5, n_cam=n_cam,
+             input_digest=digest(pts, harm, cams), coverage=val, tuples=tuples)
+
+
+def view_state_goldens():
+    base, h_polar, h_azim = ref_su.get_all_harmonics_under_degree(8, 7, 14, "cpu")
+    b2, hp2, ha2 = o_vs.bin_centre_harmonics(8, 7, 14)
+    must_equal(base, b2, "base harmonics")
+    must_equal(h_polar, hp2, "h_polar")
+    must_equal(h_azim, ha2, "h_azim")
+    save("view_base_harmonics", base=base, h_polar=h_polar, h_azim=h_azim)
+    for name, B, P, V, seed in (("view_state_small", 2, 500, 3, 201), ("view_state_10views", 1, 4096, 10, 202)):
+        pts, X_view = synth.view_state_inputs(B, P, V, seed)
+        if name == "view_state_small":
+            X_view[0] = torch.tensor([0.0, 1.5, 0.0])   # straight above: exercises the bin wrap-around
+            X_view[1] = torch.tensor([0.0, -1.5, 0.0])  # straight below
+        state = ref_su.compute_view_state(pts, X_view, 7, 14)
+        must_equal(state, o_vs.view_state(pts, X_view, 7, 14), name)
+        vh = ref_su.compute_view_harmonics(state, base, h_polar, h_azim, 7, 14)
+        must_equal(vh, o_vs.view_harmonics(state, base, h_polar, 7, 14, point_chunk=777), name + " harmonics")
+        save(name, B=B, P=P, V=V, seed=seed, X_view=X_view, input_digest=digest(pts, X_view),
+             state_bits=np.packbits(state.numpy().astype(np.uint8), axis=-1), view_harmonics=vh)
+
+
+def sampling_goldens():
+    gen = torch.Generator().manual_seed(301)
+    N = 20000
+    X = torch.rand(N, 3, generator=gen) - 0.5
+    preds = torch.rand(N, 1, generator=gen)
+    vh = torch.randn(N, 64, generator=gen)
+    u = torch.rand(2048, 1, generator=gen)
+    # drive the reference with the same uniforms through the global generator it reads
+    state = torch.get_rng_state()
+    torch.manual_seed(4242)
+    u_global = torch.rand(2048, 1)
+    torch.manual_seed(4242)
+    res, res_h, inv = ref_su.sample_proxy_points(X, preds, vh, 2048, 0.1, return_index=True)
+    torch.set_rng_state(state)
+    r2, h2, i2 = o_sampling.sample_proxy_points(X, preds, vh, 2048, 0.1, u=u_global)
+    must_equal(res, r2, "sampling points")
+    must_equal(res_h, h2, "sampling harmonics")
+    must_equal(inv, i2, "sampling inverse")
+    del u
+    save("sampling_20k", seed=301, N=N, n_sample=2048, min_occ=0.1, u=u_global, input_digest=digest(X, preds, vh),
+         res=res, inverse=inv, res_h_checksum=res_h.double().sum(dim=0))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    covgain_goldens()
+    view_state_goldens()
+    sampling_goldens()
+    print("all oracle == reference checks passed (bitwise)")

@@ -1,0 +1,123 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol the header declares,
+the product path refuses to run without CUDA (no fallback), and the generated change of basis used by
+the kernel is mathematically right (checked by compiling the same header for the host)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import sh_cov
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "macarons_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mac_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from macarons_b200 import _lib
+    lib = ctypes.CDLL(_lib.lib_path())
+    syms = _header_symbols()
+    assert len(syms) >= 9
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+    assert sorted(_lib.SYMBOLS) == syms, "ctypes table and header drifted apart"
+    handle = _lib.load()
+    assert handle.mac_version() >= 100 and handle.mac_built_for_sm() == 100
+    assert handle.mac_covgain_workspace_bytes(2, 64) >= 2 * 64 * 12
+
+
+def test_library_is_sm100a_only():
+    from macarons_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.lib_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_product_path_has_no_cpu_fallback():
+    from macarons_b200 import _lib, ops
+    from macarons_b200.networks.SconeVis import SconeVis
+    vis = SconeVis()
+    pts, harm, cams = torch.zeros(1, 8, 4), torch.zeros(1, 8, 64), torch.ones(1, 2, 3)
+    with pytest.raises(_lib.MacaronsB200Error):
+        vis.compute_coverage_gain(pts, harm, cams)
+    with pytest.raises(_lib.MacaronsB200Error):
+        ops.visibility_gains(pts, harm, cams)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "macarons_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src or f.endswith(".py") is False or "sys.path" not in src, f
+
+
+def test_state_dict_layout_matches_reference_contract():
+    """parameter names/shapes of SconeVis must let reference checkpoints load."""
+    from macarons_b200.networks.SconeVis import SconeVis
+    sd = SconeVis().state_dict()
+    want = {"embedding.linear1.weight": (126, 4), "embedding.linear2.weight": (126, 126),
+            "encoders.2.mhsa.w_q.weight": (64, 256), "encoders.0.mhsa.w_v.weight": (256, 256),
+            "encoders.1.mhsa.out.weight": (256, 256), "encoders.0.ff.linear1.weight": (512, 256),
+            "encoders.0.ff.linear2.weight": (256, 512), "norm.weight": (256,), "fc1.weight": (192, 256),
+            "fc2.weight": (128, 256), "fc3.weight": (64, 128), "fc3.bias": (64,)}
+    for k, shape in want.items():
+        assert tuple(sd[k].shape) == shape, k
+    assert sum(v.numel() for v in sd.values()) == 1392888
+
+
+HOST_HARNESS = r"""
+#include <cmath>
+#include <cstdio>
+#define __device__
+#define __forceinline__ inline
+#include "sh_horner_gen.h"
+int main() {
+    float h[64], g[64]; double d[3];
+    int n; if (scanf("%d", &n) != 1) return 1;
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 64; ++k) if (scanf("%f", &h[k]) != 1) return 1;
+        if (scanf("%lf %lf %lf", &d[0], &d[1], &d[2]) != 3) return 1;
+        mac_sh_pretransform(h, g, 1.0f);
+        double r = std::sqrt(d[0]*d[0] + d[1]*d[1] + d[2]*d[2]);
+        printf("%.9g\n", mac_sh_eval(g, (float)(d[0]/r), (float)(d[1]/r), (float)(d[2]/r)));
+    }
+    return 0;
+}
+"""
+
+
+def test_generated_change_of_basis_on_host(tmp_path):
+    """sum_k H_k Y_k(u) == Re sum_m (A_m(ct) - i B_m(ct)) (uz + i ux)^m with the generated constants."""
+    src = tmp_path / "harness.cpp"
+    src.write_text(HOST_HARNESS)
+    exe = tmp_path / "harness"
+    subprocess.check_call(["g++", "-O2", "-I", os.path.join(ROOT, "macarons_b200", "csrc"), str(src), "-o", str(exe)])
+    rng = np.random.default_rng(0)
+    n = 400
+    H = rng.normal(size=(n, 64)).astype(np.float32)
+    D = rng.normal(size=(n, 3))
+    D[:8, 0] = 0.0   # rays in the y-z plane (the reference's acos is ill-conditioned there; we are not)
+    D[8:12, [0, 2]] = 1e-4 * D[8:12][:, [0, 2]]   # nearly straight up/down
+    lines = ["%d" % n] + [" ".join("%.9g" % v for v in H[i]) + " %.17g %.17g %.17g" % tuple(D[i]) for i in range(n)]
+    out = subprocess.run([str(exe)], input="\n".join(lines), capture_output=True, text=True, check=True).stdout
+    got = np.array([float(x) for x in out.split()])
+    want = np.sum(sh_cov.sh_basis_closed_form_f64(D) * H.astype(np.float64), axis=-1)
+    assert np.abs(got - want).max() < 3e-5, np.abs(got - want).max()
+
+
+def test_generated_header_is_current():
+    path = os.path.join(ROOT, "macarons_b200", "csrc", "sh_horner_gen.h")
+    before = open(path).read()
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_sh_tables.py")], stdout=subprocess.DEVNULL)
+    assert open(path).read() == before
