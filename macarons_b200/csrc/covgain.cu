@@ -4,9 +4,10 @@
 // Macarons.compute_visibility_gains (reference networks/SconeVis.py:164-252, Macarons.py:138-178).
 //
 // Design (sm_100a, CUDA cores; see DESIGN.md section "coverage-gain kernel"):
-//   * one surface point per lane.  Its 64 SH coefficients are staged global -> shared with the bulk
-//     async-copy engine (one 256-B cp.async.bulk per lane into a padded row, mbarrier completion),
-//     pulled into registers with 16 conflict-free LDS.128 and converted ONCE to 64 "Horner-ready"
+//   * one surface point per lane.  The 32 x 64 coefficient tile of a warp is staged global -> shared by
+//     TMA (two 32-row x 128-B boxes of a 3-D tensor map over (64, P, B), SWIZZLE_128B, mbarrier
+//     completion; rows past P are zero-filled by the hardware), pulled into registers with 16
+//     conflict-free LDS.128 (the swizzle un-does the 128-B row stride) and converted ONCE to 64 "Horner-ready"
 //     coefficients (sh_horner_gen.h): the SH sum becomes Re sum_m (A_m(ct) - i B_m(ct)) (uz + i ux)^m
 //     with u the unit ray, i.e. 49 + 26 FMAs per (point, camera) pair and no trigonometry.
 //   * the warp then sweeps a chunk of cameras (broadcast LDS.128 from a per-warp table).  Per-pair
@@ -16,6 +17,9 @@
 //     (task, camera); integer addition is associative, so the result is bitwise independent of
 //     scheduling, launch geometry and of how cameras are partitioned across GPUs.  The last CTA to
 //     finish converts the accumulators to the fp32 mean and re-zeroes the workspace.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "mac_common.h"
 #include "sh_horner_gen.h"
 
@@ -23,9 +27,7 @@ namespace mac {
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
-constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kRowFloats = 68;     // 64 coefficients + 4 pad: rows 272 B apart -> LDS.128 conflict-free
+constexpr int kBoxBytes = 32 * 128;  // one TMA box: 32 points x 32 coefficients (128 B, the SWIZZLE_128B span)
 constexpr int kRedStride = 36;     // transpose buffer row stride (floats)
 constexpr int kCamChunkMax = 128;  // cameras per warp task
 
@@ -33,15 +35,14 @@ constexpr float kNegLog2e = -1.4426950408889634f;
 constexpr float kFixSigmoid = 4294967296.0f;  // 2^32: sums of sigmoid values, |s| <= 32 * tiles_per_task
 constexpr float kFixRelu = 16777216.0f;       // 2^24: sums of relu values (unbounded inputs)
 
-struct __align__(128) WarpSmem {
-    float stage[32 * kRowFloats];  // bulk-copy landing zone; re-used as the 32x36 transpose buffer
-    float4 cams[kCamChunkMax];
+struct __align__(1024) WarpSmem {
+    float stage[2 * kBoxBytes / 4];  // TMA landing zone (coefficients 0-31 | 32-63); re-used as the 32x36 transpose buffer
+    float4 cams[kCamChunkMax + 2];  // +2: the pipelined sweep normalises one pair ahead
     float wacc[kCamChunkMax];
     uint64_t bar;
-    uint64_t pad_[15];
 };
-static_assert(sizeof(WarpSmem) % 128 == 0, "per-warp shared block must keep 128-B alignment");
-static_assert(32 * kRedStride <= 32 * kRowFloats, "transpose buffer must fit in the staging rows");
+static_assert(sizeof(WarpSmem) % 1024 == 0, "SWIZZLE_128B boxes need 1024-B aligned shared memory");
+static_assert(32 * kRedStride * 4 <= 2 * kBoxBytes, "transpose buffer must fit in the staging area");
 
 struct CovgainParams {
     const float *pts;
@@ -62,24 +63,68 @@ struct CovgainParams {
     int total_tasks;           // B * runs_per_cloud * n_cam_chunks
 };
 
-template <bool SIGMOID>
-__device__ __forceinline__ float pair_value(const float (&g)[64], float px, float py, float pz, float4 cam)
+struct Ray {
+    float ux, ct, uz;  // unit vector from the surface point to the camera: (x, y, z) / r
+};
+
+__device__ __forceinline__ Ray make_ray(const float4 cam, const float px, const float py, const float pz)
 {
     const float dx = cam.x - px, dy = cam.y - py, dz = cam.z - pz;
-    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    const float rinv = rsqrt_approx(r2);
-    const float z = mac_sh_eval(g, dx * rinv, dy * rinv, dz * rinv);
-    if (SIGMOID) {
-        // g was pre-scaled by -log2(e): z = -x*log2(e), sigmoid(x) = 1 / (1 + 2^z)
-        return rcp_approx(1.0f + ex2_approx(z));
-    }
-    return fmaxf(z, 0.0f);
+    const float rinv = rsqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    return Ray{dx * rinv, dy * rinv, dz * rinv};
 }
 
-template <bool SIGMOID, bool REDUCE>
-__global__ void __launch_bounds__(kThreads, 2) covgain_kernel(const CovgainParams prm)
+template <bool PACKED, int NG, int NG0, int NGP>
+__device__ __forceinline__ void load_coefficients(const float (&h)[64], float (&g)[NG], float (&g0)[NG0],
+                                                  unsigned long long (&gp)[NGP], const float scale)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if constexpr (PACKED) mac_sh_pretransform_packed(h, g0, gp, scale);
+    else mac_sh_pretransform(h, g, scale);
+}
+template <bool PACKED, int NG, int NG0, int NGP>
+__device__ __forceinline__ void eval_two_rays(const float (&g)[NG], const float (&g0)[NG0],
+                                              const unsigned long long (&gp)[NGP], const Ray a, const Ray b, float &za,
+                                              float &zb)
+{
+    if constexpr (PACKED) mac_sh_eval2_packed(g0, gp, a.ux, a.ct, a.uz, b.ux, b.ct, b.uz, za, zb);
+    else mac_sh_eval2(g, a.ux, a.ct, a.uz, b.ux, b.ct, b.uz, za, zb);
+}
+
+// The activation is split so that its two MUFU results are consumed one loop iteration apart.
+// Sigmoid: g was pre-scaled by -log2(e), so z = -x*log2(e) and sigmoid(x) = 1 / (1 + 2^z).
+template <bool SIGMOID>
+__device__ __forceinline__ float activation_start(const float z)
+{
+    return SIGMOID ? ex2_approx(z) : fmaxf(z, 0.0f);
+}
+template <bool SIGMOID>
+__device__ __forceinline__ float activation_finish(const float e)
+{
+    return SIGMOID ? rcp_approx(1.0f + e) : e;
+}
+
+// Sum over the 32 points of a tile for the 32 cameras of one batch: lane j adds up row j of the transpose
+// buffer (8 conflict-free LDS.128) and accumulates into the per-warp, per-camera partial sum.
+__device__ __forceinline__ void reduce_batch(const float *red, float *wacc, const int cb, const int lane)
+{
+    __syncwarp();
+    const float4 *r4 = reinterpret_cast<const float4 *>(&red[lane * kRedStride]);
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 v = r4[q];
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    wacc[cb + lane] += s;  // lane j owns camera cb + j
+    __syncwarp();
+}
+
+// WARPS x MINB = resident warps per SM (register budget 65536 / (32 * WARPS * MINB)); PACKED selects the
+// fma.rn.f32x2 evaluator.
+template <bool SIGMOID, bool REDUCE, bool PACKED, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const CovgainParams prm, const __grid_constant__ CUtensorMap harm_map)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     WarpSmem &ws = reinterpret_cast<WarpSmem *>(smem_raw)[warp];
@@ -91,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 2) covgain_kernel(const CovgainParam
     }
     __syncwarp();
 
-    const int task = blockIdx.x * kWarpsPerCta + warp;
+    const int task = blockIdx.x * WARPS + warp;
     if (task < prm.total_tasks) {
         // task -> (cloud, run of point tiles, camera chunk); camera chunk fastest so that the warps of
         // one CTA share their coefficient rows through L1/L2.
@@ -103,14 +148,14 @@ __global__ void __launch_bounds__(kThreads, 2) covgain_kernel(const CovgainParam
         const int ncam = min(prm.cams_per_task, prm.cam_end - cam0);
         const int ncam32 = (ncam + 31) & ~31;
 
-        for (int j = lane; j < ncam32; j += 32) {
+        for (int j = lane; j < ncam32 + 2; j += 32) {
             float4 c = make_float4(0.f, 0.f, 1048576.f, 0.f);  // padding camera: finite, result discarded
             if (j < ncam) {
                 const float *src = prm.cams + (static_cast<size_t>(b) * prm.C + cam0 + j) * 3;
                 c = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), 0.f);
             }
             ws.cams[j] = c;
-            ws.wacc[j] = 0.f;
+            if (j < ncam32) ws.wacc[j] = 0.f;
         }
 
         uint32_t parity = 0;
@@ -123,13 +168,14 @@ __global__ void __launch_bounds__(kThreads, 2) covgain_kernel(const CovgainParam
             // ---- stage this tile's coefficient rows (async proxy), fetch the point meanwhile ----
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(&ws.bar, static_cast<uint32_t>(nvalid) * 256u);
-            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&ws.bar, 2u * kBoxBytes);
+                tma_load_3d(&ws.stage[0], &harm_map, 0, tile * 32, b, &ws.bar);
+                tma_load_3d(&ws.stage[kBoxBytes / 4], &harm_map, 32, tile * 32, b, &ws.bar);
+            }
             float px = 0.f, py = 0.f, pz = 0.f;
             if (valid) {
-                const size_t row = static_cast<size_t>(b) * prm.P + p;
-                bulk_g2s(&ws.stage[lane * kRowFloats], prm.harm + row * MAC_N_HARMONICS, 256u, &ws.bar);
-                const float *pp = prm.pts + row * prm.pts_dim;
+                const float *pp = prm.pts + (static_cast<size_t>(b) * prm.P + p) * prm.pts_dim;
                 px = __ldg(pp);
                 py = __ldg(pp + 1);
                 pz = __ldg(pp + 2);
@@ -137,19 +183,23 @@ __global__ void __launch_bounds__(kThreads, 2) covgain_kernel(const CovgainParam
             mbar_wait(&ws.bar, parity);
             parity ^= 1u;
 
-            float g[64];
+            float g[PACKED ? 1 : 64];
+            float g0[PACKED ? 8 : 1];
+            unsigned long long gp[PACKED ? 28 : 1];
             {
+                // element (row r, 16-B chunk c) of a SWIZZLE_128B box sits at r*128 + ((c ^ (r & 7)) << 4)
                 float h[64];
-                const float4 *row4 = reinterpret_cast<const float4 *>(&ws.stage[lane * kRowFloats]);
+                const unsigned char *row = reinterpret_cast<const unsigned char *>(ws.stage) + lane * 128;
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                    const float4 v = valid ? row4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 v = *reinterpret_cast<const float4 *>(row + (q >> 3) * kBoxBytes +
+                                                                       (((q & 7) ^ (lane & 7)) << 4));
                     h[4 * q + 0] = v.x;
                     h[4 * q + 1] = v.y;
                     h[4 * q + 2] = v.z;
                     h[4 * q + 3] = v.w;
                 }
-                mac_sh_pretransform(h, g, SIGMOID ? kNegLog2e : 1.0f);
+                load_coefficients<PACKED>(h, g, g0, gp, SIGMOID ? kNegLog2e : 1.0f);
             }
             __syncwarp();  // every lane has its row in registers: the staging rows become `red`
 
@@ -158,27 +208,52 @@ __global__ void __launch_bounds__(kThreads, 2) covgain_kernel(const CovgainParam
                 __syncwarp();
             }
 
-            for (int cb = 0; cb < ncam32; cb += 32) {
-#pragma unroll 2
-                for (int j = 0; j < 32; ++j) {
-                    const float v = pair_value<SIGMOID>(g, px, py, pz, ws.cams[cb + j]);
-                    if (REDUCE) {
-                        if (valid) red[j * kRedStride + lane] = v;
-                    } else if (valid && cb + j < ncam) {
-                        prm.out[(static_cast<size_t>(b) * prm.C + cam0 + cb + j) * prm.P + p] = v;
-                    }
-                }
+            // ---- camera sweep, two rays per iteration, software-pipelined by hand: iteration jj evaluates
+            // pair jj (rays normalised in iteration jj-1), finishes the activation of pair jj-1 (its ex2 was
+            // issued in iteration jj-1) and normalises the rays of pair jj+1, so that no LDS / MUFU result
+            // is consumed in the iteration that produced it.
+            Ray rA = make_ray(ws.cams[0], px, py, pz), rB = make_ray(ws.cams[1], px, py, pz);
+            float eA = 0.f, eB = 0.f;
+            const int npairs = ncam32 >> 1;
+#pragma unroll 1
+            for (int jj = 0; jj < npairs; ++jj) {
+                const float4 nA = ws.cams[2 * jj + 2], nB = ws.cams[2 * jj + 3];  // table has 2 pad entries
+                const Ray qA = make_ray(nA, px, py, pz), qB = make_ray(nB, px, py, pz);
+                float zA, zB;
+                eval_two_rays<PACKED>(g, g0, gp, rA, rB, zA, zB);
+                const float vA = activation_finish<SIGMOID>(eA), vB = activation_finish<SIGMOID>(eB);
+                // camera (within the chunk) of the pair being finished; at jj == 0 there is none: c = -2 and the
+                // value lands in rows 30/31 of the transpose buffer, which are rewritten before they are summed.
+                const int c = 2 * jj - 2;
                 if (REDUCE) {
-                    __syncwarp();
-                    const float4 *r4 = reinterpret_cast<const float4 *>(&red[lane * kRedStride]);
-                    float s = 0.f;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 v = r4[q];
-                        s += (v.x + v.y) + (v.z + v.w);
+                    if (valid) {
+                        red[(c & 31) * kRedStride + lane] = vA;
+                        red[((c & 31) + 1) * kRedStride + lane] = vB;
                     }
-                    ws.wacc[cb + lane] += s;  // lane j owns camera cb + j
-                    __syncwarp();
+                } else if (valid) {
+                    float *o = prm.out + (static_cast<size_t>(b) * prm.C + cam0 + c) * prm.P + p;
+                    if (c >= 0 && c < ncam) o[0] = vA;
+                    if (c >= 0 && c + 1 < ncam) o[prm.P] = vB;
+                }
+                eA = activation_start<SIGMOID>(zA);
+                eB = activation_start<SIGMOID>(zB);
+                rA = qA;
+                rB = qB;
+                if (REDUCE && (jj & 15) == 0 && jj > 0) reduce_batch(red, ws.wacc, c & ~31, lane);
+            }
+            {
+                const float vA = activation_finish<SIGMOID>(eA), vB = activation_finish<SIGMOID>(eB);
+                const int c = ncam32 - 2;
+                if (REDUCE) {
+                    if (valid) {
+                        red[(c & 31) * kRedStride + lane] = vA;
+                        red[((c & 31) + 1) * kRedStride + lane] = vB;
+                    }
+                    reduce_batch(red, ws.wacc, c & ~31, lane);
+                } else if (valid) {
+                    float *o = prm.out + (static_cast<size_t>(b) * prm.C + cam0 + c) * prm.P + p;
+                    if (c < ncam) o[0] = vA;
+                    if (c + 1 < ncam) o[prm.P] = vB;
                 }
             }
         }
@@ -210,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 2) covgain_kernel(const CovgainParam
             __threadfence();
             const int nloc = prm.cam_end - prm.cam_begin;
             const double unfix = 1.0 / static_cast<double>(SIGMOID ? kFixSigmoid : kFixRelu);
-            for (int i = threadIdx.x; i < prm.B * nloc; i += kThreads) {
+            for (int i = threadIdx.x; i < prm.B * nloc; i += WARPS * 32) {
                 const size_t idx = static_cast<size_t>(i / nloc) * prm.C + prm.cam_begin + (i % nloc);
                 const long long q = static_cast<long long>(atomicExch(prm.acc + idx, 0ull));
                 const unsigned int bad = atomicExch(prm.flags + idx, 0u);
@@ -223,6 +298,39 @@ __global__ void __launch_bounds__(kThreads, 2) covgain_kernel(const CovgainParam
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// 3-D tensor map over the harmonics (fastest first: 64 coefficients, P points, B clouds); box = 32 coefficients
+// (128 B) x 32 points, SWIZZLE_128B.  Out-of-range points of the last tile of a cloud are zero-filled.
+int make_harmonics_map(CUtensorMap *map, const float *harm, int B, int P)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MAC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return MAC_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[3] = {MAC_N_HARMONICS, static_cast<cuuint64_t>(P), static_cast<cuuint64_t>(B)};
+    const cuuint64_t strides[2] = {MAC_N_HARMONICS * sizeof(float),
+                                   static_cast<cuuint64_t>(P) * MAC_N_HARMONICS * sizeof(float)};
+    const cuuint32_t box[3] = {32, 32, 1};
+    const cuuint32_t elem[3] = {1, 1, 1};
+    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(harm), dims, strides, box,
+                               elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(rc));
+        return MAC_ERR_CUDA;
+    }
+    return MAC_OK;
+}
 
 int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *harm, const float *cams, float *out,
                     int B, int P, int C, int cam_begin, int cam_end, int act, void *workspace,
@@ -263,9 +371,22 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
         prm.done = reinterpret_cast<unsigned int *>(w);
     }
 
+    CUtensorMap harm_map;
+    if (int rc = make_harmonics_map(&harm_map, harm, B, P)) return rc;
+
     int device = 0;
     MAC_CUDA(cudaGetDevice(&device));
-    const long long slots = static_cast<long long>(sm_count(device)) * 2 * kWarpsPerCta;  // resident warps
+    // MAC_COVGAIN_VARIANT=1 selects the scalar-FFMA evaluator (ablation knob for tools/bench_covgain.py);
+    // default 0 = packed fma.rn.f32x2 Horner steps.
+    static const int variant = [] {
+        const char *e = getenv("MAC_COVGAIN_VARIANT");
+        return e ? atoi(e) : 0;
+    }();
+    // 8 warps x 2 CTAs/SM (128 registers) measured fastest; 12 x 1 (168 regs) and 16 x 1 were 9-11 % slower
+    // (profiles/r01_covgain.md).
+    const int warps_per_cta = 8;
+    const int ctas_per_sm = 2;
+    const long long slots = static_cast<long long>(sm_count(device)) * ctas_per_sm * warps_per_cta;  // resident warps
     const int n_local = cam_end - cam_begin;
     prm.tiles_per_cloud = (P + 31) / 32;
     // Camera chunk per warp task: as large as possible (amortises the per-tile load + change of basis)
@@ -287,22 +408,29 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
     prm.tiles_per_task = static_cast<int>(tpt);
     prm.runs_per_cloud = (prm.tiles_per_cloud + prm.tiles_per_task - 1) / prm.tiles_per_task;
     const long long total = static_cast<long long>(B) * prm.runs_per_cloud * prm.n_cam_chunks;
-    MAC_REQUIRE(total < (1ll << 31) - kWarpsPerCta, "problem too large for one launch (%lld tasks)", total);
+    MAC_REQUIRE(total < (1ll << 31) - 64, "problem too large for one launch (%lld tasks)", total);
     prm.total_tasks = static_cast<int>(total);
 
-    const dim3 grid(static_cast<unsigned>((total + kWarpsPerCta - 1) / kWarpsPerCta));
-    const size_t smem = sizeof(WarpSmem) * kWarpsPerCta;
+    const dim3 grid(static_cast<unsigned>((total + warps_per_cta - 1) / warps_per_cta));
+    const size_t smem = sizeof(WarpSmem) * warps_per_cta;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-#define MAC_LAUNCH(SIG, RED)                                                                                      \
+#define MAC_LAUNCH_V(SIG, RED, PACKED, WARPS, MINB)                                                              \
     do {                                                                                                          \
         static bool attr_done = false;                                                                            \
         if (!attr_done) {                                                                                         \
-            MAC_CUDA(cudaFuncSetAttribute(covgain_kernel<SIG, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                          static_cast<int>(smem)));                                               \
+            MAC_CUDA(cudaFuncSetAttribute(covgain_kernel<SIG, RED, PACKED, WARPS, MINB>,                          \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
             attr_done = true;                                                                                     \
         }                                                                                                         \
-        covgain_kernel<SIG, RED><<<grid, kThreads, smem, st>>>(prm);                                              \
+        covgain_kernel<SIG, RED, PACKED, WARPS, MINB><<<grid, WARPS * 32, smem, st>>>(prm, harm_map);             \
+    } while (0)
+#define MAC_LAUNCH(SIG, RED)                                       \
+    do {                                                           \
+        switch (variant) {                                         \
+        case 1: MAC_LAUNCH_V(SIG, RED, false, 8, 2); break;        \
+        default: MAC_LAUNCH_V(SIG, RED, true, 8, 2); break;        \
+        }                                                          \
     } while (0)
 
     if (reduce) {
@@ -312,6 +440,7 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
         if (act == MAC_ACT_SIGMOID) MAC_LAUNCH(true, false);
         else MAC_LAUNCH(false, false);
     }
+#undef MAC_LAUNCH_V
 #undef MAC_LAUNCH
     MAC_CUDA(cudaGetLastError());
     count_launch();

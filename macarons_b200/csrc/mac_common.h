@@ -77,6 +77,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// TMA tiled load of one box of a 3-D tensor map (SASS UTMALDG); coordinates fastest dimension first
+__device__ __forceinline__ void tma_load_3d(void *dst_smem, const void *tensor_map, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tensor_map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ float rsqrt_approx(float x)
 {
     float y;

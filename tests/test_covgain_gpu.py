@@ -98,8 +98,11 @@ def test_edge_shapes_against_oracle(B, P, C, D, cuda_device):
     pts, harm, cams = synth.covgain_inputs(B, P, C, seed=1000 + P + C, pts_dim=D)
     got = ops.coverage_gain(pts.to(cuda_device), harm.to(cuda_device), cams.to(cuda_device)).cpu()
     want = sh_cov.coverage_gain(pts, harm, cams, cam_chunk=32)
-    assert (got - want).abs().max().item() <= COVERAGE_ATOL
-    assert torch.equal(got.argmax(-1), want.argmax(-1))
+    # the reference's own ill-conditioned rays (tolerances.py) are not averaged away when P is small
+    assert (got - want).abs().max().item() <= COVERAGE_ATOL + 2e-3 / P
+    truth = sh_cov.coverage_gain_f64(pts.numpy(), harm.numpy(), cams.numpy())
+    assert np.abs(got.numpy() - truth).max() <= 2e-6
+    assert np.array_equal(got.numpy().argmax(-1), truth.argmax(-1))
     per_point = ops.visibility_gains(pts.to(cuda_device), harm.to(cuda_device), cams.to(cuda_device))
     assert (per_point.mean(-1).cpu() - got).abs().max().item() <= 1e-6
 
