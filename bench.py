@@ -31,7 +31,8 @@ WORKLOADS = {
 METRIC = "coverage_gain_evals_per_sec"
 UNIT = "evals/s"
 N_INPUT_SETS = 5          # distinct resident input sets rotated between steps (5 x 54.6 MB > 126 MB L2)
-INSTR_PER_PAIR = 94.3     # SASS count of the covgain inner loop (profiles/r01_covgain_sass.md)
+FMA_CYCLES_PER_PAIR = 85.0  # FMA-pipe issue cycles per (point, camera) pair: 35 FFMA + 21 FFMA2 x 2 + 8 FADD/FMUL
+                            # (SASS of the sweep loop, profiles/r01_covgain.md); 1 per cycle per SM sub-partition
 
 
 def load_peaks():
@@ -43,47 +44,60 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU through NVML every ~2 ms while the timed region
+    runs (nvidia-smi's own polling loop is too coarse for a region of a few tens of milliseconds)."""
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
         self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv, h = self._nv, self._h
+        while not self._stop.is_set():
+            try:
+                self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h), nv.nvmlDeviceGetPowerUsage(h) / 1e3))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+        if self._h is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
 
     def stop(self, t_begin, t_end):
-        if self.proc is None:
+        if self._thread is None:
             return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t_begin <= t <= t_end + 0.1 and len(r) >= 7] or [r for _, r in self.rows[-3:]]
+        self._stop.set()
+        self._thread.join(timeout=1.0)
+        nv = self._nv
+        rows = [r for r in self.rows if t_begin <= r[0] <= t_end] or self.rows[-3:]
         if not rows:
             return None
-        def num(x):
-            try:
-                return float(x)
-            except ValueError:
-                return float("nan")
-        sm = [num(r[0]) for r in rows]
-        reasons = [n for i, n in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"),
-                                  (6, "sw_power_cap")) if any(r[i].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": num(rows[0][1]), "reasons": reasons,
-                "samples": len(rows), "power_w_max": max(num(r[2]) for r in rows)}
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"),
+                 ("hw_power_brake", "nvmlClocksEventReasonHwPowerBrakeSlowdown"))
+        reasons = [n for n, attr in names if bits & getattr(nv, attr, 0)]
+        try:
+            sm_max = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        except Exception:
+            sm_max = None
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": sm_max, "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(r[3] for r in rows), "source": "NVML, 2 ms period"}
 
 
 def make_inputs(cfg, n_sets):
@@ -181,9 +195,18 @@ def run_ours(args, cfg):
     pinned = [(p.pin_memory(), h.pin_memory()) for p, h in host_sets[:2]]
     cams_pin = cams_h.pin_memory()
     local = torch.zeros(B, C, device=dev)
+    board, exchange = None, "nccl all_gather + torch.argmax"
+    if not args.nccl_gather:
+        try:
+            board = parallel.PeerScoreBoard(B, C, dev)
+            exchange = "fused: scores pushed to every peer's board from the scoring kernel (NVLink P2P), 1 wait+argmax kernel"
+        except Exception as exc:  # symmetric memory unavailable: fall back to the NCCL collective
+            exchange += " (peer board unavailable: %s)" % type(exc).__name__
 
     def step(i, ev=None):
         pts, harm = dev_sets[i % N_INPUT_SETS]
+        if board is not None:
+            return board.step(pts, harm, cams, use_sigmoid=vis.use_sigmoid, events=ev)
         if ev is not None:
             ev[0].record()
         ops.coverage_gain(pts, harm, cams, use_sigmoid=vis.use_sigmoid, cam_range=(c0, c1), out=local)
@@ -204,7 +227,7 @@ def run_ours(args, cfg):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.02)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = ops.launch_count()
@@ -235,7 +258,10 @@ def run_ours(args, cfg):
         pts = p_h.to(dev, non_blocking=True)
         harm = h_h.to(dev, non_blocking=True)
         cam_d = cams_pin.to(dev, non_blocking=True)
-        s, b = parallel.sharded_coverage_gain(vis.compute_coverage_gain, pts, harm, cam_d)
+        if board is not None:
+            s, b = board.step(pts, harm, cam_d, use_sigmoid=vis.use_sigmoid)
+        else:
+            s, b = parallel.sharded_coverage_gain(vis.compute_coverage_gain, pts, harm, cam_d)
         return s.cpu(), b.cpu()
 
     for i in range(2):
@@ -258,6 +284,8 @@ def run_ours(args, cfg):
         from oracle import sh_cov
         pts_h, harm_h = host_sets[(args.warmup + args.steps - 1) % N_INPUT_SETS]
         got = scores.cpu().numpy()
+        if board is not None:
+            board.check()
         top = np.argsort(-got[0])[:4].tolist()
         truth = sh_cov.coverage_gain_f64(pts_h.numpy(), harm_h.numpy(), cams_h.numpy()[:, top])
         check = {"nbv_index": int(best[0]), "max_abs_err_vs_f64_top4": float(np.abs(got[:, top] - truth).max()),
@@ -269,8 +297,8 @@ def run_ours(args, cfg):
         alg_bytes = B * P * (4 * vis.pts_dim + 256) + B * n_local * 12 + B * n_local * 4
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-        issue_peak = 148 * 4 * sm_mhz * 1e6                    # warp instructions / s at the sampled clock
-        issue_rate = B * P * n_local * INSTR_PER_PAIR / 32 / (kernel_ms * 1e-3)
+        issue_peak = 148 * 4 * sm_mhz * 1e6                    # FMA-pipe warp-cycles / s at the sampled clock
+        issue_rate = B * P * n_local * FMA_CYCLES_PER_PAIR / 32 / (kernel_ms * 1e-3)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "covgain_traffic.json")
         if os.path.exists(tpath) and world == 1 and args.workload == "cfg5":
@@ -282,22 +310,24 @@ def run_ours(args, cfg):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": args.workload + ": " + cfg["desc"], "B": B, "P": P, "C": C,
                        "parallelism": "camera axis sharded x%d (points replicated), 1 all-gather of scores" % world,
+                       "exchange": exchange,
                        "cameras_per_gpu": n_local,
                        "l2": "inputs rotate over %d distinct resident sets (%.0f MB > 126 MB L2)"
                              % (N_INPUT_SETS, N_INPUT_SETS * B * P * 272 / 1e6)},
             "clocks": clocks,
             "e2e": {"value": B * C * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "api": "pinned host tensors -> SconeVis.compute_coverage_gain -> parallel.gather_scores -> argmax -> .cpu()"},
+                    "api": "pinned host tensors -> .to(device) -> scoring step (same as value) -> scores, argmax .cpu()"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                          "kernel": "covgain_kernel<sigmoid,reduce>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "kernel is fp32-issue bound at >= 8 cameras per point pass (DESIGN.md 4.3)",
-                         "fp32_issue": {"instr_per_pair": INSTR_PER_PAIR, "warp_instr_per_s": issue_rate,
-                                        "peak_warp_instr_per_s": issue_peak, "frac": issue_rate / issue_peak,
-                                        "sm_mhz": sm_mhz}},
+                         "note": "kernel is bound by the fp32 FMA pipe, not HBM, at >= 8 cameras per point pass "
+                                 "(DESIGN.md section 4); fp32_pipe is the binding roofline",
+                         "fp32_pipe": {"fma_cycles_per_pair": FMA_CYCLES_PER_PAIR, "warp_cycles_per_s": issue_rate,
+                                       "peak_warp_cycles_per_s": issue_peak, "frac": issue_rate / issue_peak,
+                                       "sm_mhz": sm_mhz}},
             "parity": check,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -315,6 +345,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true", help="use the NCCL all_gather instead of the fused peer push")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     cfg = WORKLOADS[args.workload]

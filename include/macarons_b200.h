@@ -89,6 +89,39 @@ int mac_covgain_host(const float *pts, int pts_dim, const float *harmonics, cons
                      int device);
 void mac_host_release(void);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused score all-gather over NVLink peer memory (multi-GPU, one process per GPU).
+ *
+ * Every rank owns a "score board" in peer-mapped device memory (e.g. torch symmetric memory):
+ *     scores  (B, C) fp32   the assembled score matrix
+ *     flags   (world) u32   flags[r] = last epoch for which rank r's columns have landed
+ * mac_covgain_push_f32 is mac_covgain_f32 whose finishing CTA, instead of (only) writing a local `out`,
+ * stores this rank's columns [cam_begin, cam_end) straight into the score board of EVERY rank (its own
+ * included) and then release-stores `epoch` into flags[rank] on every board: compute and exchange are one
+ * kernel, there is no separate collective.  `board->scores[r]` / `board->flags[r]` are the addresses of
+ * rank r's board as mapped into THIS process.  Epochs must increase by one per step; with two boards
+ * used alternately (even / odd epochs) a rank can never overwrite scores a peer is still reading.
+ *
+ * mac_gather_wait_argmax enqueues a one-CTA kernel that waits (acquire loads, bounded by ~2 s) until all
+ * `world` flags of the local board have reached `epoch`, then writes best[b] = index of the first maximum
+ * of scores[b, :] (NaN counts as maximal, like torch.argmax) and status[0] = 0, or status[0] = 1 on timeout.
+ * ------------------------------------------------------------------------------------------- */
+#define MAC_MAX_PEERS 16
+typedef struct mac_peer_board {
+    int world;
+    int rank;
+    unsigned int epoch;
+    float *scores[MAC_MAX_PEERS];
+    unsigned int *flags[MAC_MAX_PEERS];
+} mac_peer_board_t;
+
+int mac_covgain_push_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams, int B,
+                         int P, int C, int cam_begin, int cam_end, int act, void *workspace,
+                         size_t workspace_bytes, const mac_peer_board_t *board, void *stream);
+
+int mac_gather_wait_argmax(const float *scores, const unsigned int *flags, int world, unsigned int epoch,
+                           int B, int C, long long *best, int *status, void *stream);
+
 /* Number of kernel launches the library has enqueued since load (for bench.py's gpu_launches). */
 unsigned long long mac_launch_count(void);
 

@@ -61,6 +61,12 @@ struct CovgainParams {
     int tiles_per_task;
     int runs_per_cloud;        // ceil(tiles_per_cloud / tiles_per_task)
     int total_tasks;           // B * runs_per_cloud * n_cam_chunks
+    // fused all-gather (REDUCE only, push_world > 0): the finishing CTA stores this rank's score columns into the
+    // (B, C) score board of every peer over NVLink and then raises its arrival flag there.
+    int push_world, push_rank;
+    unsigned int push_epoch;
+    float *push_dst[MAC_MAX_PEERS];
+    unsigned int *push_flag[MAC_MAX_PEERS];
 };
 
 struct Ray {
@@ -290,7 +296,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
                 const long long q = static_cast<long long>(atomicExch(prm.acc + idx, 0ull));
                 const unsigned int bad = atomicExch(prm.flags + idx, 0u);
                 const float total = static_cast<float>(static_cast<double>(q) * unfix);
-                prm.out[idx] = bad ? __int_as_float(0x7fc00000) : __fdiv_rn(total, static_cast<float>(prm.P));
+                const float score = bad ? __int_as_float(0x7fc00000) : __fdiv_rn(total, static_cast<float>(prm.P));
+                if (prm.out) prm.out[idx] = score;
+                for (int r = 0; r < prm.push_world; ++r) prm.push_dst[r][idx] = score;  // peer-mapped stores
+            }
+            if (prm.push_world > 0) {
+                __threadfence_system();  // every thread: its score stores are visible system-wide ...
+                __syncthreads();
+                if (threadIdx.x < prm.push_world)  // ... before the arrival flag of this rank is
+                    st_release_sys(prm.push_flag[threadIdx.x] + prm.push_rank, prm.push_epoch);
             }
             if (threadIdx.x == 0) *prm.done = 0u;
         }
@@ -334,16 +348,23 @@ int make_harmonics_map(CUtensorMap *map, const float *harm, int B, int P)
 
 int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *harm, const float *cams, float *out,
                     int B, int P, int C, int cam_begin, int cam_end, int act, void *workspace,
-                    size_t workspace_bytes, void *stream)
+                    size_t workspace_bytes, void *stream, const mac_peer_board_t *board = nullptr)
 {
-    MAC_REQUIRE(pts && harm && cams && out, "null tensor pointer");
+    MAC_REQUIRE(pts && harm && cams && (out || board), "null tensor pointer");
+    if (board) {
+        MAC_REQUIRE(reduce, "score push needs the reducing kernel");
+        MAC_REQUIRE(board->world >= 1 && board->world <= MAC_MAX_PEERS && board->rank >= 0 && board->rank < board->world,
+                    "bad peer board: rank %d of %d (max %d peers)", board->rank, board->world, MAC_MAX_PEERS);
+        for (int r = 0; r < board->world; ++r)
+            MAC_REQUIRE(board->scores[r] && board->flags[r], "peer board pointer %d is null", r);
+    }
     MAC_REQUIRE(B > 0 && P > 0 && C > 0, "B, P, C must be positive (got %d, %d, %d)", B, P, C);
     MAC_REQUIRE(pts_dim >= 3, "pts_dim must be >= 3 (got %d)", pts_dim);
     MAC_REQUIRE(0 <= cam_begin && cam_begin <= cam_end && cam_end <= C, "bad camera range [%d, %d) for C=%d",
                 cam_begin, cam_end, C);
     MAC_REQUIRE(act == MAC_ACT_RELU || act == MAC_ACT_SIGMOID, "act must be MAC_ACT_RELU or MAC_ACT_SIGMOID");
     MAC_REQUIRE((reinterpret_cast<uintptr_t>(harm) & 15u) == 0, "harmonics must be 16-byte aligned");
-    if (cam_begin == cam_end) return MAC_OK;
+    if (cam_begin == cam_end && !board) return MAC_OK;
 
     CovgainParams prm{};
     prm.pts = pts;
@@ -356,6 +377,15 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
     prm.C = C;
     prm.cam_begin = cam_begin;
     prm.cam_end = cam_end;
+    if (board) {
+        prm.push_world = board->world;
+        prm.push_rank = board->rank;
+        prm.push_epoch = board->epoch;
+        for (int r = 0; r < board->world; ++r) {
+            prm.push_dst[r] = board->scores[r];
+            prm.push_flag[r] = board->flags[r];
+        }
+    }
     if (reduce) {
         const size_t need = mac_covgain_workspace_bytes(B, C);
         if (!workspace || workspace_bytes < need) {
@@ -411,7 +441,7 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
     MAC_REQUIRE(total < (1ll << 31) - 64, "problem too large for one launch (%lld tasks)", total);
     prm.total_tasks = static_cast<int>(total);
 
-    const dim3 grid(static_cast<unsigned>((total + warps_per_cta - 1) / warps_per_cta));
+    const dim3 grid(static_cast<unsigned>(total > 0 ? (total + warps_per_cta - 1) / warps_per_cta : 1));
     const size_t smem = sizeof(WarpSmem) * warps_per_cta;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
@@ -470,4 +500,16 @@ extern "C" int mac_visibility_f32(const float *pts, int pts_dim, const float *ha
 {
     return mac::plan_and_launch(false, pts, pts_dim, harmonics, cams, out, B, P, C, cam_begin, cam_end, act, nullptr,
                                 0, stream);
+}
+
+extern "C" int mac_covgain_push_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams, int B,
+                                    int P, int C, int cam_begin, int cam_end, int act, void *workspace,
+                                    size_t workspace_bytes, const mac_peer_board_t *board, void *stream)
+{
+    if (!board) {
+        mac::set_error("mac_covgain_push_f32 needs a peer board");
+        return MAC_ERR_INVALID_ARGUMENT;
+    }
+    return mac::plan_and_launch(true, pts, pts_dim, harmonics, cams, nullptr, B, P, C, cam_begin, cam_end, act,
+                                workspace, workspace_bytes, stream, board);
 }

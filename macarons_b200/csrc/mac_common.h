@@ -86,6 +86,17 @@ __device__ __forceinline__ void tma_load_3d(void *dst_smem, const void *tensor_m
         "l"(tensor_map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
 }
+// system-scope release store / acquire load: flags that live in (possibly peer) device memory
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ float rsqrt_approx(float x)
 {
     float y;

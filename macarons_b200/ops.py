@@ -94,6 +94,34 @@ def visibility_gains(pts, harmonics, X_cam, use_sigmoid=True, cam_range=None, ou
     return out
 
 
+def coverage_gain_push(pts, harmonics, X_cam, use_sigmoid, cam_range, score_ptrs, flag_ptrs, rank, epoch):
+    """Score cameras [c0, c1) and store them, from inside the kernel, into the (B, C) score board of every
+    rank (`score_ptrs[r]`, `flag_ptrs[r]`: rank r's board as mapped into this process), then raise this rank's
+    arrival flag (= epoch) on every board.  See include/macarons_b200.h, "Fused score all-gather"."""
+    pts, harmonics, X_cam, B, P, D, C = _prep(pts, harmonics, X_cam)
+    board = _lib.PeerBoard()
+    board.world, board.rank, board.epoch = len(score_ptrs), int(rank), int(epoch) & 0xFFFFFFFF
+    for r, (sp, fp) in enumerate(zip(score_ptrs, flag_ptrs)):
+        board.scores[r] = sp
+        board.flags[r] = fp
+    lib = _lib.load()
+    with torch.cuda.device(pts.device):
+        ws = _workspace(pts.device, B, C)
+        _lib.check(lib.mac_covgain_push_f32(pts.data_ptr(), D, harmonics.data_ptr(), X_cam.data_ptr(), B, P, C,
+                                            int(cam_range[0]), int(cam_range[1]),
+                                            ACT_SIGMOID if use_sigmoid else ACT_RELU, ws.data_ptr(), ws.numel(),
+                                            board, _stream_ptr(pts.device)))
+
+
+def gather_wait_argmax(scores, flags, world, epoch, best, status):
+    """Enqueue the wait-for-all-ranks + argmax kernel on the local score board."""
+    B, C = scores.shape
+    lib = _lib.load()
+    with torch.cuda.device(scores.device):
+        _lib.check(lib.mac_gather_wait_argmax(scores.data_ptr(), flags.data_ptr(), int(world), int(epoch) & 0xFFFFFFFF,
+                                              B, C, best.data_ptr(), status.data_ptr(), _stream_ptr(scores.device)))
+
+
 def coverage_gain_host(pts, harmonics, X_cam, use_sigmoid=True, cam_range=None, device=0, out=None):
     """Host-buffer entry point (numpy float32 arrays or CPU tensors in, numpy out): what a caller
     without torch-on-GPU uses; copies are done inside the C call."""

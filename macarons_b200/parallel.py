@@ -61,3 +61,71 @@ def sharded_coverage_gain(score_fn, pts, harmonics, X_cam, group=None):
 def nbv_argmax(scores):
     """First maximum along the camera axis (reference testers/shapenet.py:172, testers/scene.py:454)."""
     return torch.argmax(scores, dim=-1)
+
+
+class PeerScoreBoard:
+    """Fused compute + exchange for the sharded scoring step: the coverage-gain kernel of every rank stores
+    its score columns directly into the (B, C) score board of every peer through NVLink peer mappings
+    (torch symmetric memory) and raises a flag; a one-CTA kernel then waits for all ranks and takes the
+    argmax.  Two kernels per step, no NCCL call on the data path.
+
+    Two boards are used alternately (even / odd epochs) so a fast rank can never overwrite scores that a
+    slow peer is still reading (a rank's step k+2 push is stream-ordered after its own step k+1 wait, which
+    needs every peer's step k+1 push, which is stream-ordered after that peer's step k argmax).
+
+    `scores` returned by `step()` is a view of the live board: consume (or clone) it before calling `step()`
+    two more times."""
+
+    def __init__(self, n_clouds, n_cameras, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.B, self.C = int(n_clouds), int(n_cameras)
+        self.device = torch.device(device)
+        self.rank, self.world = _world(group)
+        self.epoch = 0
+        n_scores = self.B * self.C
+        self._flag_off = 2 * n_scores            # in 4-byte words: [board 0 | board 1 | flags(world) | pad]
+        words = self._flag_off + 64
+        if self.world > 1:
+            grp = group if group is not None else dist.group.WORLD
+            self._buf = symm_mem.empty(words, dtype=torch.float32, device=self.device)
+            self._buf.zero_()
+            self._hdl = symm_mem.rendezvous(self._buf, grp)
+            bases = [int(p) for p in self._hdl.buffer_ptrs]
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)            # every board is zeroed before anyone pushes
+        else:
+            self._buf = torch.zeros(words, dtype=torch.float32, device=self.device)
+            bases = [self._buf.data_ptr()]
+        self._bases = bases
+        self._flags = self._buf[self._flag_off:self._flag_off + 64].view(torch.int32)
+        self.best = torch.zeros(self.B, dtype=torch.int64, device=self.device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def _board(self, parity):
+        n = self.B * self.C
+        return self._buf[parity * n:(parity + 1) * n].view(self.B, self.C)
+
+    def step(self, pts, harmonics, X_cam, use_sigmoid=True, events=None):
+        """-> ((B, C) scores, (B,) argmax), identical on every rank.  `events` = optional pair of
+        torch.cuda.Event recorded around the scoring kernel (bench.py's roofline timing)."""
+        from . import ops
+        self.epoch += 1
+        parity = self.epoch & 1
+        n = self.B * self.C
+        score_ptrs = [b + 4 * parity * n for b in self._bases]
+        flag_ptrs = [b + 4 * self._flag_off for b in self._bases]
+        c0, c1 = camera_partition(self.C, self.world, self.rank)
+        if events is not None:
+            events[0].record()
+        ops.coverage_gain_push(pts, harmonics, X_cam, use_sigmoid, (c0, c1), score_ptrs, flag_ptrs, self.rank,
+                               self.epoch)
+        if events is not None:
+            events[1].record()
+        scores = self._board(parity)
+        ops.gather_wait_argmax(scores, self._flags, self.world, self.epoch, self.best, self.status)
+        return scores, self.best
+
+    def check(self):
+        """Synchronises; raises if a wait timed out (a peer never arrived)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("PeerScoreBoard: timed out waiting for a peer's scores")

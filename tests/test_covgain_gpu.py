@@ -198,3 +198,25 @@ def test_full_size_cfg5_properties(cuda_device):
     # fp32 oracle (reference arithmetic) on 2 cameras over all points
     want = sh_cov.coverage_gain(pts, harm, cams[:, :2])
     assert (full.cpu()[:, :2] - want).abs().max().item() <= COVERAGE_ATOL
+
+
+def test_fused_push_and_argmax_single_rank(cuda_device):
+    """World size 1 of the fused gather: the kernel pushes into a local board, the wait kernel takes the argmax."""
+    pts, harm, cams = synth.covgain_inputs(3, 900, 70, seed=31)
+    d = [t.to(cuda_device) for t in (pts, harm, cams)]
+    board = parallel.PeerScoreBoard(3, 70, cuda_device)
+    want = ops.coverage_gain(*d)
+    for _ in range(3):   # alternates between the two boards
+        scores, best = board.step(*d)
+        board.check()
+        assert torch.equal(scores, want)
+        assert torch.equal(best, want.argmax(-1))
+    # ties and NaN follow torch.argmax: first maximum, NaN is maximal
+    s = torch.tensor([[0.5, 0.7, 0.7, 0.1], [0.2, float("nan"), 0.9, float("nan")]], device=cuda_device)
+    flags = torch.full((1,), 5, dtype=torch.int32, device=cuda_device)
+    best = torch.zeros(2, dtype=torch.int64, device=cuda_device)
+    status = torch.ones(1, dtype=torch.int32, device=cuda_device)
+    ops.gather_wait_argmax(s, flags, 1, 5, best, status)
+    assert best.tolist() == [1, 1] and status.item() == 0
+    ops.gather_wait_argmax(s, flags, 1, 6, best, status)   # epoch never arrives -> bounded wait, status 1
+    assert status.item() == 1
