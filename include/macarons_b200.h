@@ -122,6 +122,29 @@ int mac_covgain_push_f32(const float *pts, int pts_dim, const float *harmonics, 
 int mac_gather_wait_argmax(const float *scores, const unsigned int *flags, int world, unsigned int epoch,
                            int B, int C, long long *best, int *status, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused linear layer on tcgen05 tensor cores (building block of SconeOcc / SconeVis; replaces the
+ * nn.Linear + LayerNorm + GELU + residual sequences of /root/reference/macarons/networks/Attention.py:96-98,
+ * 160-162, 225-226, 281-298 and the pooling of networks/SconeOcc.py:120-127).
+ *
+ *   out[m, n] = res[m, n] + act( sum_k X[m, k] * W[n, k] + bias[n] )          (res, bias optional)
+ *   ln_out    = LayerNorm_N(out) * ln_g + ln_b                                  (optional, N <= 256)
+ *   pool = 16: out (M/16, 2N) = [max | mean] of `out` over groups of 16 consecutive rows
+ *
+ * X (M, K) row stride ldx, W (N, K) row stride ldw, both 16-byte aligned with strides that are multiples
+ * of 4 floats.  W_hi / W_lo are the two TF32 halves of the fp32 weight (W_hi = tf32(W), W_lo = tf32(W - W_hi),
+ * see macarons_b200/packing.py); the kernel splits X the same way on chip and accumulates the three cross
+ * products in fp32, which reproduces an fp32 matmul to ~1e-6 relative.  W_lo = NULL selects plain
+ * single-pass TF32 (10 mantissa bits).
+ * ------------------------------------------------------------------------------------------- */
+#define MAC_LIN_NONE 0
+#define MAC_LIN_RELU 1
+#define MAC_LIN_GELU 2 /* exact (erf) GELU, torch.nn.GELU() default */
+
+int mac_linear_f32(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias,
+                   float *out, int ldo, int M, int N, int K, int act, const float *res, int ldr, float *ln_out,
+                   int ldl, const float *ln_g, const float *ln_b, float ln_eps, int pool, void *stream);
+
 /* Number of kernel launches the library has enqueued since load (for bench.py's gpu_launches). */
 unsigned long long mac_launch_count(void);
 

@@ -50,6 +50,12 @@ SYMBOLS["mac_gather_wait_argmax"] = (ctypes.c_int, [_c_float_p, ctypes.c_void_p,
                                                     ctypes.c_void_p])
 
 
+SYMBOLS["mac_linear_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_int, _c_float_p,
+                                            _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, _c_float_p, ctypes.c_int, _c_float_p, ctypes.c_int,
+                                            _c_float_p, _c_float_p, ctypes.c_float, ctypes.c_int, ctypes.c_void_p])
+
+
 class MacaronsB200Error(RuntimeError):
     pass
 

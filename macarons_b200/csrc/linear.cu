@@ -1,0 +1,404 @@
+// Fused linear layer on the 5th-generation tensor cores:
+//     Y = epilogue( X (M,K) . W (N,K)^T + bias )
+// the building block of every dense contraction of SconeOcc / SconeVis (reference nn.Linear calls in
+// networks/Attention.py:96-98,160-162,173,225-226, networks/SconeOcc.py:18-22,103,227-229,
+// networks/SconeVis.py:114-119).
+//
+// Design (sm_100a):
+//   * CTA tile 128 (M) x BN (N), K swept in chunks of 32 fp32 = 128-byte rows.  Warp 0 streams the X and W
+//     tiles global -> shared with TMA (SWIZZLE_128B tensor maps, mbarrier completion, out-of-range rows
+//     and columns zero-filled by the hardware, so K, N, M need no padding).
+//   * warp 1 issues tcgen05.mma kind::tf32 (UMMA 128 x BN x 8) with the fp32 accumulator in TMEM.
+//   * fp32 accuracy: TF32 keeps 10 mantissa bits, far too few for parity with the fp32 reference, so
+//     every product is evaluated as  x_hi w_hi + x_lo w_hi + x_hi w_lo  (x = x_hi + x_lo with both parts
+//     exactly representable in TF32; the dropped x_lo w_lo term is 2^-22 relative).  W is split once when
+//     the weights are packed; X is split in shared memory by the epilogue warps while they wait
+//     (element-wise, hence oblivious to the swizzle), fenced to the async proxy and handed to the MMA
+//     warp through a second mbarrier.
+//   * epilogue: the 4 epilogue warps read their 32 TMEM lanes (one output row per thread) with
+//     tcgen05.ld and apply bias -> activation (ReLU / exact GELU) -> residual add; optionally they also
+//     emit LayerNorm(Y) for the next layer (two-pass statistics over the TMEM row, the tile spans all N)
+//     or max / mean pool groups of 16 consecutive rows (the 16-token neighbourhoods of SconeOcc).
+#include <cuda.h>
+#include <math.h>
+
+#include "tc_common.h"
+
+namespace mac {
+
+int make_tensor_map_2d(CUtensorMap *map, const float *base, int rows, int cols, int ld, int box_rows)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MAC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return MAC_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    MAC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0 && ld % 4 == 0,
+                "TMA operand must be 16-byte aligned with a row stride that is a multiple of 4 floats (ld=%d)", ld);
+    MAC_REQUIRE(rows > 0 && cols > 0 && cols <= ld && box_rows >= 1 && box_rows <= 256, "bad tensor map shape");
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
+    const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t elem[2] = {1, 1};
+    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box,
+                               elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d cols=%d ld=%d box_rows=%d)",
+                  static_cast<int>(rc), rows, cols, ld, box_rows);
+        return MAC_ERR_CUDA;
+    }
+    return MAC_OK;
+}
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 32;             // fp32 per k-chunk: one 128-byte swizzle span
+constexpr int kUmmaK = 8;           // tf32 MMA depth (32 bytes)
+constexpr int kATileBytes = kBM * kBK * 4;
+constexpr int kThreads = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 split + epilogue
+constexpr int kMaxStages = 4;
+
+struct LinearParams {
+    int M, N, K;
+    const float *bias;
+    float *out;
+    int ldo;
+    const float *res;
+    int ldr;
+    float *ln_out;
+    int ldl;
+    const float *ln_g, *ln_b;
+    float ln_eps;
+    int act;
+    int pool;  // 0, or 16: max | mean over groups of 16 rows -> out (M/16, 2N)
+};
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float apply_act(float y, int act)
+{
+    if (act == MAC_LIN_RELU) return fmaxf(y, 0.f);
+    if (act == MAC_LIN_GELU) return gelu_exact(y);
+    return y;
+}
+
+template <int BN, bool SPLIT>
+struct Cfg {
+    static constexpr int kBTileBytes = BN * kBK * 4;
+    static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kATileBytes + kBTileBytes);
+    static constexpr int kStages = (200 * 1024 / kStageBytes) < kMaxStages ? (200 * 1024 / kStageBytes) : kMaxStages;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t kTxBytes = kATileBytes + (SPLIT ? 2 : 1) * kBTileBytes;
+};
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
+              const __grid_constant__ CUtensorMap mapBlo, const LinearParams p)
+{
+    using C = Cfg<BN, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes);
+    uint64_t *full = bars;                       // TMA landed
+    uint64_t *ready = bars + kMaxStages;         // X split done (SPLIT only)
+    uint64_t *empty = bars + 2 * kMaxStages;     // MMAs that read the stage have completed
+    uint64_t *acc_full = bars + 3 * kMaxStages;  // accumulator complete
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * kMaxStages + 1);
+
+    auto a_hi = [&](int s) { return smem + s * C::kStageBytes; };
+    auto b_hi = [&](int s) { return smem + s * C::kStageBytes + kATileBytes; };
+    auto a_lo = [&](int s) { return smem + s * C::kStageBytes + kATileBytes + C::kBTileBytes; };
+    auto b_lo = [&](int s) { return smem + s * C::kStageBytes + 2 * kATileBytes + C::kBTileBytes; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+    const int nk = (p.K + kBK - 1) / kBK;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapBhi);
+        if (SPLIT) tma_prefetch_desc(&mapBlo);
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&ready[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % C::kStages;
+                const uint32_t ph = (kc / C::kStages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], C::kTxBytes);
+                tma_load_2d(a_hi(s), &mapA, kc * kBK, m0, &full[s]);
+                tma_load_2d(b_hi(s), &mapBhi, kc * kBK, n0, &full[s]);
+                if (SPLIT) tma_load_2d(b_lo(s), &mapBlo, kc * kBK, n0, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % C::kStages;
+                const uint32_t ph = (kc / C::kStages) & 1;
+                mbar_wait(SPLIT ? &ready[s] : &full[s], ph);
+                tc_fence_after_sync();
+                const uint32_t ah = smem_u32(a_hi(s)), bh = smem_u32(b_hi(s));
+                const uint32_t al = smem_u32(a_lo(s)), bl = smem_u32(b_lo(s));
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k) {
+                    const uint32_t off = k * kUmmaK * 4;
+                    if (SPLIT) {
+                        umma_tf32(tmem_base, umma_desc_k_sw128(al + off), umma_desc_k_sw128(bh + off), idesc, (kc | k) != 0);
+                        umma_tf32(tmem_base, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bl + off), idesc, 1);
+                        umma_tf32(tmem_base, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, 1);
+                    } else {
+                        umma_tf32(tmem_base, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, (kc | k) != 0);
+                    }
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ===== X split (main loop) + epilogue =====
+        const int t = threadIdx.x - 64;  // 0..127
+        if (SPLIT) {
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % C::kStages;
+                const uint32_t ph = (kc / C::kStages) & 1;
+                mbar_wait(&full[s], ph);
+                float4 *hi = reinterpret_cast<float4 *>(a_hi(s));
+                float4 *lo = reinterpret_cast<float4 *>(a_lo(s));
+#pragma unroll
+                for (int i = 0; i < kATileBytes / 16 / 128; ++i) {
+                    const float4 v = hi[t + i * 128];
+                    float4 h, l;
+                    h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
+                    l.x = to_tf32(v.x - h.x), l.y = to_tf32(v.y - h.y), l.z = to_tf32(v.z - h.z), l.w = to_tf32(v.w - h.w);
+                    hi[t + i * 128] = h;
+                    lo[t + i * 128] = l;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&ready[s]);
+            }
+        }
+        mbar_wait(acc_full, 0);
+        tc_fence_after_sync();
+
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int row = m0 + q * 32 + lane;     // output row of this thread
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const bool row_ok = row < p.M;
+        const int ncols = min(BN, p.N - n0);    // valid columns of this tile
+        float v[32];
+
+        auto value = [&](float acc, int col) {  // bias -> activation -> residual
+            float y = acc + (p.bias ? __ldg(p.bias + col) : 0.f);
+            y = apply_act(y, p.act);
+            if (p.res) y += __ldg(p.res + static_cast<size_t>(row) * p.ldr + col);
+            return y;
+        };
+
+        if (p.pool) {
+            // groups of 16 consecutive rows -> out[row/16, col] = max, out[row/16, N + col] = mean
+            const int g = row >> 4, gl = lane & 15;
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                tmem_ld32(taddr + c0, v);
+                float mx[2], sm[2];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c0 + j;
+                    float y = (row_ok && col < p.N) ? value(v[j], col) : 0.f;
+                    float a = y, b = y;
+#pragma unroll
+                    for (int d = 8; d >= 1; d >>= 1) {
+                        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, d));
+                        b += __shfl_xor_sync(0xffffffffu, b, d);
+                    }
+                    if ((j & 15) == gl) mx[j >> 4] = a, sm[j >> 4] = b;
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = n0 + c0 + h * 16 + gl;
+                        if (col < p.N) {
+                            p.out[static_cast<size_t>(g) * p.ldo + col] = mx[h];
+                            p.out[static_cast<size_t>(g) * p.ldo + p.N + col] = sm[h] * (1.0f / 16.0f);
+                        }
+                    }
+                }
+            }
+        } else {
+            float sum = 0.f;
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                tmem_ld32(taddr + c0, v);
+                if (row_ok) {
+                    float *dst = p.out ? p.out + static_cast<size_t>(row) * p.ldo + n0 + c0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int col = n0 + c0 + j;
+                        if (col + 3 < p.N) {
+                            float4 y;
+                            y.x = value(v[j], col), y.y = value(v[j + 1], col + 1);
+                            y.z = value(v[j + 2], col + 2), y.w = value(v[j + 3], col + 3);
+                            sum += (y.x + y.y) + (y.z + y.w);
+                            if (dst) *reinterpret_cast<float4 *>(dst + j) = y;
+                        } else {
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < p.N) {
+                                    const float y = value(v[j + e], col + e);
+                                    sum += y;
+                                    if (dst) dst[j + e] = y;
+                                }
+                        }
+                    }
+                }
+            }
+            if (p.ln_out) {
+                // LayerNorm over the N columns of this row (the tile spans all of N): mean, then centred variance
+                const float mean = sum / static_cast<float>(p.N);
+                float var = 0.f;
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    tmem_ld32(taddr + c0, v);
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c0 + j < ncols) {
+                                const float d = value(v[j], n0 + c0 + j) - mean;
+                                var = fmaf(d, d, var);
+                            }
+                    }
+                }
+                const float rstd = 1.0f / sqrtf(var / static_cast<float>(p.N) + p.ln_eps);
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    tmem_ld32(taddr + c0, v);
+                    if (row_ok) {
+                        float *dst = p.ln_out + static_cast<size_t>(row) * p.ldl + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (c0 + j + 3 < ncols) {
+                                float4 y;
+                                float *ye = &y.x;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int col = c0 + j + e;
+                                    ye[e] = (value(v[j + e], col) - mean) * rstd * __ldg(p.ln_g + col) + __ldg(p.ln_b + col);
+                                }
+                                *reinterpret_cast<float4 *>(dst + j) = y;
+                            } else {
+                                for (int e = 0; e < 4; ++e) {
+                                    const int col = c0 + j + e;
+                                    if (col < ncols)
+                                        dst[j + e] = (value(v[j + e], col) - mean) * rstd * __ldg(p.ln_g + col) + __ldg(p.ln_b + col);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+template <int BN, bool SPLIT>
+int launch(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap &mapBlo, const LinearParams &p,
+           cudaStream_t stream)
+{
+    using C = Cfg<BN, SPLIT>;
+    static bool configured = false;
+    if (!configured) {
+        MAC_CUDA(cudaFuncSetAttribute(linear_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        configured = true;
+    }
+    dim3 grid((p.M + kBM - 1) / kBM, (p.N + BN - 1) / BN);
+    linear_kernel<BN, SPLIT><<<grid, kThreads, C::kSmemBytes, stream>>>(mapA, mapBhi, mapBlo, p);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+}  // namespace
+
+int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias, float *out,
+                   int ldo, int M, int N, int K, int act, const float *res, int ldr, float *ln_out, int ldl,
+                   const float *ln_g, const float *ln_b, float ln_eps, int pool, cudaStream_t stream)
+{
+    MAC_REQUIRE(X && W_hi && (out || ln_out), "null tensor pointer");
+    MAC_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive (got %d, %d, %d)", M, N, K);
+    MAC_REQUIRE(act == MAC_LIN_NONE || act == MAC_LIN_RELU || act == MAC_LIN_GELU, "bad activation %d", act);
+    MAC_REQUIRE(pool == 0 || pool == 16, "pool must be 0 or 16");
+    MAC_REQUIRE(!pool || (M % 16 == 0 && out && !ln_out), "pooling needs M %% 16 == 0 and no LayerNorm output");
+    MAC_REQUIRE(!ln_out || (N <= 256 && ln_g && ln_b && ldl % 4 == 0), "fused LayerNorm needs N <= 256, gamma and beta");
+    MAC_REQUIRE(!out || pool || (ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0),
+                "out must be 16-byte aligned with ldo %% 4 == 0");
+    const bool split = W_lo != nullptr;
+
+    int bn;
+    if (ln_out || pool) bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    else bn = N <= 64 ? 64 : ((N <= 128 || M <= 16384) ? 128 : 256);
+    MAC_REQUIRE(!(ln_out || pool) || N <= bn, "row-wise epilogues need the tile to span N");
+
+    CUtensorMap mapA, mapBhi, mapBlo;
+    if (int rc = make_tensor_map_2d(&mapA, X, M, K, ldx, kBM)) return rc;
+    if (int rc = make_tensor_map_2d(&mapBhi, W_hi, N, K, ldw, bn)) return rc;
+    if (int rc = make_tensor_map_2d(&mapBlo, split ? W_lo : W_hi, N, K, ldw, bn)) return rc;
+
+    LinearParams p{};
+    p.M = M, p.N = N, p.K = K;
+    p.bias = bias;
+    p.out = out, p.ldo = ldo;
+    p.res = res, p.ldr = ldr;
+    p.ln_out = ln_out, p.ldl = ldl, p.ln_g = ln_g, p.ln_b = ln_b, p.ln_eps = ln_eps;
+    p.act = act, p.pool = pool;
+
+    if (split) {
+        if (bn == 64) return launch<64, true>(mapA, mapBhi, mapBlo, p, stream);
+        if (bn == 128) return launch<128, true>(mapA, mapBhi, mapBlo, p, stream);
+        return launch<256, true>(mapA, mapBhi, mapBlo, p, stream);
+    }
+    if (bn == 64) return launch<64, false>(mapA, mapBhi, mapBlo, p, stream);
+    if (bn == 128) return launch<128, false>(mapA, mapBhi, mapBlo, p, stream);
+    return launch<256, false>(mapA, mapBhi, mapBlo, p, stream);
+}
+
+}  // namespace mac
+
+extern "C" int mac_linear_f32(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias,
+                              float *out, int ldo, int M, int N, int K, int act, const float *res, int ldr,
+                              float *ln_out, int ldl, const float *ln_g, const float *ln_b, float ln_eps, int pool,
+                              void *stream)
+{
+    return mac::linear_forward(X, ldx, W_hi, W_lo, ldw, bias, out, ldo, M, N, K, act, res, ldr, ln_out, ldl, ln_g, ln_b,
+                               ln_eps, pool, static_cast<cudaStream_t>(stream));
+}

@@ -148,3 +148,45 @@ def coverage_gain_host(pts, harmonics, X_cam, use_sigmoid=True, cam_range=None, 
 
 def launch_count():
     return int(_lib.load().mac_launch_count())
+
+
+# ---- tensor-core linear layer (csrc/linear.cu) ----------------------------------------------------
+ACT_NONE, ACT_LIN_RELU, ACT_GELU = 0, 1, 2
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def linear(x, packed, act=ACT_NONE, residual=None, out=None, ln=None, pool=0, K=None):
+    """out = residual + act(x @ W^T + b) through mac_linear_f32.
+
+    x (M, >=K) fp32 CUDA with row stride % 4 == 0; `packed` a packing.PackedLinear; `ln=(gamma, beta, eps)`
+    additionally returns LayerNorm(out); `pool=16` returns (M/16, 2N) = [max | mean] over 16-row groups;
+    `out` may be a column slice of a wider buffer (last-dim stride 1)."""
+    _require_cuda_f32("x", x)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be 2-D with unit column stride")
+    M = x.shape[0]
+    K = packed.K if K is None else K
+    N = packed.N
+    if x.shape[1] < K:
+        raise ValueError("x has %d columns, the layer needs %d" % (x.shape[1], K))
+    dev = x.device
+    Np = (N + 3) // 4 * 4   # rows padded to 16 bytes: the epilogue stores float4, TMA reads need it as well
+    if out is None:
+        out = torch.empty((M // 16, 2 * N), dtype=torch.float32, device=dev) if pool else \
+            torch.empty((M, Np), dtype=torch.float32, device=dev)[:, :N]
+    ln_out = None
+    if ln is not None:
+        ln_out = torch.empty((M, Np), dtype=torch.float32, device=dev)[:, :N]
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.mac_linear_f32(
+            x.data_ptr(), x.stride(0), packed.hi.data_ptr(), _ptr(packed.lo), packed.ldw, _ptr(packed.bias),
+            out.data_ptr(), out.stride(0), M, N, K, int(act),
+            _ptr(residual), 0 if residual is None else residual.stride(0),
+            _ptr(ln_out), 0 if ln_out is None else ln_out.stride(0),
+            0 if ln is None else ln[0].data_ptr(), 0 if ln is None else ln[1].data_ptr(),
+            0.0 if ln is None else float(ln[2]), int(pool), _stream_ptr(dev)))
+    return (out, ln_out) if ln is not None else out
