@@ -145,6 +145,82 @@ int mac_linear_f32(const float *X, int ldx, const float *W_hi, const float *W_lo
                    float *out, int ldo, int M, int N, int K, int act, const float *res, int ldr, float *ln_out,
                    int ldl, const float *ln_g, const float *ln_b, float ln_eps, int pool, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * k nearest neighbours (k = 16)  --  replaces get_knn_points, /root/reference/macarons/utility/utils.py:1497-1509
+ * (torch.cdist + topk + knn_gather): idx (B, Q, 16) int32 indices into pc (B, N, 3) of the 16 nearest
+ * points of every query x (B, Q, 3), nearest first; dist (B, Q, 16) Euclidean distances (may be NULL).
+ * No (B, Q, N) distance matrix is materialised.
+ * ------------------------------------------------------------------------------------------- */
+int mac_knn16_f32(const float *x, const float *pc, int *idx, float *dist, int B, int Q, int N, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SconeOcc / SconeVis forward passes.  Weights are packed once by the caller (macarons_b200/packing.py)
+ * into the structs below; all pointers are device pointers owned by the caller.
+ *   mac_linear_w_t   one nn.Linear as the two TF32 halves of its (N, K) weight (row stride ldw) + bias
+ *   mac_encoder_w_t  one pre-LayerNorm encoder, networks/Attention.py:239-300; qkv = rows [w_q; w_k; w_v]
+ *   mac_pct_w_t      PCTransformer, networks/SconeOcc.py:45-130.  emb2 is Embedding.linear2 extended by
+ *                    identity rows so that the GEMM also performs the `cat((res, x))` of Attention.py:125
+ * ------------------------------------------------------------------------------------------- */
+#define MAC_MAX_ENCODERS 4
+#define MAC_MAX_SCALES 4
+typedef struct mac_linear_w {
+    const float *hi, *lo, *bias;
+    int N, K, ldw;
+} mac_linear_w_t;
+typedef struct mac_encoder_w {
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    mac_linear_w_t qkv, out, ff1, ff2;
+} mac_encoder_w_t;
+typedef struct mac_pct_w {
+    const float *emb1_w, *emb1_b; /* Embedding.linear1, plain fp32 (inner, in_dim) */
+    int in_dim, inner;
+    mac_linear_w_t emb2;
+    int n_enc, d_model, dqk, dv;  /* dqk, dv: per-head dims (4 heads) */
+    mac_encoder_w_t enc[MAC_MAX_ENCODERS];
+    const float *ln_g, *ln_b;
+    mac_linear_w_t linear0;
+} mac_pct_w_t;
+typedef struct mac_sconeocc_w {
+    mac_pct_w_t global_pct;
+    int n_scale;
+    mac_pct_w_t local_pct[MAC_MAX_SCALES];
+    const float *xemb1_w, *xemb1_b; /* XEmbedding.linear1, plain fp32 (128, 3) */
+    int xemb1_n;
+    mac_linear_w_t xemb2, xemb3;
+    const float *lin1_wg;           /* linear1 columns that multiply the global feature, plain fp32 (512, 512) */
+    int lin1_wg_ld, global_dim;
+    const float *lin1_b;
+    mac_linear_w_t lin1;            /* remaining columns [local | x | view harmonics]; bias unused */
+    mac_linear_w_t lin2, lin3;
+} mac_sconeocc_w_t;
+typedef struct mac_sconevis_w {
+    const float *emb1_w, *emb1_b;   /* Embedding.linear1, plain fp32 (126, 4) */
+    int in_dim, inner;
+    mac_linear_w_t emb2;
+    int n_enc, d_model, dqk, dv;
+    mac_encoder_w_t enc[MAC_MAX_ENCODERS];
+    const float *ln_g, *ln_b;
+    mac_linear_w_t fc1, fc2, fc3;
+} mac_sconevis_w_t;
+
+/* SconeVis.forward, /root/reference/macarons/networks/SconeVis.py:121-162 (default architecture:
+ * global max-pooled feature, view harmonics concatenated before fc2, no mask):
+ *   pts (B, S, 4), view_harmonics (B, S, 64) -> out (B, S, 64) SH coefficients of the visibility gains. */
+size_t mac_sconevis_workspace_bytes(int B, int S);
+int mac_sconevis_forward_f32(const mac_sconevis_w_t *w, const float *pts, const float *view_harmonics, float *out, int B,
+                             int S, void *workspace, size_t workspace_bytes, void *stream);
+
+/* SconeOcc.forward, /root/reference/macarons/networks/SconeOcc.py:250-347, after the caller has drawn the
+ * random sub-samples (torch.randperm, :269 and :311, stays on the host so that the RNG stream matches):
+ *   pc_global (B, Sg, 3)           the <= seq_len points fed to the global transformer
+ *   pc_scale[s] (B, n_scale_pts[s], 3)   the cloud kNN is taken in at scale s (full, /ds, /ds^2)
+ *   x (B, Q, 3) queries, view_harmonics (B, Q, 64)  ->  out (B, Q, 1) = GELU(MLP(...)) occupancy values.
+ * Queries are processed `chunk` at a time (results do not depend on it). */
+size_t mac_sconeocc_workspace_bytes(int B, int Sg, int chunk);
+int mac_sconeocc_forward_f32(const mac_sconeocc_w_t *w, const float *pc_global, int Sg, const float *const *pc_scale,
+                             const int *n_scale_pts, const float *x, const float *view_harmonics, float *out, int B,
+                             int Q, int chunk, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Number of kernel launches the library has enqueued since load (for bench.py's gpu_launches). */
 unsigned long long mac_launch_count(void);
 

@@ -56,6 +56,18 @@ SYMBOLS["mac_linear_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p
                                             _c_float_p, _c_float_p, ctypes.c_float, ctypes.c_int, ctypes.c_void_p])
 
 
+SYMBOLS["mac_knn16_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_void_p])
+SYMBOLS["mac_sconevis_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int])
+SYMBOLS["mac_sconevis_forward_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
+                                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])
+SYMBOLS["mac_sconeocc_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
+SYMBOLS["mac_sconeocc_forward_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_void_p,
+                                                      ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
+                                                      ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                                      ctypes.c_void_p])
+
+
 class MacaronsB200Error(RuntimeError):
     pass
 

@@ -1,0 +1,21 @@
+// Internal launchers of the SconeOcc / SconeVis building blocks (pointnet.cu, linear.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mac_common.h"
+
+namespace mac {
+
+int knn16(const float *x, const float *pc, int *idx, float *dist, int B, int Q, int N, cudaStream_t stream);
+int embed_first(const float *in, int ld_in, int in_dim, const float *pc, const float *x, const int *idx, int Q, int N,
+                const float *w, const float *b, int inner, int append, float *out, int ldo, long long T,
+                cudaStream_t stream);
+int attn16(const float *qkv, int ldq, float *out, int ldo, long long n_seq, int dqk, int dv, cudaStream_t stream);
+int attn_dense(const float *qkv, int ldq, float *out, int ldo, int B, int S, int dqk, int dv, cudaStream_t stream);
+int colpool(const float *in, int ld, int B, int S, int N, float *out_max, float *out_mean, int ldo, cudaStream_t stream);
+int vis_embed_finish(float *x0, int ld, const float *gmax, int ldg, const float *pts, int ldp, int F, int in_dim, int S,
+                     long long T, const float *g, const float *b, float eps, float *ln, int ldl, cudaStream_t stream);
+int bias_gemv(const float *W, int ldw, const float *bias, const float *g, int ldg, int N, int K, float *out, int B,
+              cudaStream_t stream);
+
+}  // namespace mac

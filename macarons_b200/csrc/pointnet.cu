@@ -1,0 +1,539 @@
+// CUDA-core kernels around the tensor-core linear layers of SconeOcc / SconeVis:
+//   knn16           16 nearest neighbours of every query in a cloud     (reference utility/utils.py:1497-1509)
+//   embed_first     first embedding layer (K = 3 or 4 inputs) + GELU, optional neighbour gather / offset and
+//                   input concatenation                                  (networks/Attention.py:96-98,124-126;
+//                                                                        networks/SconeOcc.py:293-296, 18-36)
+//   attn16          self-attention over 16-token neighbourhoods         (networks/Attention.py:8-36,182-204)
+//   attn_dense      self-attention over one cloud (<= a few thousand tokens), flash-style online softmax
+//   colpool         max / mean over the tokens of a cloud               (networks/SconeOcc.py:120-127,
+//                                                                        networks/Attention.py:110-114)
+//   vis_embed_finish  [features | global max | input] concatenation + LayerNorm (networks/Attention.py:110-126)
+//   bias_gemv       per-cloud bias = b + W_g . global_feature (folds the broadcast global feature of
+//                   networks/SconeOcc.py:330-334 into the first head layer)
+#include <float.h>
+#include <math.h>
+
+#include "tc_common.h"
+#include "nets.h"
+
+namespace mac {
+
+namespace {
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ------------------------------------------------------------------------------------------------
+// kNN: one thread per query, cloud tiled through shared memory, sorted top-16 kept in registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int kKnn = 16;
+constexpr int kKnnTile = 1024;
+
+__global__ void __launch_bounds__(128) knn16_kernel(const float *__restrict__ x, const float *__restrict__ pc,
+                                                    int *__restrict__ idx_out, float *__restrict__ dist_out, int Q, int N)
+{
+    __shared__ float sp[kKnnTile * 3];
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = q < Q;
+    const float *xb = x + (static_cast<size_t>(b) * Q + (live ? q : 0)) * 3;
+    const float qx = xb[0], qy = xb[1], qz = xb[2];
+    const float *pcb = pc + static_cast<size_t>(b) * N * 3;
+
+    float bd[kKnn];
+    int bi[kKnn];
+#pragma unroll
+    for (int i = 0; i < kKnn; ++i) bd[i] = FLT_MAX, bi[i] = 0;
+
+    for (int t0 = 0; t0 < N; t0 += kKnnTile) {
+        const int n = min(kKnnTile, N - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n * 3; i += blockDim.x) sp[i] = pcb[static_cast<size_t>(t0) * 3 + i];
+        __syncthreads();
+        for (int j = 0; j < n; ++j) {
+            const float dx = qx - sp[3 * j], dy = qy - sp[3 * j + 1], dz = qz - sp[3 * j + 2];
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (d < bd[kKnn - 1]) {
+                bd[kKnn - 1] = d;
+                bi[kKnn - 1] = t0 + j;
+#pragma unroll
+                for (int i = kKnn - 1; i > 0; --i) {
+                    if (bd[i] < bd[i - 1]) {
+                        const float td = bd[i];
+                        bd[i] = bd[i - 1];
+                        bd[i - 1] = td;
+                        const int ti = bi[i];
+                        bi[i] = bi[i - 1];
+                        bi[i - 1] = ti;
+                    }
+                }
+            }
+        }
+    }
+    if (live) {
+        int *io = idx_out + (static_cast<size_t>(b) * Q + q) * kKnn;
+#pragma unroll
+        for (int i = 0; i < kKnn; i += 4) *reinterpret_cast<int4 *>(io + i) = make_int4(bi[i], bi[i + 1], bi[i + 2], bi[i + 3]);
+        if (dist_out) {
+            float *dout = dist_out + (static_cast<size_t>(b) * Q + q) * kKnn;
+#pragma unroll
+            for (int i = 0; i < kKnn; ++i) dout[i] = sqrtf(bd[i]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// First embedding layer: h = GELU(W1 p + b1), p in R^IN (IN = 3 or 4); one thread per (token, 4 features).
+// GATHER: p = pc[b, idx[b, q, j]] - x[b, q]  (token = (b*Q + q)*16 + j); otherwise p = in[token].
+// append: copy p behind the features (columns inner .. inner+IN-1).
+// ------------------------------------------------------------------------------------------------
+struct EmbedParams {
+    const float *in;      // (T, ld_in) rows, first IN entries used            [!GATHER]
+    int ld_in;
+    const float *pc;      // (B, N, 3)                                          [GATHER]
+    const float *x;       // (B, Q, 3)
+    const int *idx;       // (B, Q, 16)
+    int Q, N;
+    const float *w, *b;   // (inner, IN), (inner)
+    int inner, append;
+    float *out;           // (T, ldo)
+    int ldo;
+    long long T;
+};
+
+template <int IN, bool GATHER>
+__global__ void __launch_bounds__(256) embed_first_kernel(const EmbedParams p)
+{
+    extern __shared__ float sw[];  // w (inner*IN) | b (inner)
+    for (int i = threadIdx.x; i < p.inner * IN; i += blockDim.x) sw[i] = p.w[i];
+    for (int i = threadIdx.x; i < p.inner; i += blockDim.x) sw[p.inner * IN + i] = p.b[i];
+    __syncthreads();
+    const float *sb = sw + p.inner * IN;
+    const int groups = (p.inner + (p.append ? IN : 0) + 3) / 4;  // float4 groups per token
+    const long long total = p.T * 32;                              // 32 lanes per token (ldo <= 128)
+    for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < total;
+         g += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long t = g >> 5;
+        const int c4 = static_cast<int>(g & 31);
+        if (c4 >= groups) continue;
+        float v[IN];
+        if (GATHER) {
+            const long long bq = t >> 4;            // b*Q + q
+            const int b = static_cast<int>(bq / p.Q);
+            const int n = p.idx[t];
+            const float *pp = p.pc + (static_cast<size_t>(b) * p.N + n) * 3;
+            const float *xx = p.x + bq * 3;
+#pragma unroll
+            for (int e = 0; e < IN; ++e) v[e] = pp[e] - xx[e];
+        } else {
+            const float *pp = p.in + t * p.ld_in;
+#pragma unroll
+            for (int e = 0; e < IN; ++e) v[e] = pp[e];
+        }
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            float y = 0.f;
+            if (c < p.inner) {
+                y = sb[c];
+#pragma unroll
+                for (int k = 0; k < IN; ++k) y = fmaf(sw[c * IN + k], v[k], y);
+                y = gelu_exact(y);
+            } else if (p.append && c < p.inner + IN) {
+                y = v[c - p.inner];
+            }
+            o[e] = y;
+        }
+        *reinterpret_cast<float4 *>(p.out + t * p.ldo + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attn16: one warp per 16-token sequence, 4 heads; lane = (query i, head pair).
+// qkv rows: [q (H*DQK) | k (H*DQK) | v (H*DV)], out rows: (H*DV).
+// ------------------------------------------------------------------------------------------------
+template <int DQK, int DV>
+__global__ void __launch_bounds__(256) attn16_kernel(const float *__restrict__ qkv, int ldq, float *__restrict__ out, int ldo,
+                                                     long long n_seq)
+{
+    constexpr int H = 4;
+    constexpr int W = 2 * H * DQK + H * DV;  // 192
+    constexpr int LD = W + 4;                // padded row: conflict-free 128-bit row reads
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *t = smem + warp * 16 * LD;
+    const int i = lane & 15, hh = lane >> 4;
+    const float scale = rsqrtf(static_cast<float>(DQK)) * 1.4426950408889634f;  // 1/sqrt(d) * log2(e)
+
+    for (long long s = blockIdx.x * 8ll + warp; s < n_seq; s += gridDim.x * 8ll) {
+        const float *src = qkv + s * 16 * ldq;
+        __syncwarp();
+        for (int e = lane; e < 16 * (W / 4); e += 32) {
+            const int r = e / (W / 4), c = e % (W / 4);
+            *reinterpret_cast<float4 *>(t + r * LD + c * 4) = *reinterpret_cast<const float4 *>(src + r * ldq + c * 4);
+        }
+        __syncwarp();
+        float o[2][DV];
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+            const int h = 2 * hh + hq;
+            float q[DQK];
+#pragma unroll
+            for (int c = 0; c < DQK; c += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(t + i * LD + h * DQK + c);
+                q[c] = v.x, q[c + 1] = v.y, q[c + 2] = v.z, q[c + 3] = v.w;
+            }
+            float sc[16];
+            float m = -FLT_MAX;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int c = 0; c < DQK; c += 4) {
+                    const float4 k = *reinterpret_cast<const float4 *>(t + j * LD + H * DQK + h * DQK + c);
+                    a = fmaf(q[c], k.x, a), a = fmaf(q[c + 1], k.y, a), a = fmaf(q[c + 2], k.z, a), a = fmaf(q[c + 3], k.w, a);
+                }
+                sc[j] = a * scale;
+                m = fmaxf(m, sc[j]);
+            }
+            float l = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                sc[j] = exp2f(sc[j] - m);
+                l += sc[j];
+            }
+            const float inv = 1.0f / l;
+#pragma unroll
+            for (int d = 0; d < DV; ++d) o[hq][d] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float pj = sc[j] * inv;
+#pragma unroll
+                for (int d = 0; d < DV; d += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(t + j * LD + 2 * H * DQK + h * DV + d);
+                    o[hq][d] = fmaf(pj, v.x, o[hq][d]), o[hq][d + 1] = fmaf(pj, v.y, o[hq][d + 1]);
+                    o[hq][d + 2] = fmaf(pj, v.z, o[hq][d + 2]), o[hq][d + 3] = fmaf(pj, v.w, o[hq][d + 3]);
+                }
+            }
+        }
+        __syncwarp();  // everyone is done reading q/k/v: reuse the tile (columns 0 .. H*DV-1) as the output stage
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq)
+#pragma unroll
+            for (int d = 0; d < DV; d += 4)
+                *reinterpret_cast<float4 *>(t + i * LD + (2 * hh + hq) * DV + d) =
+                    make_float4(o[hq][d], o[hq][d + 1], o[hq][d + 2], o[hq][d + 3]);
+        __syncwarp();
+        float *dst = out + s * 16 * ldo;
+        for (int e = lane; e < 16 * (H * DV / 4); e += 32) {
+            const int r = e / (H * DV / 4), c = e % (H * DV / 4);
+            *reinterpret_cast<float4 *>(dst + r * ldo + c * 4) = *reinterpret_cast<const float4 *>(t + r * LD + c * 4);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attn_dense: block = 64 queries of one (cloud, head), 128 threads = (query, half of the value dims);
+// keys / values staged through shared memory 64 at a time, online softmax.
+// ------------------------------------------------------------------------------------------------
+template <int DQK, int DV>
+__global__ void __launch_bounds__(128) attn_dense_kernel(const float *__restrict__ qkv, int ldq, float *__restrict__ out,
+                                                         int ldo, int S)
+{
+    constexpr int H = 4, KT = 64, DH = DV / 2;
+    __shared__ __align__(16) float sk[KT * DQK];
+    __shared__ __align__(16) float sv[KT * DV];
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int qi = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int half = threadIdx.x >> 6;
+    const bool live = qi < S;
+    const float *base = qkv + static_cast<size_t>(b) * S * ldq;
+    const float scale = rsqrtf(static_cast<float>(DQK)) * 1.4426950408889634f;
+
+    float q[DQK];
+    {
+        const float *qp = base + static_cast<size_t>(live ? qi : 0) * ldq + h * DQK;
+#pragma unroll
+        for (int c = 0; c < DQK; c += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(qp + c);
+            q[c] = v.x * scale, q[c + 1] = v.y * scale, q[c + 2] = v.z * scale, q[c + 3] = v.w * scale;
+        }
+    }
+    float acc[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+    float m = -FLT_MAX, l = 0.f;
+
+    for (int k0 = 0; k0 < S; k0 += KT) {
+        const int nk = min(KT, S - k0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < KT * (DQK / 4); e += 128) {
+            const int r = e / (DQK / 4), c = e % (DQK / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nk) v = *reinterpret_cast<const float4 *>(base + static_cast<size_t>(k0 + r) * ldq + H * DQK + h * DQK + c * 4);
+            *reinterpret_cast<float4 *>(sk + r * DQK + c * 4) = v;
+        }
+        for (int e = threadIdx.x; e < KT * (DV / 4); e += 128) {
+            const int r = e / (DV / 4), c = e % (DV / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nk) v = *reinterpret_cast<const float4 *>(base + static_cast<size_t>(k0 + r) * ldq + 2 * H * DQK + h * DV + c * 4);
+            *reinterpret_cast<float4 *>(sv + r * DV + c * 4) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j0 = 0; j0 < KT; j0 += 16) {
+            if (j0 >= nk) break;
+            float sc[16];
+            float tm = m;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int c = 0; c < DQK; c += 4) {
+                    const float4 k = *reinterpret_cast<const float4 *>(sk + (j0 + j) * DQK + c);
+                    a = fmaf(q[c], k.x, a), a = fmaf(q[c + 1], k.y, a), a = fmaf(q[c + 2], k.z, a), a = fmaf(q[c + 3], k.w, a);
+                }
+                sc[j] = (j0 + j < nk) ? a : -FLT_MAX;
+                tm = fmaxf(tm, sc[j]);
+            }
+            const float corr = exp2f(m - tm);
+            m = tm;
+            l *= corr;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc[d] *= corr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float pj = (j0 + j < nk) ? exp2f(sc[j] - m) : 0.f;
+                l += pj;
+#pragma unroll
+                for (int d = 0; d < DH; d += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(sv + (j0 + j) * DV + half * DH + d);
+                    acc[d] = fmaf(pj, v.x, acc[d]), acc[d + 1] = fmaf(pj, v.y, acc[d + 1]);
+                    acc[d + 2] = fmaf(pj, v.z, acc[d + 2]), acc[d + 3] = fmaf(pj, v.w, acc[d + 3]);
+                }
+            }
+        }
+    }
+    if (live) {
+        const float inv = 1.0f / l;
+        float *dst = out + (static_cast<size_t>(b) * S + qi) * ldo + h * DV + half * DH;
+#pragma unroll
+        for (int d = 0; d < DH; d += 4)
+            *reinterpret_cast<float4 *>(dst + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// colpool: out_max[b, c] = max_s in[b, s, c]; out_mean[b, c] = mean_s in[b, s, c]   (either may be null)
+// block = 32 columns x 8 row lanes
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colpool_kernel(const float *__restrict__ in, int ld, int S, int N,
+                                                      float *__restrict__ out_max, float *__restrict__ out_mean, int ldo)
+{
+    __shared__ float smax[8][33], ssum[8][33];
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;
+    float mx = -FLT_MAX, sm = 0.f;
+    if (c < N) {
+        const float *p = in + static_cast<size_t>(b) * S * ld + c;
+        for (int s = ry; s < S; s += 8) {
+            const float v = p[static_cast<size_t>(s) * ld];
+            mx = fmaxf(mx, v);
+            sm += v;
+        }
+    }
+    smax[ry][threadIdx.x & 31] = mx;
+    ssum[ry][threadIdx.x & 31] = sm;
+    __syncthreads();
+    if (ry == 0 && c < N) {
+#pragma unroll
+        for (int r = 1; r < 8; ++r) {
+            mx = fmaxf(mx, smax[r][threadIdx.x]);
+            sm += ssum[r][threadIdx.x];
+        }
+        if (out_max) out_max[static_cast<size_t>(b) * ldo + c] = mx;
+        if (out_mean) out_mean[static_cast<size_t>(b) * ldo + c] = sm / static_cast<float>(S);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vis_embed_finish: x0[t] = [e (F) | gmax[b] (F) | pts[t] (IN)]  (width D = 2F + IN <= 256), ln = LayerNorm(x0)
+// e is already in x0[:, :F]; one warp per token, 8 columns per lane.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vis_embed_finish_kernel(float *__restrict__ x0, int ld, const float *__restrict__ gmax,
+                                                               int ldg, const float *__restrict__ pts, int ldp, int F, int IN,
+                                                               int S, long long T, const float *__restrict__ g,
+                                                               const float *__restrict__ bta, float eps, float *__restrict__ ln,
+                                                               int ldl)
+{
+    const int D = 2 * F + IN;
+    const int lane = threadIdx.x & 31;
+    const long long t = blockIdx.x * 8ll + (threadIdx.x >> 5);
+    if (t >= T) return;
+    const int b = static_cast<int>(t / S);
+    float v[8];
+    float sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = lane + 32 * e;
+        float y = 0.f;
+        if (c < F) y = x0[t * ld + c];
+        else if (c < 2 * F) y = gmax[static_cast<size_t>(b) * ldg + c - F];
+        else if (c < D) y = pts[t * ldp + c - 2 * F];
+        v[e] = y;
+        if (c >= F && c < D) x0[t * ld + c] = y;
+        sum += y;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const float mean = sum / static_cast<float>(D);
+    float var = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = lane + 32 * e;
+        if (c < D) {
+            const float d = v[e] - mean;
+            var = fmaf(d, d, var);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+    const float rstd = 1.0f / sqrtf(var / static_cast<float>(D) + eps);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = lane + 32 * e;
+        if (c < D) ln[t * ldl + c] = (v[e] - mean) * rstd * g[c] + bta[c];
+    }
+}
+
+// bias_out[b, n] = bias[n] + sum_k W[n, k] * g[b, k];   one warp per (b, n)
+__global__ void __launch_bounds__(256) bias_gemv_kernel(const float *__restrict__ W, int ldw, const float *__restrict__ bias,
+                                                        const float *__restrict__ g, int ldg, int N, int K,
+                                                        float *__restrict__ out, int B)
+{
+    const int lane = threadIdx.x & 31;
+    const long long w = blockIdx.x * 8ll + (threadIdx.x >> 5);
+    if (w >= static_cast<long long>(B) * N) return;
+    const int b = static_cast<int>(w / N), n = static_cast<int>(w % N);
+    float a = 0.f;
+    for (int k = lane; k < K; k += 32) a = fmaf(W[static_cast<size_t>(n) * ldw + k], g[static_cast<size_t>(b) * ldg + k], a);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+    if (lane == 0) out[static_cast<size_t>(b) * N + n] = a + bias[n];
+}
+
+}  // namespace
+
+// ---- host launchers ----------------------------------------------------------------------------
+int knn16(const float *x, const float *pc, int *idx, float *dist, int B, int Q, int N, cudaStream_t stream)
+{
+    MAC_REQUIRE(x && pc && idx, "null tensor pointer");
+    MAC_REQUIRE(B > 0 && Q > 0 && N >= kKnn, "kNN needs B > 0, Q > 0 and at least 16 cloud points (got B=%d Q=%d N=%d)", B, Q, N);
+    MAC_REQUIRE((reinterpret_cast<uintptr_t>(idx) & 15u) == 0, "idx must be 16-byte aligned");
+    dim3 grid((Q + 127) / 128, B);
+    knn16_kernel<<<grid, 128, 0, stream>>>(x, pc, idx, dist, Q, N);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+int embed_first(const float *in, int ld_in, int in_dim, const float *pc, const float *x, const int *idx, int Q, int N,
+                const float *w, const float *b, int inner, int append, float *out, int ldo, long long T,
+                cudaStream_t stream)
+{
+    MAC_REQUIRE(w && b && out && T > 0, "null tensor pointer");
+    MAC_REQUIRE(in_dim == 3 || in_dim == 4, "embedding input dimension must be 3 or 4");
+    MAC_REQUIRE(inner + (append ? in_dim : 0) <= 128 && ldo % 4 == 0 && ldo >= (inner + (append ? in_dim : 0) + 3) / 4 * 4,
+                "embedding width %d does not fit the 128-column staging row (ldo=%d)", inner, ldo);
+    const bool gather = idx != nullptr;
+    MAC_REQUIRE(gather ? (pc && x && in_dim == 3) : (in != nullptr), "embedding input missing");
+    EmbedParams p{};
+    p.in = in, p.ld_in = ld_in, p.pc = pc, p.x = x, p.idx = idx, p.Q = Q, p.N = N;
+    p.w = w, p.b = b, p.inner = inner, p.append = append, p.out = out, p.ldo = ldo, p.T = T;
+    const size_t smem = static_cast<size_t>(inner) * (in_dim + 1) * sizeof(float);
+    const long long want = (T * 32 + 255) / 256;
+    const int grid = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+    if (gather) embed_first_kernel<3, true><<<grid, 256, smem, stream>>>(p);
+    else if (in_dim == 3) embed_first_kernel<3, false><<<grid, 256, smem, stream>>>(p);
+    else embed_first_kernel<4, false><<<grid, 256, smem, stream>>>(p);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+int attn16(const float *qkv, int ldq, float *out, int ldo, long long n_seq, int dqk, int dv, cudaStream_t stream)
+{
+    MAC_REQUIRE(qkv && out && n_seq > 0, "null tensor pointer");
+    MAC_REQUIRE(dqk == 8 && dv == 32, "attn16 is built for 4 heads of (8, 32) dims");
+    MAC_REQUIRE(ldq % 4 == 0 && ldo % 4 == 0, "attention rows must be 16-byte aligned");
+    constexpr int LD = 2 * 4 * 8 + 4 * 32 + 4;
+    const size_t smem = 8 * 16 * LD * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        MAC_CUDA(cudaFuncSetAttribute(attn16_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = true;
+    }
+    const long long want = (n_seq + 7) / 8;
+    const int grid = static_cast<int>(want < 148 * 2 ? want : 148 * 2);
+    attn16_kernel<8, 32><<<grid, 256, smem, stream>>>(qkv, ldq, out, ldo, n_seq);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+int attn_dense(const float *qkv, int ldq, float *out, int ldo, int B, int S, int dqk, int dv, cudaStream_t stream)
+{
+    MAC_REQUIRE(qkv && out && B > 0 && S > 0, "null tensor pointer");
+    MAC_REQUIRE(ldq % 4 == 0 && ldo % 4 == 0, "attention rows must be 16-byte aligned");
+    dim3 grid((S + 63) / 64, 4, B);
+    if (dqk == 8 && dv == 32) attn_dense_kernel<8, 32><<<grid, 128, 0, stream>>>(qkv, ldq, out, ldo, S);
+    else if (dqk == 16 && dv == 64) attn_dense_kernel<16, 64><<<grid, 128, 0, stream>>>(qkv, ldq, out, ldo, S);
+    else {
+        set_error("attn_dense is built for 4 heads of (8, 32) or (16, 64) dims, got (%d, %d)", dqk, dv);
+        return MAC_ERR_UNSUPPORTED;
+    }
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+int colpool(const float *in, int ld, int B, int S, int N, float *out_max, float *out_mean, int ldo, cudaStream_t stream)
+{
+    MAC_REQUIRE(in && (out_max || out_mean) && B > 0 && S > 0 && N > 0, "null tensor pointer");
+    dim3 grid((N + 31) / 32, B);
+    colpool_kernel<<<grid, 256, 0, stream>>>(in, ld, S, N, out_max, out_mean, ldo);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+int vis_embed_finish(float *x0, int ld, const float *gmax, int ldg, const float *pts, int ldp, int F, int in_dim, int S,
+                     long long T, const float *g, const float *b, float eps, float *ln, int ldl, cudaStream_t stream)
+{
+    MAC_REQUIRE(x0 && gmax && pts && g && b && ln && T > 0, "null tensor pointer");
+    MAC_REQUIRE(2 * F + in_dim <= 256, "embedding width %d exceeds 256", 2 * F + in_dim);
+    vis_embed_finish_kernel<<<static_cast<unsigned>((T + 7) / 8), 256, 0, stream>>>(x0, ld, gmax, ldg, pts, ldp, F, in_dim, S, T, g,
+                                                                                   b, eps, ln, ldl);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+int bias_gemv(const float *W, int ldw, const float *bias, const float *g, int ldg, int N, int K, float *out, int B,
+              cudaStream_t stream)
+{
+    MAC_REQUIRE(W && bias && g && out && B > 0, "null tensor pointer");
+    const long long warps = static_cast<long long>(B) * N;
+    bias_gemv_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, stream>>>(W, ldw, bias, g, ldg, N, K, out, B);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+}  // namespace mac
+
+extern "C" int mac_knn16_f32(const float *x, const float *pc, int *idx, float *dist, int B, int Q, int N, void *stream)
+{
+    return mac::knn16(x, pc, idx, dist, B, Q, N, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,265 @@
+// Forward passes of SconeOcc and SconeVis assembled from the tensor-core linear layer (linear.cu) and the
+// CUDA-core kernels of pointnet.cu.  Reference: networks/SconeOcc.py:250-347, networks/SconeVis.py:121-162,
+// networks/Attention.py.  Everything is enqueued on one stream; the caller owns weights and workspace.
+#include "nets.h"
+#include "tc_common.h"
+
+namespace mac {
+
+namespace {
+
+constexpr float kLnEps = 1e-5f;  // torch.nn.LayerNorm default
+constexpr int kHeads = 4;
+
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct Bump {  // carve the caller's workspace
+    unsigned char *base;
+    size_t used, cap;
+    float *f(size_t n)
+    {
+        float *p = reinterpret_cast<float *>(base + used);
+        used += align256(n * sizeof(float));
+        return p;
+    }
+};
+
+int lin(const float *X, int ldx, const mac_linear_w_t &w, const float *bias, float *out, int ldo, long long M, int act,
+        const float *res, int ldr, float *ln_out, int ldl, const float *g, const float *b, int pool, cudaStream_t st)
+{
+    return linear_forward(X, ldx, w.hi, w.lo, w.ldw, bias, out, ldo, static_cast<int>(M), w.N, w.K, act, res, ldr, ln_out, ldl,
+                          g, b, kLnEps, pool, st);
+}
+
+// Buffers of one encoder stack over T tokens of width D.
+struct EncBufs {
+    float *x, *x2, *ln, *qkv, *att, *ff;
+    int ldqkv;
+};
+size_t enc_floats_per_token(int D, int qkv_n) { return 3 * static_cast<size_t>(D) + qkv_n + D + 2 * D; }
+
+EncBufs carve_enc(Bump &ws, long long T, int D, int qkv_n)
+{
+    EncBufs e;
+    e.x = ws.f(T * D), e.x2 = ws.f(T * D), e.ln = ws.f(T * D);
+    e.qkv = ws.f(T * qkv_n), e.att = ws.f(T * D), e.ff = ws.f(T * 2 * D);
+    e.ldqkv = qkv_n;
+    return e;
+}
+
+// On entry e.x = residual stream, e.ln = norm1 of encoder 0 applied to it.  On exit e.ln = final LayerNorm(x).
+// seq16: attention over groups of 16 tokens; otherwise over B clouds of S tokens.
+int encoder_stack(const mac_encoder_w_t *enc, int n_enc, const float *fin_g, const float *fin_b, EncBufs &e, long long T,
+                  int D, int dqk, int dv, bool seq16, int B, int S, cudaStream_t st)
+{
+    for (int i = 0; i < n_enc; ++i) {
+        const mac_encoder_w_t &w = enc[i];
+        if (int rc = lin(e.ln, D, w.qkv, w.qkv.bias, e.qkv, e.ldqkv, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+            return rc;
+        if (seq16) {
+            if (int rc = attn16(e.qkv, e.ldqkv, e.att, D, T / 16, dqk, dv, st)) return rc;
+        } else {
+            if (int rc = attn_dense(e.qkv, e.ldqkv, e.att, D, B, S, dqk, dv, st)) return rc;
+        }
+        // x2 = x + out(att);  ln = norm2(x2)
+        if (int rc = lin(e.att, D, w.out, w.out.bias, e.x2, D, T, MAC_LIN_NONE, e.x, D, e.ln, D, w.ln2_g, w.ln2_b, 0, st)) return rc;
+        if (int rc = lin(e.ln, D, w.ff1, w.ff1.bias, e.ff, 2 * D, T, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+            return rc;
+        // x = x2 + ff2(ff);  ln = next norm1 (or the final norm)
+        const float *ng = (i + 1 < n_enc) ? enc[i + 1].ln1_g : fin_g;
+        const float *nb = (i + 1 < n_enc) ? enc[i + 1].ln1_b : fin_b;
+        if (int rc = lin(e.ff, 2 * D, w.ff2, w.ff2.bias, e.x, D, T, MAC_LIN_NONE, e.x2, D, e.ln, D, ng, nb, 0, st)) return rc;
+    }
+    return MAC_OK;
+}
+
+int check_pct(const mac_pct_w_t &w)
+{
+    MAC_REQUIRE(w.n_enc >= 1 && w.n_enc <= MAC_MAX_ENCODERS, "bad encoder count %d", w.n_enc);
+    MAC_REQUIRE(w.d_model == 128 && w.dqk == 8 && w.dv == 32, "PCTransformer kernels are built for d_model 128, 4 heads of (8, 32)");
+    MAC_REQUIRE(w.in_dim == 3 && w.inner + w.in_dim == w.d_model && w.emb2.K == w.d_model && w.emb2.N == w.d_model,
+                "PCTransformer embedding must be 3 -> %d -> %d (+3 input)", w.inner, w.inner);
+    return MAC_OK;
+}
+
+}  // namespace
+
+}  // namespace mac
+
+using namespace mac;
+
+// ------------------------------------------------------------------------------------------------
+// SconeVis
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t mac_sconevis_workspace_bytes(int B, int S)
+{
+    const size_t T = static_cast<size_t>(B) * S;
+    size_t n = 0;
+    n += align256(T * 128 * 4);                       // h
+    n += align256(static_cast<size_t>(B) * 128 * 4);  // gmax
+    n += 6 * align256(T * 512 * 4);                   // encoder buffers (upper bound: D = 256, qkv 384, ff 512)
+    n += align256(T * 256 * 4) + align256(T * 128 * 4);
+    return n + 4096;
+}
+
+extern "C" int mac_sconevis_forward_f32(const mac_sconevis_w_t *w, const float *pts, const float *vh, float *out, int B, int S,
+                                        void *workspace, size_t workspace_bytes, void *stream)
+{
+    MAC_REQUIRE(w && pts && vh && out && workspace, "null pointer");
+    MAC_REQUIRE(B > 0 && S > 0, "B and S must be positive (got %d, %d)", B, S);
+    MAC_REQUIRE(w->d_model == 256 && w->dqk == 16 && w->dv == 64 && w->in_dim == 4 && 2 * w->inner + w->in_dim == 256,
+                "SconeVis kernels are built for pts_dim 4, d_model 256, 4 heads of (16, 64)");
+    MAC_REQUIRE(w->n_enc >= 1 && w->n_enc <= MAC_MAX_ENCODERS, "bad encoder count %d", w->n_enc);
+    MAC_REQUIRE(w->fc1.N == 192 && w->fc2.K == 256 && w->fc3.N == MAC_N_HARMONICS, "unexpected SconeVis head shape");
+    if (workspace_bytes < mac_sconevis_workspace_bytes(B, S)) {
+        set_error("workspace too small: need %zu bytes, got %zu", mac_sconevis_workspace_bytes(B, S), workspace_bytes);
+        return MAC_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long T = static_cast<long long>(B) * S;
+    const int D = 256, F = w->inner;
+    Bump ws{static_cast<unsigned char *>(workspace), 0, workspace_bytes};
+    float *h = ws.f(T * 128);
+    float *gmax = ws.f(static_cast<size_t>(B) * 128);
+    EncBufs e = carve_enc(ws, T, D, w->enc[0].qkv.N);
+    float *hb = ws.f(T * 256);
+    float *h2 = ws.f(T * 128);
+
+    // embedding: h = GELU(W1 p + b1); e = W2 h + b2 -> x[:, :F]; global max; concat + norm1
+    if (int rc = embed_first(pts, 4, 4, nullptr, nullptr, nullptr, 0, 0, w->emb1_w, w->emb1_b, F, 0, h, 128, T, st)) return rc;
+    if (int rc = lin(h, 128, w->emb2, w->emb2.bias, e.x, D, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st)) return rc;
+    if (int rc = colpool(e.x, D, B, S, F, gmax, nullptr, 128, st)) return rc;
+    if (int rc = vis_embed_finish(e.x, D, gmax, 128, pts, 4, F, 4, S, T, w->enc[0].ln1_g, w->enc[0].ln1_b, kLnEps, e.ln, D, st))
+        return rc;
+    if (int rc = encoder_stack(w->enc, w->n_enc, w->ln_g, w->ln_b, e, T, D, w->dqk, w->dv, false, B, S, st)) return rc;
+    // head: fc1 + GELU | view harmonics -> fc2 + GELU -> fc3
+    if (int rc = lin(e.ln, D, w->fc1, w->fc1.bias, hb, 256, T, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st)) return rc;
+    MAC_CUDA(cudaMemcpy2DAsync(hb + 192, 256 * sizeof(float), vh, 64 * sizeof(float), 64 * sizeof(float), T,
+                               cudaMemcpyDeviceToDevice, st));
+    if (int rc = lin(hb, 256, w->fc2, w->fc2.bias, h2, 128, T, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st)) return rc;
+    if (int rc = lin(h2, 128, w->fc3, w->fc3.bias, out, 64, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st)) return rc;
+    return MAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SconeOcc
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kFeat = 3 * 256 + 512 + 64;  // [3 x local | x embedding | view harmonics] = 1344
+
+struct OccLayout {
+    size_t global_T, local_T;
+};
+}  // namespace
+
+extern "C" size_t mac_sconeocc_workspace_bytes(int B, int Sg, int chunk)
+{
+    const size_t Tg = static_cast<size_t>(B) * Sg, Tl = static_cast<size_t>(chunk) * 16;
+    const size_t Tm = Tg > Tl ? Tg : Tl;
+    size_t n = 0;
+    n += align256(Tm * 128 * 4);                                  // h
+    n += 3 * align256(Tm * 128 * 4) + align256(Tm * 192 * 4) + align256(Tm * 128 * 4) + align256(Tm * 256 * 4);  // encoder
+    n += align256(Tg * 256 * 4);                                  // global linear0 output
+    n += 2 * align256(static_cast<size_t>(B) * 512 * 4);          // global feature, per-cloud bias
+    n += align256(static_cast<size_t>(chunk) * 16 * 4);           // kNN indices
+    n += align256(static_cast<size_t>(chunk) * kFeat * 4);        // feature rows
+    n += align256(static_cast<size_t>(chunk) * 128 * 4) + align256(static_cast<size_t>(chunk) * 256 * 4);  // x embedding
+    n += align256(static_cast<size_t>(chunk) * 512 * 4) + align256(static_cast<size_t>(chunk) * 256 * 4) +
+         align256(static_cast<size_t>(chunk) * 4 * 4);            // head
+    return n + 4096;
+}
+
+extern "C" int mac_sconeocc_forward_f32(const mac_sconeocc_w_t *w, const float *pc_global, int Sg, const float *const *pc_scale,
+                                        const int *n_scale_pts, const float *x, const float *vh, float *out, int B, int Q,
+                                        int chunk, void *workspace, size_t workspace_bytes, void *stream)
+{
+    MAC_REQUIRE(w && pc_global && pc_scale && n_scale_pts && x && vh && out && workspace, "null pointer");
+    MAC_REQUIRE(B > 0 && Q > 0 && Sg > 0 && chunk > 0, "B, Q, Sg, chunk must be positive");
+    MAC_REQUIRE(w->n_scale == 3, "SconeOcc kernels are built for 3 neighbourhood scales");
+    if (int rc = check_pct(w->global_pct)) return rc;
+    for (int s = 0; s < w->n_scale; ++s) {
+        if (int rc = check_pct(w->local_pct[s])) return rc;
+        MAC_REQUIRE(w->local_pct[s].linear0.N == 128, "local feature must be 2 x 128");
+        MAC_REQUIRE(pc_scale[s] && n_scale_pts[s] >= 16, "scale %d: kNN needs at least 16 cloud points (got %d)", s, n_scale_pts[s]);
+    }
+    MAC_REQUIRE(w->global_pct.linear0.N == 256 && w->global_dim == 512 && w->lin1.K == kFeat && w->lin1.N == 512 &&
+                    w->xemb1_n == 128 && w->xemb3.N == 512 && w->lin3.N == 1,
+                "unexpected SconeOcc head shape");
+    if (workspace_bytes < mac_sconeocc_workspace_bytes(B, Sg, chunk)) {
+        set_error("workspace too small: need %zu bytes, got %zu", mac_sconeocc_workspace_bytes(B, Sg, chunk), workspace_bytes);
+        return MAC_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int D = 128;
+    const long long Tg = static_cast<long long>(B) * Sg, Tl = static_cast<long long>(chunk) * 16;
+    const long long Tm = Tg > Tl ? Tg : Tl;
+    Bump ws{static_cast<unsigned char *>(workspace), 0, workspace_bytes};
+    float *h = ws.f(Tm * 128);
+    EncBufs e = carve_enc(ws, Tm, D, 192);
+    float *g0 = ws.f(Tg * 256);
+    float *gfeat = ws.f(static_cast<size_t>(B) * 512);
+    float *bias1 = ws.f(static_cast<size_t>(B) * 512);
+    int *idx = reinterpret_cast<int *>(ws.f(static_cast<size_t>(chunk) * 16));
+    float *feat = ws.f(static_cast<size_t>(chunk) * kFeat);
+    float *xe1 = ws.f(static_cast<size_t>(chunk) * 128);
+    float *xe2 = ws.f(static_cast<size_t>(chunk) * 256);
+    float *l1 = ws.f(static_cast<size_t>(chunk) * 512);
+    float *l2 = ws.f(static_cast<size_t>(chunk) * 256);
+    float *l3 = ws.f(static_cast<size_t>(chunk) * 4);
+
+    // ---- global point-cloud feature (SconeOcc.py:269-275, PCTransformer.forward :105-130) ----
+    {
+        const mac_pct_w_t &g = w->global_pct;
+        if (int rc = embed_first(pc_global, 3, 3, nullptr, nullptr, nullptr, 0, 0, g.emb1_w, g.emb1_b, g.inner, 1, h, 128, Tg, st)) return rc;
+        if (int rc = lin(h, 128, g.emb2, g.emb2.bias, e.x, D, Tg, MAC_LIN_NONE, nullptr, 0, e.ln, D, g.enc[0].ln1_g, g.enc[0].ln1_b, 0, st))
+            return rc;
+        if (int rc = encoder_stack(g.enc, g.n_enc, g.ln_g, g.ln_b, e, Tg, D, g.dqk, g.dv, false, B, Sg, st)) return rc;
+        if (int rc = lin(e.ln, D, g.linear0, g.linear0.bias, g0, 256, Tg, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+            return rc;
+        if (int rc = colpool(g0, 256, B, Sg, 256, gfeat, gfeat + 256, 512, st)) return rc;
+        // the global feature is the same for every query of a cloud: fold it into the bias of linear1
+        if (int rc = bias_gemv(w->lin1_wg, w->lin1_wg_ld, w->lin1_b, gfeat, 512, 512, 512, bias1, B, st)) return rc;
+    }
+
+    // ---- per query: 3 neighbourhood transformers + x embedding + head (SconeOcc.py:293-342) ----
+    for (int b = 0; b < B; ++b) {
+        for (int q0 = 0; q0 < Q; q0 += chunk) {
+            const int nq = Q - q0 < chunk ? Q - q0 : chunk;
+            const long long T = static_cast<long long>(nq) * 16;
+            const float *xq = x + (static_cast<size_t>(b) * Q + q0) * 3;
+            for (int s = 0; s < w->n_scale; ++s) {
+                const mac_pct_w_t &l = w->local_pct[s];
+                const int N = n_scale_pts[s];
+                const float *pcs = pc_scale[s] + static_cast<size_t>(b) * N * 3;
+                if (int rc = knn16(xq, pcs, idx, nullptr, 1, nq, N, st)) return rc;
+                if (int rc = embed_first(nullptr, 0, 3, pcs, xq, idx, nq, N, l.emb1_w, l.emb1_b, l.inner, 1, h, 128, T, st)) return rc;
+                if (int rc = lin(h, 128, l.emb2, l.emb2.bias, e.x, D, T, MAC_LIN_NONE, nullptr, 0, e.ln, D, l.enc[0].ln1_g,
+                                 l.enc[0].ln1_b, 0, st))
+                    return rc;
+                if (int rc = encoder_stack(l.enc, l.n_enc, l.ln_g, l.ln_b, e, T, D, l.dqk, l.dv, true, 0, 0, st)) return rc;
+                if (int rc = lin(e.ln, D, l.linear0, l.linear0.bias, feat + s * 256, kFeat, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0,
+                                 nullptr, nullptr, 16, st))
+                    return rc;
+            }
+            if (int rc = embed_first(xq, 3, 3, nullptr, nullptr, nullptr, 0, 0, w->xemb1_w, w->xemb1_b, w->xemb1_n, 0, xe1, 128, nq, st))
+                return rc;
+            if (int rc = lin(xe1, 128, w->xemb2, w->xemb2.bias, xe2, 256, nq, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+                return rc;
+            if (int rc = lin(xe2, 256, w->xemb3, w->xemb3.bias, feat + 768, kFeat, nq, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr,
+                             nullptr, 0, st))
+                return rc;
+            MAC_CUDA(cudaMemcpy2DAsync(feat + 1280, kFeat * sizeof(float), vh + (static_cast<size_t>(b) * Q + q0) * 64,
+                                       64 * sizeof(float), 64 * sizeof(float), nq, cudaMemcpyDeviceToDevice, st));
+            if (int rc = lin(feat, kFeat, w->lin1, bias1 + static_cast<size_t>(b) * 512, l1, 512, nq, MAC_LIN_GELU, nullptr, 0, nullptr,
+                             0, nullptr, nullptr, 0, st))
+                return rc;
+            if (int rc = lin(l1, 512, w->lin2, w->lin2.bias, l2, 256, nq, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+                return rc;
+            if (int rc = lin(l2, 256, w->lin3, w->lin3.bias, l3, 4, nq, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+                return rc;
+            MAC_CUDA(cudaMemcpy2DAsync(out + static_cast<size_t>(b) * Q + q0, sizeof(float), l3, 4 * sizeof(float), sizeof(float), nq,
+                                       cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return MAC_OK;
+}

@@ -1,0 +1,163 @@
+"""Pack the parameters of SconeOcc / SconeVis modules into the C structs of include/macarons_b200.h
+(mac_linear_w_t, mac_encoder_w_t, mac_pct_w_t, mac_sconeocc_w_t, mac_sconevis_w_t).
+
+Packing = TF32 hi/lo split of every Linear weight (packing.split_tf32), K padded to a multiple of 4 floats,
+w_q / w_k / w_v stacked into one (qk+qk+v, d) matrix, and Embedding.linear2 of the PCTransformers extended with
+identity rows so that the GEMM also concatenates the raw input (Attention.py:125).  A pack is cached on the
+module and rebuilt when any parameter's storage or version counter changes (load_state_dict, .to(), training).
+"""
+import ctypes
+
+import torch
+
+from . import packing
+
+MAX_ENCODERS, MAX_SCALES = 4, 4
+_fp = ctypes.c_void_p
+
+
+class LinearW(ctypes.Structure):
+    _fields_ = [("hi", _fp), ("lo", _fp), ("bias", _fp), ("N", ctypes.c_int), ("K", ctypes.c_int), ("ldw", ctypes.c_int)]
+
+
+class EncoderW(ctypes.Structure):
+    _fields_ = [("ln1_g", _fp), ("ln1_b", _fp), ("ln2_g", _fp), ("ln2_b", _fp),
+                ("qkv", LinearW), ("out", LinearW), ("ff1", LinearW), ("ff2", LinearW)]
+
+
+class PctW(ctypes.Structure):
+    _fields_ = [("emb1_w", _fp), ("emb1_b", _fp), ("in_dim", ctypes.c_int), ("inner", ctypes.c_int),
+                ("emb2", LinearW), ("n_enc", ctypes.c_int), ("d_model", ctypes.c_int), ("dqk", ctypes.c_int),
+                ("dv", ctypes.c_int), ("enc", EncoderW * MAX_ENCODERS), ("ln_g", _fp), ("ln_b", _fp),
+                ("linear0", LinearW)]
+
+
+class SconeOccW(ctypes.Structure):
+    _fields_ = [("global_pct", PctW), ("n_scale", ctypes.c_int), ("local_pct", PctW * MAX_SCALES),
+                ("xemb1_w", _fp), ("xemb1_b", _fp), ("xemb1_n", ctypes.c_int), ("xemb2", LinearW), ("xemb3", LinearW),
+                ("lin1_wg", _fp), ("lin1_wg_ld", ctypes.c_int), ("global_dim", ctypes.c_int), ("lin1_b", _fp),
+                ("lin1", LinearW), ("lin2", LinearW), ("lin3", LinearW)]
+
+
+class SconeVisW(ctypes.Structure):
+    _fields_ = [("emb1_w", _fp), ("emb1_b", _fp), ("in_dim", ctypes.c_int), ("inner", ctypes.c_int),
+                ("emb2", LinearW), ("n_enc", ctypes.c_int), ("d_model", ctypes.c_int), ("dqk", ctypes.c_int),
+                ("dv", ctypes.c_int), ("enc", EncoderW * MAX_ENCODERS), ("ln_g", _fp), ("ln_b", _fp),
+                ("fc1", LinearW), ("fc2", LinearW), ("fc3", LinearW)]
+
+
+class _Packer:
+    def __init__(self):
+        self.keep = []   # tensors the structs point into
+
+    def plain(self, t):
+        t = t.detach().to(torch.float32).contiguous()
+        self.keep.append(t)
+        return t.data_ptr()
+
+    def linear(self, weight, bias, dst):
+        pk = packing.PackedLinear(weight, bias)
+        self.keep.append(pk)
+        dst.hi, dst.lo = pk.hi.data_ptr(), pk.lo.data_ptr()
+        dst.bias = 0 if pk.bias is None else pk.bias.data_ptr()
+        dst.N, dst.K, dst.ldw = pk.N, pk.K, pk.ldw
+
+    def encoder(self, enc, dst):
+        if not enc.FF or enc.n_heads != 4:
+            raise NotImplementedError("the fused encoder supports FF=True and 4 heads")
+        dst.ln1_g, dst.ln1_b = self.plain(enc.norm1.weight), self.plain(enc.norm1.bias)
+        dst.ln2_g, dst.ln2_b = self.plain(enc.norm2.weight), self.plain(enc.norm2.bias)
+        m = enc.mhsa
+        self.linear(torch.cat((m.w_q.weight, m.w_k.weight, m.w_v.weight), dim=0),
+                    torch.cat((m.w_q.bias, m.w_k.bias, m.w_v.bias), dim=0), dst.qkv)
+        self.linear(m.out.weight, m.out.bias, dst.out)
+        self.linear(enc.ff.linear1.weight, enc.ff.linear1.bias, dst.ff1)
+        self.linear(enc.ff.linear2.weight, enc.ff.linear2.bias, dst.ff2)
+
+    def encoders(self, encoders, dst):
+        if len(encoders) > MAX_ENCODERS:
+            raise NotImplementedError("at most %d encoders" % MAX_ENCODERS)
+        dst.n_enc = len(encoders)
+        e0 = encoders[0]
+        dst.d_model, dst.dqk, dst.dv = e0.embedding_dim, e0.mhsa.qk_dim_per_head, e0.mhsa.v_dim_per_head
+        for i, enc in enumerate(encoders):
+            self.encoder(enc, dst.enc[i])
+
+    def pct(self, pct, dst):
+        emb = pct.embedding
+        if not (emb.concatenate_input and not emb.global_feature and emb.additional_feature_dim == 0 and emb.gelu):
+            raise NotImplementedError("the fused PCTransformer supports the default embedding (gelu, concatenated input)")
+        dst.emb1_w, dst.emb1_b = self.plain(emb.linear1.weight), self.plain(emb.linear1.bias)
+        dst.in_dim, dst.inner = emb.input_dim, emb.inner_dim
+        # [e | x] = [[W2, 0], [0, I]] [h | x] + [b2 | 0]
+        feat, inner, d_in = emb.feature_dim, emb.inner_dim, emb.input_dim
+        w2 = emb.linear2.weight.detach()
+        aug = torch.zeros(feat + d_in, inner + d_in, dtype=torch.float32, device=w2.device)
+        aug[:feat, :inner] = w2
+        aug[feat:, inner:] = torch.eye(d_in, device=w2.device)
+        b2 = torch.cat((emb.linear2.bias.detach(), torch.zeros(d_in, device=w2.device)))
+        self.linear(aug, b2, dst.emb2)
+        self.encoders(pct.encoders, dst)
+        dst.ln_g, dst.ln_b = self.plain(pct.norm.weight), self.plain(pct.norm.bias)
+        self.linear(pct.linear0.weight, pct.linear0.bias, dst.linear0)
+
+
+def _fingerprint(module):
+    return tuple((p.data_ptr(), p._version, p.device.index) for p in module.parameters())
+
+
+def _cached(module, build):
+    fp = _fingerprint(module)
+    cache = module.__dict__.get("_mac_pack")
+    if cache is None or cache[0] != fp:
+        cache = (fp,) + build()
+        module.__dict__["_mac_pack"] = cache
+    return cache[1]
+
+
+def pack_sconevis(vis):
+    """-> SconeVisW (kept alive, with its tensors, on the module)."""
+    def build():
+        emb = vis.embedding
+        if not (vis.use_view_state and vis.view_state_mode == "end" and vis.use_global_feature and not vis.alt
+                and emb.concatenate_input and emb.gelu and emb.additional_feature_dim == 0):
+            raise NotImplementedError("the fused SconeVis forward supports the reference's default architecture "
+                                      "(global feature, view harmonics concatenated at the end, alt=False)")
+        pk, w = _Packer(), SconeVisW()
+        w.emb1_w, w.emb1_b = pk.plain(emb.linear1.weight), pk.plain(emb.linear1.bias)
+        w.in_dim, w.inner = emb.input_dim, emb.inner_dim
+        pk.linear(emb.linear2.weight, emb.linear2.bias, w.emb2)
+        pk.encoders(vis.encoders, w)
+        w.ln_g, w.ln_b = pk.plain(vis.norm.weight), pk.plain(vis.norm.bias)
+        pk.linear(vis.fc1.weight, vis.fc1.bias, w.fc1)
+        pk.linear(vis.fc2.weight, vis.fc2.bias, w.fc2)
+        pk.linear(vis.fc3.weight, vis.fc3.bias, w.fc3)
+        return w, pk
+    return _cached(vis, build)
+
+
+def pack_sconeocc(occ):
+    """-> SconeOccW (kept alive, with its tensors, on the module)."""
+    def build():
+        if occ.n_scale != 3 or not occ.offset or not occ.gelu or occ.k_for_knn != 16:
+            raise NotImplementedError("the fused SconeOcc forward supports n_scale=3, k_for_knn=16, offset=True, gelu")
+        pk, w = _Packer(), SconeOccW()
+        pk.pct(occ.global_transformer, w.global_pct)
+        w.n_scale = occ.n_scale
+        for s, lt in enumerate(occ.local_transformers):
+            pk.pct(lt, w.local_pct[s])
+        xe = occ.x_embedding
+        w.xemb1_w, w.xemb1_b, w.xemb1_n = pk.plain(xe.linear1.weight), pk.plain(xe.linear1.bias), xe.linear1.out_features
+        pk.linear(xe.linear2.weight, xe.linear2.bias, w.xemb2)
+        pk.linear(xe.linear3.weight, xe.linear3.bias, w.xemb3)
+        g = occ.global_feature_dim
+        w1 = occ.linear1.weight.detach()
+        wg = w1[:, :g].to(torch.float32).contiguous()
+        pk.keep.append(wg)
+        w.lin1_wg, w.lin1_wg_ld, w.global_dim = wg.data_ptr(), wg.stride(0), g
+        w.lin1_b = pk.plain(occ.linear1.bias)
+        pk.linear(w1[:, g:], None, w.lin1)
+        pk.linear(occ.linear2.weight, occ.linear2.bias, w.lin2)
+        pk.linear(occ.linear3.weight, occ.linear3.bias, w.lin3)
+        return w, pk
+    return _cached(occ, build)

@@ -8,7 +8,7 @@ import torch
 from torch import nn
 
 from .Attention import Embedding, Encoder
-from .. import ops
+from .. import netpack, ops
 from ..utility.spherical_harmonics import clear_spherical_harmonics_cache
 
 
@@ -50,20 +50,13 @@ class SconeVis(nn.Module):
 
     # ---- a6: per-point SH coefficients of the visibility-gain function (SconeVis.py:121-162) ----
     def forward(self, pts, mask=None, view_harmonics=None):
-        n_clouds, seq_len = pts.shape[0], pts.shape[1]
-        start = self.use_view_state and self.view_state_mode == "start"
-        x = self.embedding(pts, additional_feature=view_harmonics) if start else self.embedding(pts)
-        for encoder in self.encoders:
-            x = encoder(x, mask=mask)
-        x = self.norm(x)
-        if self.alt:
-            x = self.nonlinear1(self.fc1(torch.cat((x, view_harmonics), dim=-1)))
-        else:
-            x = self.nonlinear1(self.fc1(x))
-            if self.use_view_state and self.view_state_mode == "end":
-                x = torch.cat((x, view_harmonics), dim=-1)
-        x = self.fc3(self.nonlinear2(self.fc2(x)))
-        return x.view(n_clouds, seq_len, self.n_harmonics)
+        """pts (B,S,4) [xyz, occupancy], view_harmonics (B,S,64) -> (B,S,64): one fused CUDA forward
+        (csrc/scone_nets.cu: tcgen05 linear layers + dense attention kernel)."""
+        if mask is not None:
+            raise NotImplementedError("attention masks are never used on the NBV path (SURVEY.md A.4)")
+        if view_harmonics is None:
+            raise NameError("view_harmonics is required (use_view_state=True, view_state_mode='end')")
+        return ops.sconevis_forward(netpack.pack_sconevis(self), pts, view_harmonics)
 
     # ---- a3/a4: SH integration over candidate cameras: CUDA kernel --------------------------------
     def compute_visibilities(self, pts, harmonics, X_cam):

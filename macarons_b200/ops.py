@@ -190,3 +190,84 @@ def linear(x, packed, act=ACT_NONE, residual=None, out=None, ln=None, pool=0, K=
             0 if ln is None else ln[0].data_ptr(), 0 if ln is None else ln[1].data_ptr(),
             0.0 if ln is None else float(ln[2]), int(pool), _stream_ptr(dev)))
     return (out, ln_out) if ln is not None else out
+
+
+# ---- kNN and the fused network forwards (csrc/pointnet.cu, csrc/scone_nets.cu) --------------------
+_net_workspaces = {}
+
+
+def _net_workspace(device, nbytes):
+    key = (device.index, _stream_ptr(device))
+    ws = _net_workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _net_workspaces[key] = ws
+    return ws
+
+
+def knn16(x, pc, return_dists=True):
+    """x (B,Q,3), pc (B,N,3) -> idx (B,Q,16) int32 nearest first [, dists (B,Q,16)]."""
+    _require_cuda_f32("x", x)
+    _require_cuda_f32("pc", pc)
+    if x.dim() != 3 or pc.dim() != 3 or x.shape[-1] != 3 or pc.shape[-1] != 3 or x.shape[0] != pc.shape[0]:
+        raise ValueError("x must be (B,Q,3) and pc (B,N,3)")
+    x, pc = x.contiguous(), pc.contiguous()
+    B, Q, _ = x.shape
+    N = pc.shape[1]
+    idx = torch.empty((B, Q, 16), dtype=torch.int32, device=x.device)
+    dists = torch.empty((B, Q, 16), dtype=torch.float32, device=x.device) if return_dists else None
+    if Q > 0:
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().mac_knn16_f32(x.data_ptr(), pc.data_ptr(), idx.data_ptr(), _ptr(dists), B, Q, N,
+                                                 _stream_ptr(x.device)))
+    return (idx, dists) if return_dists else idx
+
+
+def sconevis_forward(w, pts, view_harmonics):
+    """Packed weights (netpack.SconeVisW), pts (B,S,4), view_harmonics (B,S,64) -> (B,S,64)."""
+    import ctypes
+    _require_cuda_f32("pts", pts)
+    _require_cuda_f32("view_harmonics", view_harmonics)
+    B, S, D = pts.shape
+    if D != 4 or tuple(view_harmonics.shape) != (B, S, N_HARMONICS):
+        raise ValueError("pts must be (B,S,4) and view_harmonics (B,S,64); got %s, %s"
+                         % (tuple(pts.shape), tuple(view_harmonics.shape)))
+    pts, view_harmonics = pts.contiguous(), view_harmonics.contiguous()
+    out = torch.empty((B, S, N_HARMONICS), dtype=torch.float32, device=pts.device)
+    if B * S == 0:
+        return out
+    lib = _lib.load()
+    with torch.cuda.device(pts.device):
+        ws = _net_workspace(pts.device, lib.mac_sconevis_workspace_bytes(B, S))
+        _lib.check(lib.mac_sconevis_forward_f32(ctypes.byref(w), pts.data_ptr(), view_harmonics.data_ptr(), out.data_ptr(),
+                                                B, S, ws.data_ptr(), ws.numel(), _stream_ptr(pts.device)))
+    return out
+
+
+def sconeocc_forward(w, pc_global, pc_scales, x, view_harmonics, chunk=16384):
+    """Packed weights (netpack.SconeOccW); pc_global (B,Sg,3); pc_scales: list of 3 (B,N_s,3) clouds;
+    x (B,Q,3); view_harmonics (B,Q,64) -> (B,Q,1)."""
+    import ctypes
+    for name, t in (("pc_global", pc_global), ("x", x), ("view_harmonics", view_harmonics)):
+        _require_cuda_f32(name, t)
+    B, Q, _ = x.shape
+    if tuple(view_harmonics.shape) != (B, Q, N_HARMONICS) or pc_global.shape[0] != B or pc_global.shape[2] != 3:
+        raise ValueError("inconsistent SconeOcc input shapes")
+    pc_global, x, view_harmonics = pc_global.contiguous(), x.contiguous(), view_harmonics.contiguous()
+    pc_scales = [p.contiguous() for p in pc_scales]
+    for p in pc_scales:
+        _require_cuda_f32("pc_scale", p)
+    out = torch.empty((B, Q, 1), dtype=torch.float32, device=x.device)
+    if Q == 0:
+        return out
+    chunk = int(min(chunk, Q))
+    Sg = pc_global.shape[1]
+    ptrs = (ctypes.c_void_p * len(pc_scales))(*[p.data_ptr() for p in pc_scales])
+    counts = (ctypes.c_int * len(pc_scales))(*[p.shape[1] for p in pc_scales])
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        ws = _net_workspace(x.device, lib.mac_sconeocc_workspace_bytes(B, Sg, chunk))
+        _lib.check(lib.mac_sconeocc_forward_f32(ctypes.byref(w), pc_global.data_ptr(), Sg, ptrs, counts, x.data_ptr(),
+                                                view_harmonics.data_ptr(), out.data_ptr(), B, Q, chunk, ws.data_ptr(),
+                                                ws.numel(), _stream_ptr(x.device)))
+    return out

@@ -29,7 +29,10 @@ import synth  # noqa: E402
 from macarons.networks.SconeVis import SconeVis  # noqa: E402  (the reference's)
 from macarons.networks.Macarons import Macarons  # noqa: E402
 from macarons.utility import scone_utils as ref_su  # noqa: E402
+from macarons.networks.SconeOcc import SconeOcc  # noqa: E402
+from macarons.utility import utils as ref_utils  # noqa: E402
 from oracle import sampling as o_sampling  # noqa: E402
+from oracle import scone_nets as o_nets  # noqa: E402
 from oracle import sh_cov as o_cov  # noqa: E402
 from oracle import view_state as o_vs  # noqa: E402
 
@@ -134,9 +137,62 @@ def sampling_goldens():
          res=res, inverse=inv, res_h_checksum=res_h.double().sum(dim=0))
 
 
+# (name, B, S, seed, row stride of the stored output)
+SCONEVIS_CASES = [("sconevis_small", 2, 300, 401, 1), ("sconevis_2048", 1, 2048, 402, 8)]
+# (name, B, N, Q, seed, grid)
+SCONEOCC_CASES = [("sconeocc_small", 2, 700, 150, 501, False), ("sconeocc_cfg1", 1, 2048, 4096, 502, True)]
+NET_WEIGHT_SEED = 5
+
+
+def nets_goldens():
+    """SconeVis.forward, SconeOcc.forward, get_knn_points and compute_occupancy_probability of the reference,
+    with weights from synth.seeded_state_dict loaded through load_state_dict (state_dict compatibility)."""
+    vis = SconeVis()
+    vis_sd = synth.seeded_state_dict(vis.state_dict(), NET_WEIGHT_SEED)
+    vis.load_state_dict(vis_sd)
+    vis.eval()
+    with torch.no_grad():
+        for name, B, S, seed, stride in SCONEVIS_CASES:
+            pts, vh = synth.sconevis_inputs(B, S, seed)
+            out = vis(pts, view_harmonics=vh)
+            must_equal(out, o_nets.scone_vis_forward(vis_sd, pts, vh), name)
+            save(name, B=B, S=S, seed=seed, weight_seed=NET_WEIGHT_SEED, weights_digest=synth.state_dict_digest(vis_sd),
+                 input_digest=digest(pts, vh), row_stride=stride, harmonics=out[:, ::stride])
+    occ = SconeOcc()
+    occ_sd = synth.seeded_state_dict(occ.state_dict(), NET_WEIGHT_SEED)
+    occ.load_state_dict(occ_sd)
+    occ.eval()
+    with torch.no_grad():
+        for name, B, N, Q, seed, grid in SCONEOCC_CASES:
+            pc, x, vh = synth.sconeocc_inputs(B, N, Q, seed, grid=grid)
+            torch.manual_seed(seed)
+            out = occ(pc, x, vh)
+            torch.manual_seed(seed)
+            must_equal(out, o_nets.scone_occ_forward(occ_sd, pc, x, vh), name)
+            pts_k, d_k, i_k = ref_utils.get_knn_points(x, pc, 16)
+            p2, d2, i2 = o_nets.knn_points(x, pc, 16)
+            must_equal(pts_k, p2, name + " knn points")
+            must_equal(i_k, i2, name + " knn idx")
+            save(name, B=B, N=N, Q=Q, seed=seed, grid=int(grid), weight_seed=NET_WEIGHT_SEED,
+                 weights_digest=synth.state_dict_digest(occ_sd), input_digest=digest(pc, x, vh), occupancy=out,
+                 knn_idx=i_k.to(torch.int32) if Q <= 512 else i_k[:, ::16].to(torch.int32), knn_dist=d_k if Q <= 512 else d_k[:, ::16])
+        # chunked inference (utility/scone_utils.py:965-998): 3 forward calls with fresh sub-samples each
+        pc, x, vh = synth.sconeocc_inputs(1, 600, 250, 503)
+        torch.manual_seed(503)
+        out = ref_su.compute_occupancy_probability(occ, pc, x, vh, max_points_per_pass=100)
+        torch.manual_seed(503)
+        must_equal(out, o_nets.compute_occupancy_probability(occ_sd, pc, x, vh, max_points_per_pass=100), "chunked occ")
+        save("sconeocc_chunked", B=1, N=600, Q=250, seed=503, max_points_per_pass=100, weight_seed=NET_WEIGHT_SEED,
+             weights_digest=synth.state_dict_digest(occ_sd), input_digest=digest(pc, x, vh), occupancy=out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--nets-only" in sys.argv:
+        nets_goldens()
+        raise SystemExit(0)
     covgain_goldens()
     view_state_goldens()
     sampling_goldens()
+    nets_goldens()
     print("all oracle == reference checks passed (bitwise)")

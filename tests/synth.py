@@ -39,3 +39,94 @@ def view_state_inputs(B, P, V, seed, radius=1.5):
     pts = torch.rand(B, P, 4, generator=gen) - 0.5
     X_view = sphere_cameras(V, radius, gen)
     return pts.contiguous(), X_view.contiguous()
+
+
+# ---- networks (rows a6-a9) -----------------------------------------------------------------------
+def seeded_state_dict(template, seed):
+    """Deterministic weights for a SconeOcc / SconeVis `state_dict()` template (name -> tensor), independent of
+    module construction order: every tensor is drawn from its own generator keyed by (seed, name).
+    Scales follow the reference initialisers (utility/scone_utils.py:260-289, 399-428): Xavier-normal for
+    w_q / w_k / w_v, Kaiming-normal (relu) for the other Linear weights, default-Linear-style uniform biases;
+    LayerNorm weights / biases are perturbed away from (1, 0) so that they are actually exercised."""
+    import zlib
+    out = {}
+    for name in sorted(template):
+        shape = tuple(template[name].shape)
+        gen = torch.Generator(device="cpu").manual_seed((int(seed) * 1000003 + zlib.crc32(name.encode())) % (2 ** 31))
+        is_norm = ".norm" in name or name.startswith("norm")
+        if len(shape) == 2:
+            fan_out, fan_in = shape
+            if name.split(".")[-2] in ("w_q", "w_k", "w_v"):
+                std = math.sqrt(2.0 / (fan_in + fan_out))
+            else:
+                std = math.sqrt(2.0 / fan_in)
+            t = torch.randn(shape, generator=gen) * std
+        elif is_norm and name.endswith("weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=gen)
+        elif is_norm:
+            t = 0.1 * torch.randn(shape, generator=gen)
+        else:
+            fan_in = template[name[:-4] + "weight"].shape[1]
+            t = (torch.rand(shape, generator=gen) * 2 - 1) / math.sqrt(fan_in)
+        out[name] = t.to(torch.float32)
+    return out
+
+
+def state_dict_digest(sd):
+    import hashlib
+    h = hashlib.sha256()
+    for name in sorted(sd):
+        h.update(name.encode())
+        h.update(sd[name].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()[:16]
+
+
+def airplane_surface(n, gen):
+    """'Airplane-like' closed surface samples (ellipsoid fuselage + two flat wing boxes + tail fin), centred and
+    scaled so that the bounding-box diagonal is 1 (like adjust_mesh_diagonally, utility/utils.py:633-648)."""
+    n_f, n_w, n_t = n // 2, n // 3, n - n // 2 - n // 3
+    v = torch.randn(n_f, 3, generator=gen)
+    v = v / v.norm(dim=-1, keepdim=True)
+    fus = v * torch.tensor([0.12, 0.12, 1.0])
+    wing = (torch.rand(n_w, 3, generator=gen) - 0.5) * torch.tensor([1.6, 0.03, 0.35])
+    face = torch.randint(0, 2, (n_w,), generator=gen).float() * 2 - 1
+    wing[:, 1] = face * 0.015
+    tail = (torch.rand(n_t, 3, generator=gen) - 0.5) * torch.tensor([0.03, 0.4, 0.25])
+    tail[:, 0] = (torch.randint(0, 2, (n_t,), generator=gen).float() * 2 - 1) * 0.015
+    tail = tail + torch.tensor([0.0, 0.25, -0.85])
+    pts = torch.cat((fus, wing, tail))
+    lo, hi = pts.min(dim=0)[0], pts.max(dim=0)[0]
+    return ((pts - (lo + hi) / 2) / (hi - lo).norm()).contiguous()
+
+
+def sconeocc_inputs(B, N, Q, seed, grid=False):
+    """pc (B,N,3): the part of an airplane-like surface facing a sphere camera; x (B,Q,3) queries (a regular grid in
+    [-0.5,0.5]^3 when `grid`, Q must be a cube); view_harmonics (B,Q,64) ~ N(0, 0.3^2)."""
+    gen = torch.Generator(device="cpu").manual_seed(int(seed))
+    pcs = []
+    for _ in range(B):
+        surf = airplane_surface(8 * N, gen)
+        cam = sphere_cameras(1, 1.5, gen)[0]
+        order = torch.argsort((surf * cam).sum(-1), descending=True)   # the half facing the camera
+        keep = order[:4 * N][torch.randperm(4 * N, generator=gen)[:N]]
+        pcs.append(surf[keep])
+    pc = torch.stack(pcs)
+    if grid:
+        n = round(Q ** (1 / 3))
+        assert n ** 3 == Q
+        ax = (torch.arange(n, dtype=torch.float32) + 0.5) / n - 0.5
+        g = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1).view(1, Q, 3)
+        x = g.expand(B, Q, 3).contiguous()
+    else:
+        x = torch.rand(B, Q, 3, generator=gen) - 0.5
+    vh = 0.3 * torch.randn(B, Q, 64, generator=gen)
+    return pc.contiguous(), x, vh.contiguous()
+
+
+def sconevis_inputs(B, S, seed):
+    """pts (B,S,4) = xyz ~ U[-0.5,0.5]^3 + occupancy ~ U[0.1,1]; view_harmonics (B,S,64) ~ N(0, 0.3^2)."""
+    gen = torch.Generator(device="cpu").manual_seed(int(seed))
+    pts = torch.rand(B, S, 4, generator=gen) - 0.5
+    pts[..., 3] = 0.1 + 0.9 * torch.rand(B, S, generator=gen)
+    vh = 0.3 * torch.randn(B, S, 64, generator=gen)
+    return pts.contiguous(), vh.contiguous()

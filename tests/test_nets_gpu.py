@@ -1,0 +1,136 @@
+"""GPU parity of the fused network forwards (rows a6-a9): SconeVis.forward, SconeOcc.forward, kNN and the chunked
+occupancy inference, CUDA path through the C ABI vs the oracle on identical seeded inputs / weights / RNG state, and
+vs the fixtures generated from the unmodified reference.
+
+Tolerance: the linear layers evaluate every product with the 3-term TF32 split (exact to 2^-22) and accumulate in
+fp32, attention / LayerNorm / GELU run in fp32 -> the CUDA path is an fp32 implementation with a different
+summation order.  Stated bound: |cuda - reference| <= NET_RTOL * max|reference| over the output tensor."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from conftest import load_golden
+from macarons_b200 import ops
+from macarons_b200.networks.SconeOcc import SconeOcc
+from macarons_b200.networks.SconeVis import SconeVis
+from macarons_b200.utility import scone_utils
+from oracle import scone_nets as o_nets
+
+pytestmark = pytest.mark.gpu
+
+NET_RTOL = 1e-4
+
+
+def _load(module, g, dev):
+    sd = synth.seeded_state_dict(module.state_dict(), int(g["weight_seed"]))
+    assert synth.state_dict_digest(sd) == str(g["weights_digest"])
+    module.load_state_dict(sd)          # reference key names and shapes
+    return module.to(dev).eval(), sd
+
+
+@pytest.mark.parametrize("name", ["sconevis_small", "sconevis_2048"])
+def test_sconevis_forward(name, cuda_device):
+    g = load_golden(name)
+    vis, sd = _load(SconeVis(), g, cuda_device)
+    pts, vh = synth.sconevis_inputs(int(g["B"]), int(g["S"]), int(g["seed"]))
+    n0 = ops.launch_count()
+    with torch.no_grad():
+        got = vis(pts.to(cuda_device), view_harmonics=vh.to(cuda_device)).cpu()
+        want = o_nets.scone_vis_forward(sd, pts, vh)
+    assert ops.launch_count() > n0, "the CUDA kernels did not run"
+    assert got.shape == want.shape == (int(g["B"]), int(g["S"]), 64)
+    scale = want.abs().max().item()
+    assert (got - want).abs().max().item() <= NET_RTOL * scale
+    stride = int(g["row_stride"])
+    assert np.abs(got[:, ::stride].numpy() - g["harmonics"]).max() <= NET_RTOL * scale
+
+
+def _knn_agreement(occ, pc, x, seed, dev):
+    """(B,Q) mask of the queries whose 16-neighbour SETS agree, at all 3 scales, between the CUDA kNN and the
+    reference's cdist + topk.  The reference evaluates distances as sqrt(|x|^2 + |y|^2 - 2 x.y) in fp32 (torch.cdist's
+    matmul path), whose cancellation error (~1e-5) re-orders neighbours that are closer than that to the 16th place;
+    for those few queries the reference's own neighbour set is rounding noise and the outputs legitimately differ."""
+    torch.manual_seed(seed)
+    _, scale_idx = occ.draw_subsamples(pc.shape[1])
+    clouds = [pc]
+    for idx in scale_idx:
+        clouds.append(clouds[-1][:, idx])
+    agree = torch.ones(x.shape[:2], dtype=torch.bool)
+    for cloud in clouds:
+        got = ops.knn16(x.to(dev), cloud.to(dev), return_dists=False).cpu().long().sort(-1)[0]
+        want = o_nets.knn_points(x, cloud, 16)[2].sort(-1)[0]
+        agree &= (got == want).all(-1)
+    return agree
+
+
+@pytest.mark.parametrize("name", ["sconeocc_small", "sconeocc_cfg1"])
+def test_sconeocc_forward(name, cuda_device):
+    g = load_golden(name)
+    occ, sd = _load(SconeOcc(), g, cuda_device)
+    pc, x, vh = synth.sconeocc_inputs(int(g["B"]), int(g["N"]), int(g["Q"]), int(g["seed"]), grid=bool(g["grid"]))
+    torch.manual_seed(int(g["seed"]))
+    with torch.no_grad():
+        got = occ(pc.to(cuda_device), x.to(cuda_device), vh.to(cuda_device)).cpu()
+    torch.manual_seed(int(g["seed"]))
+    with torch.no_grad():
+        want = o_nets.scone_occ_forward(sd, pc, x, vh)
+    assert got.shape == want.shape == (int(g["B"]), int(g["Q"]), 1)
+    agree = _knn_agreement(occ, pc, x, int(g["seed"]), cuda_device)
+    assert agree.float().mean().item() >= 0.99
+    scale = max(1.0, want.abs().max().item())
+    err = (got - want).abs()[..., 0]
+    assert err[agree].max().item() <= NET_RTOL * scale
+    assert err.max().item() <= 0.05 * scale          # a swapped 16th neighbour moves the output only slightly
+    gerr = torch.from_numpy(np.abs(got.numpy() - g["occupancy"]))[..., 0]
+    assert gerr[agree].max().item() <= NET_RTOL * scale
+    # the 0.1 occupancy threshold of sample_proxy_points selects the same points
+    assert ((got > 0.1) != (want > 0.1))[..., 0][agree].float().mean().item() <= 1e-3
+
+
+def test_sconeocc_is_chunk_invariant(cuda_device):
+    g = load_golden("sconeocc_small")
+    occ, _ = _load(SconeOcc(), g, cuda_device)
+    pc, x, vh = synth.sconeocc_inputs(2, 700, 150, 501)
+    outs = []
+    for chunk in (16384, 64, 37):
+        occ.queries_per_pass = chunk
+        torch.manual_seed(1)
+        with torch.no_grad():
+            outs.append(occ(pc.to(cuda_device), x.to(cuda_device), vh.to(cuda_device)).cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_chunked_occupancy_probability(cuda_device):
+    g = load_golden("sconeocc_chunked")
+    occ, sd = _load(SconeOcc(), g, cuda_device)
+    pc, x, vh = synth.sconeocc_inputs(1, int(g["N"]), int(g["Q"]), int(g["seed"]))
+    torch.manual_seed(int(g["seed"]))
+    with torch.no_grad():
+        got = scone_utils.compute_occupancy_probability(occ, pc.to(cuda_device), x.to(cuda_device), vh.to(cuda_device),
+                                                        max_points_per_pass=int(g["max_points_per_pass"])).cpu()
+    assert got.shape == g["occupancy"].shape
+    err = np.abs(got.numpy() - g["occupancy"])[0, :, 0]
+    # (queries whose 16th neighbour is a rounding-level tie in the reference may differ, see _knn_agreement)
+    assert np.quantile(err, 0.98) <= NET_RTOL * max(1.0, np.abs(g["occupancy"]).max())
+    assert err.max() <= 0.05 * max(1.0, np.abs(g["occupancy"]).max())
+
+
+@pytest.mark.parametrize("B,Q,N", [(2, 150, 700), (1, 1000, 16), (1, 4099, 2500)])
+def test_knn16_matches_oracle(B, Q, N, cuda_device):
+    gen = torch.Generator().manual_seed(B * 1000 + Q + N)
+    x = torch.rand(B, Q, 3, generator=gen) - 0.5
+    pc = torch.rand(B, N, 3, generator=gen) - 0.5
+    idx, dist = ops.knn16(x.to(cuda_device), pc.to(cuda_device))
+    idx, dist = idx.cpu().long(), dist.cpu()
+    _, want_d, want_i = o_nets.knn_points(x, pc, 16)
+    # distances: cdist evaluates |x|^2 + |y|^2 - 2xy (cancellation ~1e-7 abs on squared distances), the kernel sums
+    # (x-y)^2 directly
+    assert (dist - want_d).abs().max().item() <= 3e-5
+    assert torch.all(dist[..., 1:] >= dist[..., :-1])        # nearest first
+    # exact distances of the returned neighbours are the 16 smallest (ties / rounding at the 16th place excepted)
+    d_all = torch.cdist(x.double(), pc.double())
+    assert (dist.double() - d_all.gather(-1, idx)).abs().max().item() <= 2e-7   # the kernel's distances are exact fp32
+    kth = d_all.topk(16, dim=-1, largest=False)[0][..., -1:]
+    assert torch.all(d_all.gather(-1, idx) <= kth + 1e-6)
+    assert (idx.sort(-1)[0] != want_i.sort(-1)[0]).any(-1).float().mean().item() <= 2e-3
