@@ -221,6 +221,39 @@ int mac_sconeocc_forward_f32(const mac_sconeocc_w_t *w, const float *pc_global, 
                              const int *n_scale_pts, const float *x, const float *view_harmonics, float *out, int B,
                              int Q, int chunk, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * View state (rows a10-a12): spherical histogram of the visited cameras around every point and its
+ * projection onto the SH basis.
+ *   mac_view_state_f32      compute_view_state, /root/reference/macarons/utility/scone_utils.py:799-860
+ *       pts (B, P, pts_dim) [xyz read], views (V, 3) -> state (B, P, n_elev*n_azim) fp32 in {0, 1};
+ *       bin arithmetic (fp32 asin / acos, torch.remainder based floor division, Python `-n // 2` clamps and
+ *       the final wrap modulo n_elev*n_azim) follows the reference statement by statement.
+ *   mac_view_harmonics_f32  compute_view_harmonics, scone_utils.py:934-960
+ *       state (B, P, n_bins), base (64, n_bins) and h_polar (n_bins) from get_all_harmonics_under_degree
+ *       -> out (B, P, 64) = sum_j state_j * base_kj * sin(polar_j) * polar_step * azim_step.
+ *   mac_gather_bins_f32     the bin permutation of move_view_state_to_view_space, scone_utils.py:928:
+ *       out[b, p, j] = in[b, p, index[j]].
+ * ------------------------------------------------------------------------------------------- */
+int mac_view_state_f32(const float *pts, int pts_dim, const float *views, float *state, int B, int P, int V, int n_elev,
+                       int n_azim, void *stream);
+int mac_view_harmonics_f32(const float *state, const float *base, const float *h_polar, float *out, int B, int P,
+                           int n_elev, int n_azim, void *stream);
+int mac_gather_bins_f32(const float *in, const int *index, float *out, int B, int P, int n_bins, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * sample_proxy_points (row a13), /root/reference/macarons/utility/scone_utils.py:1030-1076, with the uniforms
+ * supplied by the caller (the reference draws torch.rand(n_sample, 1) on the tensors' device):
+ *   X (N, 3), preds (N, 1), view_harmonics (N, 64), u (n_sample) in [0, 1)
+ *   -> res (<= n_sample, 4) [xyz, occupancy] and res_harmonics (<= n_sample, 64) of the UNIQUE picked points in
+ *      ascending index order, inverse (n_sample) int64 position of every draw in that list,
+ *      counts[0] = points with occupancy > min_occ, counts[1] = number of unique picks (rows of res that are valid).
+ * Outputs must be sized for n_sample rows; n_sample <= 4096.
+ * ------------------------------------------------------------------------------------------- */
+size_t mac_sample_proxy_workspace_bytes(int N);
+int mac_sample_proxy_points_f32(const float *X, const float *preds, const float *view_harmonics, const float *u, int N,
+                                int n_sample, float min_occ, float *res, float *res_harmonics, long long *inverse,
+                                int *counts, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Number of kernel launches the library has enqueued since load (for bench.py's gpu_launches). */
 unsigned long long mac_launch_count(void);
 

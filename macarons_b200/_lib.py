@@ -68,6 +68,19 @@ SYMBOLS["mac_sconeocc_forward_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_
                                                       ctypes.c_void_p])
 
 
+SYMBOLS["mac_view_state_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p])
+SYMBOLS["mac_view_harmonics_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
+                                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p])
+SYMBOLS["mac_gather_bins_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_void_p])
+SYMBOLS["mac_sample_proxy_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_int])
+SYMBOLS["mac_sample_proxy_points_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
+                                                         ctypes.c_int, ctypes.c_float, _c_float_p, _c_float_p,
+                                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                         ctypes.c_size_t, ctypes.c_void_p])
+
+
 class MacaronsB200Error(RuntimeError):
     pass
 

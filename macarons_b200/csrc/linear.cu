@@ -12,13 +12,18 @@
 //   * fp32 accuracy: TF32 keeps 10 mantissa bits, far too few for parity with the fp32 reference, so
 //     every product is evaluated as  x_hi w_hi + x_lo w_hi + x_hi w_lo  (x = x_hi + x_lo with both parts
 //     exactly representable in TF32; the dropped x_lo w_lo term is 2^-22 relative).  W is split once when
-//     the weights are packed; X is split in shared memory by the epilogue warps while they wait
-//     (element-wise, hence oblivious to the swizzle), fenced to the async proxy and handed to the MMA
-//     warp through a second mbarrier.
-//   * epilogue: the 4 epilogue warps read their 32 TMEM lanes (one output row per thread) with
-//     tcgen05.ld and apply bias -> activation (ReLU / exact GELU) -> residual add; optionally they also
-//     emit LayerNorm(Y) for the next layer (two-pass statistics over the TMEM row, the tile spans all N)
-//     or max / mean pool groups of 16 consecutive rows (the 16-token neighbourhoods of SconeOcc).
+//     the weights are packed; X is split in shared memory by 4 dedicated warps (element-wise, hence
+//     oblivious to the swizzle), fenced to the async proxy and handed to the MMA warp through a second
+//     mbarrier.
+//   * persistent CTAs (one per SM) walk the tiles; two TMEM accumulators let the TMA / split / MMA warps work
+//     on tile t+1 while the 4 epilogue warps drain tile t.
+//   * epilogue: one output row per thread, 32 columns at a time: tcgen05.ld -> bias -> activation (ReLU /
+//     exact GELU) -> residual add.  Residual chunks arrive by cp.async into a padded staging buffer and the
+//     results leave through the same buffer, so that every global access is a full 128-byte row segment
+//     (row-per-thread accesses straight to global memory made the first version 10x slower).  Optionally
+//     the rows are also LayerNorm-ed for the next layer (y is parked in TMEM with tcgen05.st; mean, centred
+//     variance and the normalised output are three cheap TMEM passes; the tile spans all N) or max / mean
+//     pooled over groups of 16 consecutive rows (the 16-token neighbourhoods of SconeOcc).
 #include <cuda.h>
 #include <math.h>
 
@@ -66,11 +71,15 @@ constexpr int kBM = 128;
 constexpr int kBK = 32;             // fp32 per k-chunk: one 128-byte swizzle span
 constexpr int kUmmaK = 8;           // tf32 MMA depth (32 bytes)
 constexpr int kATileBytes = kBM * kBK * 4;
-constexpr int kThreads = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 split + epilogue
+constexpr int kThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-5 X split, warps 6-9 epilogue
 constexpr int kMaxStages = 4;
+constexpr int kEpiLd = 36;          // epilogue staging row stride (floats): 32 columns + 4 pad, conflict-free float4 rows
+constexpr int kEpiBufBytes = kBM * kEpiLd * 4;
+constexpr int kEpiBar = 1;          // named barrier of the 128 epilogue threads
 
 struct LinearParams {
     int M, N, K;
+    int n_tiles_m, n_tiles_n;
     const float *bias;
     float *out;
     int ldo;
@@ -97,11 +106,16 @@ template <int BN, bool SPLIT>
 struct Cfg {
     static constexpr int kBTileBytes = BN * kBK * 4;
     static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kATileBytes + kBTileBytes);
-    static constexpr int kStages = (200 * 1024 / kStageBytes) < kMaxStages ? (200 * 1024 / kStageBytes) : kMaxStages;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kEpiBufs = (BN <= 128) ? 2 : 1;
+    static constexpr int kBudget = 226 * 1024 - 1024 - 512 - kEpiBufs * kEpiBufBytes;
+    static constexpr int kStages = (kBudget / kStageBytes) < kMaxStages ? (kBudget / kStageBytes) : kMaxStages;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBufs * kEpiBufBytes + 1024 /*alignment*/ + 512 /*barriers*/;
     static constexpr uint32_t kTxBytes = kATileBytes + (SPLIT ? 2 : 1) * kBTileBytes;
+    static_assert(kStages >= 2, "need at least a double-buffered operand pipeline");
 };
 
+// Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA and MMA warps run ahead of the
+// epilogue through a ring of operand stages and two TMEM accumulators.
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
@@ -111,12 +125,14 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes);
+    float *ebuf = reinterpret_cast<float *>(smem + C::kStages * C::kStageBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes + C::kEpiBufs * kEpiBufBytes);
     uint64_t *full = bars;                       // TMA landed
     uint64_t *ready = bars + kMaxStages;         // X split done (SPLIT only)
     uint64_t *empty = bars + 2 * kMaxStages;     // MMAs that read the stage have completed
-    uint64_t *acc_full = bars + 3 * kMaxStages;  // accumulator complete
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * kMaxStages + 1);
+    uint64_t *acc_full = bars + 3 * kMaxStages;  // [2] accumulator complete
+    uint64_t *acc_empty = acc_full + 2;          // [2] accumulator drained by the epilogue
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     auto a_hi = [&](int s) { return smem + s * C::kStageBytes; };
     auto b_hi = [&](int s) { return smem + s * C::kStageBytes + kATileBytes; };
@@ -124,8 +140,8 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     auto b_lo = [&](int s) { return smem + s * C::kStageBytes + 2 * kATileBytes + C::kBTileBytes; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
     const int nk = (p.K + kBK - 1) / kBK;
+    const int n_tiles = p.n_tiles_m * p.n_tiles_n;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA);
@@ -136,10 +152,13 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             mbar_init(&ready[s], 128);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(acc_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 128);
+        }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -148,191 +167,249 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % C::kStages;
-                const uint32_t ph = (kc / C::kStages) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], C::kTxBytes);
-                tma_load_2d(a_hi(s), &mapA, kc * kBK, m0, &full[s]);
-                tma_load_2d(b_hi(s), &mapBhi, kc * kBK, n0, &full[s]);
-                if (SPLIT) tma_load_2d(b_lo(s), &mapBlo, kc * kBK, n0, &full[s]);
+            int kt = 0;  // k-chunks issued so far (ring position)
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / p.n_tiles_n) * kBM, n0 = (tile % p.n_tiles_n) * BN;
+                for (int kc = 0; kc < nk; ++kc, ++kt) {
+                    const int s = kt % C::kStages;
+                    const uint32_t ph = (kt / C::kStages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], C::kTxBytes);
+                    tma_load_2d(a_hi(s), &mapA, kc * kBK, m0, &full[s]);
+                    tma_load_2d(b_hi(s), &mapBhi, kc * kBK, n0, &full[s]);
+                    if (SPLIT) tma_load_2d(b_lo(s), &mapBlo, kc * kBK, n0, &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % C::kStages;
-                const uint32_t ph = (kc / C::kStages) & 1;
-                mbar_wait(SPLIT ? &ready[s] : &full[s], ph);
+            int kt = 0, it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int ab = it & 1;
+                const uint32_t aph = (it >> 1) & 1;
+                mbar_wait(&acc_empty[ab], aph ^ 1);
                 tc_fence_after_sync();
-                const uint32_t ah = smem_u32(a_hi(s)), bh = smem_u32(b_hi(s));
-                const uint32_t al = smem_u32(a_lo(s)), bl = smem_u32(b_lo(s));
+                const uint32_t tacc = tmem_base + ab * BN;
+                for (int kc = 0; kc < nk; ++kc, ++kt) {
+                    const int s = kt % C::kStages;
+                    const uint32_t ph = (kt / C::kStages) & 1;
+                    mbar_wait(SPLIT ? &ready[s] : &full[s], ph);
+                    tc_fence_after_sync();
+                    const uint32_t ah = smem_u32(a_hi(s)), bh = smem_u32(b_hi(s));
+                    const uint32_t al = smem_u32(a_lo(s)), bl = smem_u32(b_lo(s));
 #pragma unroll
-                for (int k = 0; k < kBK / kUmmaK; ++k) {
-                    const uint32_t off = k * kUmmaK * 4;
-                    if (SPLIT) {
-                        umma_tf32(tmem_base, umma_desc_k_sw128(al + off), umma_desc_k_sw128(bh + off), idesc, (kc | k) != 0);
-                        umma_tf32(tmem_base, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bl + off), idesc, 1);
-                        umma_tf32(tmem_base, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, 1);
-                    } else {
-                        umma_tf32(tmem_base, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, (kc | k) != 0);
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t off = k * kUmmaK * 4;
+                        if (SPLIT) {
+                            umma_tf32(tacc, umma_desc_k_sw128(al + off), umma_desc_k_sw128(bh + off), idesc, (kc | k) != 0);
+                            umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bl + off), idesc, 1);
+                            umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, 1);
+                        } else {
+                            umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, (kc | k) != 0);
+                        }
                     }
+                    umma_commit(&empty[s]);
                 }
-                umma_commit(&empty[s]);
+                umma_commit(&acc_full[ab]);
             }
-            umma_commit(acc_full);
+        }
+    } else if (warp < 6) {
+        // ===== X split: x -> (tf32(x), tf32(x - tf32(x))), element-wise in shared memory =====
+        if (SPLIT) {
+            const int t = threadIdx.x - 64;  // 0..127
+            int kt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < nk; ++kc, ++kt) {
+                    const int s = kt % C::kStages;
+                    const uint32_t ph = (kt / C::kStages) & 1;
+                    mbar_wait(&full[s], ph);
+                    float4 *hi = reinterpret_cast<float4 *>(a_hi(s));
+                    float4 *lo = reinterpret_cast<float4 *>(a_lo(s));
+#pragma unroll
+                    for (int i = 0; i < kATileBytes / 16 / 128; ++i) {
+                        const float4 v = hi[t + i * 128];
+                        float4 h, l;
+                        h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
+                        l.x = to_tf32(v.x - h.x), l.y = to_tf32(v.y - h.y), l.z = to_tf32(v.z - h.z), l.w = to_tf32(v.w - h.w);
+                        hi[t + i * 128] = h;
+                        lo[t + i * 128] = l;
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&ready[s]);
+                }
+            }
         }
     } else {
-        // ===== X split (main loop) + epilogue =====
-        const int t = threadIdx.x - 64;  // 0..127
-        if (SPLIT) {
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % C::kStages;
-                const uint32_t ph = (kc / C::kStages) & 1;
-                mbar_wait(&full[s], ph);
-                float4 *hi = reinterpret_cast<float4 *>(a_hi(s));
-                float4 *lo = reinterpret_cast<float4 *>(a_lo(s));
-#pragma unroll
-                for (int i = 0; i < kATileBytes / 16 / 128; ++i) {
-                    const float4 v = hi[t + i * 128];
-                    float4 h, l;
-                    h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
-                    l.x = to_tf32(v.x - h.x), l.y = to_tf32(v.y - h.y), l.z = to_tf32(v.z - h.z), l.w = to_tf32(v.w - h.w);
-                    hi[t + i * 128] = h;
-                    lo[t + i * 128] = l;
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(&ready[s]);
-            }
-        }
-        mbar_wait(acc_full, 0);
-        tc_fence_after_sync();
-
+        // ===== epilogue: TMEM -> registers -> (bias, activation, residual, LayerNorm, pool) -> staged, coalesced stores =====
+        const int t = threadIdx.x - 192;        // 0..127
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        const int row = m0 + q * 32 + lane;     // output row of this thread
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const bool row_ok = row < p.M;
-        const int ncols = min(BN, p.N - n0);    // valid columns of this tile
+        const int rl = q * 32 + lane;           // row of the tile owned by this thread
         float v[32];
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile / p.n_tiles_n) * kBM, n0 = (tile % p.n_tiles_n) * BN;
+            const int ab = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int row = m0 + rl;
+            const bool row_ok = row < p.M;
+            const int ncols = min(BN, p.N - n0);          // valid columns of this tile
+            const int nch = (ncols + 31) / 32;
+            const uint32_t taddr = tmem_base + ab * BN + (static_cast<uint32_t>(q * 32) << 16);
+            auto buf = [&](int c) { return ebuf + (C::kEpiBufs == 2 ? (c & 1) : 0) * (kBM * kEpiLd); };
 
-        auto value = [&](float acc, int col) {  // bias -> activation -> residual
-            float y = acc + (p.bias ? __ldg(p.bias + col) : 0.f);
-            y = apply_act(y, p.act);
-            if (p.res) y += __ldg(p.res + static_cast<size_t>(row) * p.ldr + col);
-            return y;
-        };
-
-        if (p.pool) {
-            // groups of 16 consecutive rows -> out[row/16, col] = max, out[row/16, N + col] = mean
-            const int g = row >> 4, gl = lane & 15;
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-                tmem_ld32(taddr + c0, v);
-                float mx[2], sm[2];
+            // residual chunk c (128 rows x 32 columns) -> staging buffer, 16-byte async copies, coalesced
+            auto fetch_res = [&](int c) {
+                float *dst = buf(c);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = n0 + c0 + j;
-                    float y = (row_ok && col < p.N) ? value(v[j], col) : 0.f;
-                    float a = y, b = y;
-#pragma unroll
-                    for (int d = 8; d >= 1; d >>= 1) {
-                        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, d));
-                        b += __shfl_xor_sync(0xffffffffu, b, d);
-                    }
-                    if ((j & 15) == gl) mx[j >> 4] = a, sm[j >> 4] = b;
+                for (int i = 0; i < 8; ++i) {
+                    const int piece = t + i * 128, r = piece >> 3, sg = piece & 7;
+                    const int col = n0 + c * 32 + sg * 4;
+                    if (m0 + r < p.M && col < p.N)
+                        cp_async16(dst + r * kEpiLd + sg * 4, p.res + static_cast<size_t>(m0 + r) * p.ldr + col);
                 }
-                if (row_ok) {
+                cp_async_commit();
+            };
+            // staging buffer -> global, coalesced (8 threads cover one 128-byte row segment)
+            auto store_chunk = [&](int c, float *base, int ld) {
+                const float *src = buf(c);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col = n0 + c0 + h * 16 + gl;
-                        if (col < p.N) {
-                            p.out[static_cast<size_t>(g) * p.ldo + col] = mx[h];
-                            p.out[static_cast<size_t>(g) * p.ldo + p.N + col] = sm[h] * (1.0f / 16.0f);
+                for (int i = 0; i < 8; ++i) {
+                    const int piece = t + i * 128, r = piece >> 3, sg = piece & 7;
+                    const int col = n0 + c * 32 + sg * 4;
+                    if (m0 + r < p.M && col < p.N) {
+                        const float4 y = *reinterpret_cast<const float4 *>(src + r * kEpiLd + sg * 4);
+                        float *dst = base + static_cast<size_t>(m0 + r) * ld + col;
+                        if (col + 3 < p.N) *reinterpret_cast<float4 *>(dst) = y;
+                        else {
+                            dst[0] = y.x;
+                            if (col + 1 < p.N) dst[1] = y.y;
+                            if (col + 2 < p.N) dst[2] = y.z;
                         }
                     }
                 }
-            }
-        } else {
-            float sum = 0.f;
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-                tmem_ld32(taddr + c0, v);
-                if (row_ok) {
-                    float *dst = p.out ? p.out + static_cast<size_t>(row) * p.ldo + n0 + c0 : nullptr;
+            };
+
+            if (p.pool) {
+                mbar_wait(&acc_full[ab], aph);
+                tc_fence_after_sync();
+                // groups of 16 consecutive rows -> out[row/16, col] = max, out[row/16, N + col] = mean
+                const int g = row >> 4, gl = lane & 15;
+                for (int c = 0; c < nch; ++c) {
+                    tmem_ld32(taddr + c * 32, v);
+                    float mx[2] = {0.f, 0.f}, sm[2] = {0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const int col = n0 + c0 + j;
-                        if (col + 3 < p.N) {
-                            float4 y;
-                            y.x = value(v[j], col), y.y = value(v[j + 1], col + 1);
-                            y.z = value(v[j + 2], col + 2), y.w = value(v[j + 3], col + 3);
-                            sum += (y.x + y.y) + (y.z + y.w);
-                            if (dst) *reinterpret_cast<float4 *>(dst + j) = y;
-                        } else {
-                            for (int e = 0; e < 4; ++e)
-                                if (col + e < p.N) {
-                                    const float y = value(v[j + e], col + e);
-                                    sum += y;
-                                    if (dst) dst[j + e] = y;
-                                }
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = n0 + c * 32 + j;
+                        float y = 0.f;
+                        if (row_ok && col < p.N) y = apply_act(v[j] + (p.bias ? __ldg(p.bias + col) : 0.f), p.act);
+                        float a = y, b = y;
+#pragma unroll
+                        for (int d = 8; d >= 1; d >>= 1) {
+                            a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, d));
+                            b += __shfl_xor_sync(0xffffffffu, b, d);
                         }
+                        if ((j & 15) == gl) mx[j >> 4] = a, sm[j >> 4] = b;
                     }
-                }
-            }
-            if (p.ln_out) {
-                // LayerNorm over the N columns of this row (the tile spans all of N): mean, then centred variance
-                const float mean = sum / static_cast<float>(p.N);
-                float var = 0.f;
-                for (int c0 = 0; c0 < ncols; c0 += 32) {
-                    tmem_ld32(taddr + c0, v);
                     if (row_ok) {
 #pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int col = n0 + c * 32 + h * 16 + gl;
+                            if (col < p.N) {
+                                p.out[static_cast<size_t>(g) * p.ldo + col] = mx[h];
+                                p.out[static_cast<size_t>(g) * p.ldo + p.N + col] = sm[h] * (1.0f / 16.0f);
+                            }
+                        }
+                    }
+                }
+            } else {
+                named_bar_sync(kEpiBar, 128);  // the previous tile's last chunk store has drained the staging buffers
+                if (p.res) fetch_res(0);       // overlaps with the main loop of this tile
+                mbar_wait(&acc_full[ab], aph);
+                tc_fence_after_sync();
+                float sum = 0.f;
+                for (int c = 0; c < nch; ++c) {
+                    float *mine = buf(c) + rl * kEpiLd;
+                    if (p.res) cp_async_wait_all();
+                    named_bar_sync(kEpiBar, 128);  // residual chunk c visible; store of chunk c-1 complete
+                    if (p.res && C::kEpiBufs == 2 && c + 1 < nch) fetch_res(c + 1);
+                    tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int col = n0 + c * 32 + j;
+                        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.res) r4 = *reinterpret_cast<const float4 *>(mine + j);
+                        const float *re = &r4.x;
+                        float4 y4;
+                        float *ye = &y4.x;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float y = 0.f;
+                            if (col + e < p.N) y = apply_act(v[j + e] + (p.bias ? __ldg(p.bias + col + e) : 0.f), p.act) + re[e];
+                            ye[e] = y;
+                            v[j + e] = y;
+                            sum += y;
+                        }
+                        *reinterpret_cast<float4 *>(mine + j) = y4;
+                    }
+                    if (p.ln_out) tmem_st32(taddr + c * 32, v);  // keep y for the LayerNorm passes
+                    named_bar_sync(kEpiBar, 128);                // the 128 x 32 chunk of y is staged
+                    if (p.out) store_chunk(c, p.out, p.ldo);
+                    if (C::kEpiBufs == 1) {
+                        named_bar_sync(kEpiBar, 128);
+                        if (p.res && c + 1 < nch) fetch_res(c + 1);
+                    }
+                }
+                if (p.ln_out) {
+                    // LayerNorm over the N columns of this row (the tile spans all of N): mean, then centred variance
+                    const float mean = sum / static_cast<float>(p.N);
+                    float var = 0.f;
+                    for (int c = 0; c < nch; ++c) {
+                        tmem_ld32(taddr + c * 32, v);
+#pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (c0 + j < ncols) {
-                                const float d = value(v[j], n0 + c0 + j) - mean;
+                            if (c * 32 + j < ncols) {
+                                const float d = v[j] - mean;
                                 var = fmaf(d, d, var);
                             }
                     }
-                }
-                const float rstd = 1.0f / sqrtf(var / static_cast<float>(p.N) + p.ln_eps);
-                for (int c0 = 0; c0 < ncols; c0 += 32) {
-                    tmem_ld32(taddr + c0, v);
-                    if (row_ok) {
-                        float *dst = p.ln_out + static_cast<size_t>(row) * p.ldl + c0;
+                    const float rstd = 1.0f / sqrtf(var / static_cast<float>(p.N) + p.ln_eps);
+                    named_bar_sync(kEpiBar, 128);  // the last stores of the first pass have drained the staging buffers
+                    for (int c = 0; c < nch; ++c) {
+                        float *mine = buf(c) + rl * kEpiLd;
+                        tmem_ld32(taddr + c * 32, v);
+                        if (C::kEpiBufs == 1) named_bar_sync(kEpiBar, 128);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            if (c0 + j + 3 < ncols) {
-                                float4 y;
-                                float *ye = &y.x;
+                            float4 y4;
+                            float *ye = &y4.x;
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int col = c0 + j + e;
-                                    ye[e] = (value(v[j + e], col) - mean) * rstd * __ldg(p.ln_g + col) + __ldg(p.ln_b + col);
-                                }
-                                *reinterpret_cast<float4 *>(dst + j) = y;
-                            } else {
-                                for (int e = 0; e < 4; ++e) {
-                                    const int col = c0 + j + e;
-                                    if (col < ncols)
-                                        dst[j + e] = (value(v[j + e], col) - mean) * rstd * __ldg(p.ln_g + col) + __ldg(p.ln_b + col);
-                                }
+                            for (int e = 0; e < 4; ++e) {
+                                const int col = c * 32 + j + e;
+                                ye[e] = col < ncols ? (v[j + e] - mean) * rstd * __ldg(p.ln_g + col) + __ldg(p.ln_b + col) : 0.f;
                             }
+                            *reinterpret_cast<float4 *>(mine + j) = y4;
                         }
+                        named_bar_sync(kEpiBar, 128);
+                        store_chunk(c, p.ln_out, p.ldl);
                     }
                 }
             }
+            tc_fence_before_sync();
+            mbar_arrive(&acc_empty[ab]);
         }
-        tc_fence_before_sync();
     }
+    tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, 2 * BN);
     }
 }
 
 template <int BN, bool SPLIT>
-int launch(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap &mapBlo, const LinearParams &p,
+int launch(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap &mapBlo, LinearParams &p,
            cudaStream_t stream)
 {
     using C = Cfg<BN, SPLIT>;
@@ -341,7 +418,12 @@ int launch(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap
         MAC_CUDA(cudaFuncSetAttribute(linear_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         configured = true;
     }
-    dim3 grid((p.M + kBM - 1) / kBM, (p.N + BN - 1) / BN);
+    p.n_tiles_m = (p.M + kBM - 1) / kBM;
+    p.n_tiles_n = (p.N + BN - 1) / BN;
+    int device = 0;
+    MAC_CUDA(cudaGetDevice(&device));
+    const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+    const int grid = n_tiles < sm_count(device) ? n_tiles : sm_count(device);
     linear_kernel<BN, SPLIT><<<grid, kThreads, C::kSmemBytes, stream>>>(mapA, mapBhi, mapBlo, p);
     MAC_CUDA(cudaGetLastError());
     count_launch();
@@ -364,9 +446,14 @@ int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo
                 "out must be 16-byte aligned with ldo %% 4 == 0");
     const bool split = W_lo != nullptr;
 
+    MAC_REQUIRE(!res || (N % 4 == 0 && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(res) & 15u) == 0 && !pool),
+                "the residual needs N %% 4 == 0, a 16-byte aligned base and row stride, and no pooling");
+    MAC_REQUIRE(!ln_out || (reinterpret_cast<uintptr_t>(ln_out) & 15u) == 0, "ln_out must be 16-byte aligned");
+    // 256-wide tiles only where a row-wise epilogue (LayerNorm) must see all of N; otherwise 128-wide tiles
+    // (two per 256 columns re-read X from L2 but run two-deep epilogue staging and twice the CTAs).
     int bn;
     if (ln_out || pool) bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-    else bn = N <= 64 ? 64 : ((N <= 128 || M <= 16384) ? 128 : 256);
+    else bn = N <= 64 ? 64 : 128;
     MAC_REQUIRE(!(ln_out || pool) || N <= bn, "row-wise epilogues need the tile to span N");
 
     CUtensorMap mapA, mapBhi, mapBlo;

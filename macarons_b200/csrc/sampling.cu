@@ -1,0 +1,236 @@
+// Occupancy-weighted inverse-CDF sampling of proxy points (row a13; reference
+// utility/scone_utils.py:1030-1076).  The reference builds an (n_sample x N) difference matrix (0.8 GB at
+// N = 100k) and takes a row-wise argmin; that is a searchsorted of the uniforms in the CDF.  Here:
+//   kernel 1 (one CTA): occupancy > min_occ mask -> compacted index list, fp64 sum, probabilities p / sum (fp32),
+//                       CDF as a running fp64 sum rounded to fp32 per element (torch's CPU cumsum accumulates
+//                       in double as well), all in two passes over the points;
+//   kernel 2 (one CTA): binary search of every uniform (first CDF entry >= u, "none" -> 0), bitonic sort of the
+//                       picks in shared memory, unique + inverse map (torch.unique semantics: sorted values),
+//                       and the gather of the selected rows [xyz, occupancy] and their 64 view harmonics.
+#include "mac_common.h"
+
+namespace mac {
+
+namespace {
+
+constexpr int kScanThreads = 1024;
+constexpr int kMaxSamples = 4096;
+
+struct SampleParams {
+    const float *X;      // (N, 3)
+    const float *preds;  // (N, 1)
+    const float *vh;     // (N, 64)
+    const float *u;      // (n_sample)
+    int N, n_sample;
+    float min_occ;
+    int *kept;           // (N) compacted indices of points with occupancy > min_occ
+    float *cdf;          // (N)
+    int *n_kept;         // [0] = number kept, [1] = number of unique picks
+    float *res;          // (n_sample, 4)
+    float *res_h;        // (n_sample, 64)
+    long long *inverse;  // (n_sample)
+    long long *picks;    // (n_sample) picked index into the compacted list, unsorted (optional)
+};
+
+__global__ void __launch_bounds__(kScanThreads) sample_scan_kernel(const SampleParams p)
+{
+    __shared__ int s_cnt[kScanThreads];
+    __shared__ double s_sum[kScanThreads];
+    const int t = threadIdx.x;
+    const int per = (p.N + kScanThreads - 1) / kScanThreads;
+    const int lo = min(t * per, p.N), hi = min(lo + per, p.N);
+    int cnt = 0;
+    double sum = 0.0;
+    for (int i = lo; i < hi; ++i) {
+        const float v = p.preds[i];
+        if (v > p.min_occ) {
+            ++cnt;
+            sum += static_cast<double>(v);
+        }
+    }
+    s_cnt[t] = cnt;
+    s_sum[t] = sum;
+    __syncthreads();
+    // inclusive Hillis-Steele scan over the 1024 partials
+    for (int d = 1; d < kScanThreads; d <<= 1) {
+        const int c = t >= d ? s_cnt[t - d] : 0;
+        const double s = t >= d ? s_sum[t - d] : 0.0;
+        __syncthreads();
+        s_cnt[t] += c;
+        s_sum[t] += s;
+        __syncthreads();
+    }
+    const float total = static_cast<float>(s_sum[kScanThreads - 1]);  // torch.sum(res_preds) in fp32
+    int pos = s_cnt[t] - cnt;
+    // exclusive prefix of the probabilities in fp64: sum of (fp32) p_i / total over the kept points before `lo`.
+    // Recomputed per segment from the fp32 quotients so that it is the sum the sequential cumsum would see.
+    __shared__ double s_psum[kScanThreads];
+    double psum = 0.0;
+    for (int i = lo; i < hi; ++i) {
+        const float v = p.preds[i];
+        if (v > p.min_occ) psum += static_cast<double>(v / total);
+    }
+    s_psum[t] = psum;
+    __syncthreads();
+    for (int d = 1; d < kScanThreads; d <<= 1) {
+        const double s = t >= d ? s_psum[t - d] : 0.0;
+        __syncthreads();
+        s_psum[t] += s;
+        __syncthreads();
+    }
+    double run = s_psum[t] - psum;
+    for (int i = lo; i < hi; ++i) {
+        const float v = p.preds[i];
+        if (v > p.min_occ) {
+            run += static_cast<double>(v / total);
+            p.kept[pos] = i;
+            p.cdf[pos] = static_cast<float>(run);
+            ++pos;
+        }
+    }
+    if (t == kScanThreads - 1) p.n_kept[0] = s_cnt[t];
+}
+
+__global__ void __launch_bounds__(1024) sample_pick_kernel(const SampleParams p)
+{
+    __shared__ int s_pick[kMaxSamples];   // sorted picks
+    __shared__ int s_flag[kMaxSamples];   // unique flags -> positions
+    __shared__ int s_total;
+    const int t = threadIdx.x;
+    const int n_kept = p.n_kept[0];
+    const int n = p.n_sample;
+    if (n_kept == 0) {  // nothing above the occupancy threshold: empty result (the reference divides by zero here)
+        if (t == 0) p.n_kept[1] = 0;
+        for (int i = t; i < n; i += blockDim.x) p.inverse[i] = 0;
+        return;
+    }
+    int n_pow2 = 1;
+    while (n_pow2 < n) n_pow2 <<= 1;
+    // searchsorted(cdf, u, left): first index with cdf >= u; none -> 0 (scone_utils.py:1054-1056)
+    for (int i = t; i < n_pow2; i += blockDim.x) {
+        int pick = 0x7fffffff;
+        if (i < n) {
+            const float u = p.u[i];
+            int lo = 0, hi = n_kept;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (p.cdf[mid] < u) lo = mid + 1;
+                else hi = mid;
+            }
+            pick = lo >= n_kept ? 0 : lo;
+            if (p.picks) p.picks[i] = pick;
+        }
+        s_pick[i] = pick;
+    }
+    __syncthreads();
+    // bitonic sort (ascending); padding entries are INT_MAX
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < n_pow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int a = s_pick[i], b = s_pick[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        s_pick[i] = b;
+                        s_pick[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // unique: flag the first occurrence, inclusive scan of the flags
+    for (int i = t; i < n_pow2; i += blockDim.x) s_flag[i] = (i < n && (i == 0 || s_pick[i] != s_pick[i - 1])) ? 1 : 0;
+    __syncthreads();
+    for (int d = 1; d < n_pow2; d <<= 1) {
+        int add[kMaxSamples / 1024];
+        for (int i = t, c = 0; i < n_pow2; i += blockDim.x, ++c) add[c] = i >= d ? s_flag[i - d] : 0;
+        __syncthreads();
+        for (int i = t, c = 0; i < n_pow2; i += blockDim.x, ++c) s_flag[i] += add[c];
+        __syncthreads();
+    }
+    if (t == 0) {
+        s_total = s_flag[n - 1];
+        p.n_kept[1] = s_total;
+    }
+    __syncthreads();
+    // compact the unique values to the front of a second list (re-using the tail of s_flag is not possible: it is
+    // still read), so write them into global `kept`-independent scratch: the res rows themselves are the output.
+    // Row r of the output = unique value number r (ascending).
+    for (int i = t; i < n; i += blockDim.x) {
+        const bool first = (i == 0) || (s_pick[i] != s_pick[i - 1]);
+        if (first) {
+            const int r = s_flag[i] - 1;
+            const int src = p.kept[s_pick[i]];
+            p.res[4 * r + 0] = p.X[3 * src + 0];
+            p.res[4 * r + 1] = p.X[3 * src + 1];
+            p.res[4 * r + 2] = p.X[3 * src + 2];
+            p.res[4 * r + 3] = p.preds[src];
+        }
+    }
+    // view harmonics of the unique rows: 16 threads x float4 per row
+    for (int e = t; e < n * 16; e += blockDim.x) {
+        const int i = e >> 4, c = e & 15;
+        const bool first = (i == 0) || (s_pick[i] != s_pick[i - 1]);
+        if (first) {
+            const int r = s_flag[i] - 1;
+            const int src = p.kept[s_pick[i]];
+            reinterpret_cast<float4 *>(p.res_h + 64 * static_cast<size_t>(r))[c] =
+                reinterpret_cast<const float4 *>(p.vh + 64 * static_cast<size_t>(src))[c];
+        }
+    }
+    // inverse map: rank of each (unsorted) pick among the unique values = (scan value at its last sorted position) - 1
+    for (int i = t; i < n; i += blockDim.x) {
+        const float u = p.u[i];
+        int lo = 0, hi = n_kept;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (p.cdf[mid] < u) lo = mid + 1;
+            else hi = mid;
+        }
+        const int pick = lo >= n_kept ? 0 : lo;
+        int a = 0, b = n;   // first sorted position holding `pick`
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (s_pick[mid] < pick) a = mid + 1;
+            else b = mid;
+        }
+        p.inverse[i] = s_flag[a] - 1;
+    }
+}
+
+}  // namespace
+
+}  // namespace mac
+
+using namespace mac;
+
+extern "C" size_t mac_sample_proxy_workspace_bytes(int N) { return static_cast<size_t>(N) * 8 + 256; }
+
+extern "C" int mac_sample_proxy_points_f32(const float *X, const float *preds, const float *view_harmonics, const float *u, int N,
+                                           int n_sample, float min_occ, float *res, float *res_harmonics, long long *inverse,
+                                           int *counts, void *workspace, size_t workspace_bytes, void *stream)
+{
+    MAC_REQUIRE(X && preds && view_harmonics && u && res && res_harmonics && inverse && counts && workspace, "null pointer");
+    MAC_REQUIRE(N > 0 && n_sample > 0 && n_sample <= kMaxSamples, "need N > 0 and 0 < n_sample <= %d", kMaxSamples);
+    MAC_REQUIRE((reinterpret_cast<uintptr_t>(view_harmonics) & 15u) == 0 && (reinterpret_cast<uintptr_t>(res_harmonics) & 15u) == 0,
+                "harmonics must be 16-byte aligned");
+    if (workspace_bytes < mac_sample_proxy_workspace_bytes(N)) {
+        set_error("workspace too small: need %zu bytes, got %zu", mac_sample_proxy_workspace_bytes(N), workspace_bytes);
+        return MAC_ERR_WORKSPACE;
+    }
+    SampleParams p{};
+    p.X = X, p.preds = preds, p.vh = view_harmonics, p.u = u, p.N = N, p.n_sample = n_sample, p.min_occ = min_occ;
+    p.kept = static_cast<int *>(workspace);
+    p.cdf = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) + static_cast<size_t>(N) * 4);
+    p.n_kept = counts;
+    p.res = res, p.res_h = res_harmonics, p.inverse = inverse, p.picks = nullptr;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    sample_scan_kernel<<<1, kScanThreads, 0, st>>>(p);
+    MAC_CUDA(cudaGetLastError());
+    sample_pick_kernel<<<1, 1024, 0, st>>>(p);
+    MAC_CUDA(cudaGetLastError());
+    count_launch(2);
+    return MAC_OK;
+}

@@ -1,0 +1,199 @@
+// View-state kernels (rows a10-a12 of the scope table):
+//   view_state     spherical-histogram binning of the visited cameras around every point
+//                  (reference utility/scone_utils.py:799-860, utils.floor_divide :113-117,
+//                   CustomGeometry.get_spherical_coords :27-45)
+//   view_harmonics projection of the (n_elev x n_azim) histogram onto the 64 SH basis functions
+//                  (reference utility/scone_utils.py:934-960); never materialises the (B,P,64,98) product
+//   gather_bins    permutation of the bins used by move_view_state_to_view_space (:863-930)
+// HBM-bound element-wise work: one point per thread (binning) / per thread group (projection), coalesced rows.
+#include <math.h>
+
+#include "mac_common.h"
+
+namespace mac {
+
+namespace {
+
+constexpr int kMaxBins = 128;
+
+// torch.remainder on fp32: fmod, then shifted into [0, d) for d > 0
+__device__ __forceinline__ float torch_remainder(float x, float d)
+{
+    float m = fmodf(x, d);
+    if (m != 0.f && m < 0.f) m += d;
+    return m;
+}
+
+struct ViewStateParams {
+    const float *pts;    // (B*P, pts_dim)
+    const float *views;  // (V, 3)
+    float *state;        // (B*P, n_bins)
+    long long n_pts;
+    int pts_dim, V, n_elev, n_azim;
+    float elev_step, azim_step, half_elev_step, half_azim_step;
+    int elev_lo;         // Python -n_elev // 2
+    int azim_hi;         // n_azim // 2
+    int azim_wrap;       // Python -n_azim // 2
+    int elev_shift;      // n_elev // 2
+};
+
+// Bin of the ray pt -> view, arithmetic order of scone_utils.py:815-849.
+__device__ __forceinline__ int view_bin(const ViewStateParams &p, float dx, float dy, float dz)
+{
+    const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float sin_elev = dy / r;
+    float elev = asinf(sin_elev);
+    if (sin_elev <= -1.f) elev = -1.57079632679489661923f;
+    if (sin_elev >= 1.f) elev = 1.57079632679489661923f;
+    const float cos_azim = dz / (r * cosf(elev));
+    float azim = acosf(cos_azim);
+    if (cos_azim <= -1.f) azim = 3.14159265358979323846f;
+    if (cos_azim >= 1.f) azim = 0.f;
+    if (dx < 0.f) azim = -azim;
+
+    const float re = torch_remainder(elev, p.elev_step), ra = torch_remainder(azim, p.azim_step);
+    float ie = (elev - re) / p.elev_step, ia = (azim - ra) / p.azim_step;
+    if (re > p.half_elev_step) ie += 1.f;
+    if (ra > p.half_azim_step) ia += 1.f;
+    if (ie >= static_cast<float>(p.n_elev)) ie = static_cast<float>(p.n_elev - 1);
+    if (ie < static_cast<float>(p.elev_lo)) ie = static_cast<float>(p.elev_lo);
+    if (ia > static_cast<float>(p.azim_hi)) ia = static_cast<float>(p.azim_wrap);
+    ie += static_cast<float>(p.elev_shift);
+    if (ia < 0.f) ia += static_cast<float>(p.n_azim);
+    const int n_bins = p.n_elev * p.n_azim;
+    int idx = static_cast<int>(ie) * p.n_azim + static_cast<int>(ia);   // NaN rays -> 0 like a garbage long cast
+    idx %= n_bins;
+    if (idx < 0) idx += n_bins;
+    return idx;
+}
+
+// one warp per point: lanes split the views, bins are OR-ed into a 128-bit mask, the row is written coalesced
+__global__ void __launch_bounds__(256) view_state_kernel(const ViewStateParams p)
+{
+    extern __shared__ float sviews[];
+    for (int i = threadIdx.x; i < p.V * 3; i += blockDim.x) sviews[i] = p.views[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int n_bins = p.n_elev * p.n_azim;
+    for (long long pt = blockIdx.x * 8ll + (threadIdx.x >> 5); pt < p.n_pts; pt += gridDim.x * 8ll) {
+        const float *x = p.pts + pt * p.pts_dim;
+        const float px = x[0], py = x[1], pz = x[2];
+        unsigned m[4] = {0u, 0u, 0u, 0u};
+        for (int v = lane; v < p.V; v += 32) {
+            const int b = view_bin(p, sviews[3 * v] - px, sviews[3 * v + 1] - py, sviews[3 * v + 2] - pz);
+            m[b >> 5] |= 1u << (b & 31);
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) m[w] |= __shfl_xor_sync(0xffffffffu, m[w], d);
+        float *dst = p.state + pt * n_bins;
+        for (int j = lane; j < n_bins; j += 32) dst[j] = ((m[j >> 5] >> (j & 31)) & 1u) ? 1.0f : 0.0f;
+    }
+}
+
+// out[pt, k] = sum_j state[pt, j] * base[k, j] * sin(polar_j) * polar_step * azim_step
+// block: 32 points; W (n_bins x 64) rebuilt in shared memory per block (cheap: 6272 entries)
+__global__ void __launch_bounds__(256) view_harmonics_kernel(const float *__restrict__ state, const float *__restrict__ base,
+                                                             const float *__restrict__ h_polar, float *__restrict__ out,
+                                                             long long n_pts, int n_bins, float polar_step, float azim_step)
+{
+    extern __shared__ float sm[];
+    float *W = sm;                       // [n_bins][64]
+    float *st = sm + n_bins * 64;        // [32][n_bins + 1]
+    for (int i = threadIdx.x; i < n_bins * 64; i += blockDim.x) {
+        const int j = i >> 6, k = i & 63;
+        W[i] = base[k * n_bins + j];
+    }
+    float *sinp = st + 32 * (n_bins + 1);  // [n_bins]
+    for (int j = threadIdx.x; j < n_bins; j += blockDim.x) sinp[j] = sinf(h_polar[j]);
+    const int k = threadIdx.x & 63, g = threadIdx.x >> 6;  // 4 point groups x 64 coefficients
+    for (long long p0 = blockIdx.x * 32ll; p0 < n_pts; p0 += gridDim.x * 32ll) {
+        __syncthreads();
+        const int n = static_cast<int>(n_pts - p0 < 32 ? n_pts - p0 : 32);
+        for (int i = threadIdx.x; i < n * n_bins; i += blockDim.x) st[(i / n_bins) * (n_bins + 1) + i % n_bins] = state[p0 * n_bins + i];
+        __syncthreads();
+        for (int q = g; q < n; q += 4) {
+            const float *s = st + q * (n_bins + 1);
+            float acc = 0.f;
+            for (int j = 0; j < n_bins; ++j) acc += (((s[j] * W[j * 64 + k]) * sinp[j]) * polar_step) * azim_step;
+            out[(p0 + q) * 64 + k] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_bins_kernel(const float *__restrict__ in, const int *__restrict__ index,
+                                                          float *__restrict__ out, long long total, int n_bins)
+{
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const long long pt = i / n_bins;
+        const int j = static_cast<int>(i - pt * n_bins);
+        out[i] = in[pt * n_bins + index[j]];
+    }
+}
+
+}  // namespace
+
+}  // namespace mac
+
+using namespace mac;
+
+extern "C" int mac_view_state_f32(const float *pts, int pts_dim, const float *views, float *state, int B, int P, int V,
+                                  int n_elev, int n_azim, void *stream)
+{
+    MAC_REQUIRE(pts && views && state, "null tensor pointer");
+    MAC_REQUIRE(B > 0 && P > 0 && V >= 0 && pts_dim >= 3, "bad shape B=%d P=%d V=%d pts_dim=%d", B, P, V, pts_dim);
+    MAC_REQUIRE(n_elev > 0 && n_azim > 0 && n_elev * n_azim <= kMaxBins, "view state supports at most %d bins", kMaxBins);
+    ViewStateParams p{};
+    p.pts = pts, p.views = views, p.state = state;
+    p.n_pts = static_cast<long long>(B) * P;
+    p.pts_dim = pts_dim, p.V = V, p.n_elev = n_elev, p.n_azim = n_azim;
+    const double es = M_PI / (n_elev + 1), as = 2.0 * M_PI / n_azim;
+    p.elev_step = static_cast<float>(es), p.azim_step = static_cast<float>(as);
+    p.half_elev_step = static_cast<float>(es / 2.0), p.half_azim_step = static_cast<float>(as / 2.0);
+    p.elev_lo = -((n_elev + 1) / 2);    // Python floor division -n_elev // 2
+    p.azim_hi = n_azim / 2;
+    p.azim_wrap = -((n_azim + 1) / 2);  // Python -n_azim // 2
+    p.elev_shift = n_elev / 2;
+    const long long want = (p.n_pts + 7) / 8;
+    const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
+    view_state_kernel<<<grid, 256, static_cast<size_t>(V) * 3 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(p);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+extern "C" int mac_view_harmonics_f32(const float *state, const float *base, const float *h_polar, float *out, int B, int P,
+                                      int n_elev, int n_azim, void *stream)
+{
+    MAC_REQUIRE(state && base && h_polar && out, "null tensor pointer");
+    MAC_REQUIRE(B > 0 && P > 0, "B and P must be positive");
+    const int n_bins = n_elev * n_azim;
+    MAC_REQUIRE(n_bins > 0 && n_bins <= kMaxBins, "view state supports at most %d bins", kMaxBins);
+    const long long n_pts = static_cast<long long>(B) * P;
+    const size_t smem = (static_cast<size_t>(n_bins) * 64 + 32 * (n_bins + 1) + n_bins) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        MAC_CUDA(cudaFuncSetAttribute(view_harmonics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        configured = true;
+    }
+    const long long want = (n_pts + 31) / 32;
+    const int grid = static_cast<int>(want < 148 * 4 ? want : 148 * 4);
+    view_harmonics_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        state, base, h_polar, out, n_pts, n_bins, static_cast<float>(M_PI / (n_elev + 1)), static_cast<float>(2.0 * M_PI / n_azim));
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+extern "C" int mac_gather_bins_f32(const float *in, const int *index, float *out, int B, int P, int n_bins, void *stream)
+{
+    MAC_REQUIRE(in && index && out && B > 0 && P > 0 && n_bins > 0, "bad arguments");
+    const long long total = static_cast<long long>(B) * P * n_bins;
+    const long long want = (total + 255) / 256;
+    const int grid = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+    gather_bins_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, index, out, total, n_bins);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}

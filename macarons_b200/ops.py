@@ -271,3 +271,81 @@ def sconeocc_forward(w, pc_global, pc_scales, x, view_harmonics, chunk=16384):
                                                 view_harmonics.data_ptr(), out.data_ptr(), B, Q, chunk, ws.data_ptr(),
                                                 ws.numel(), _stream_ptr(x.device)))
     return out
+
+
+# ---- view state and proxy sampling (csrc/viewstate.cu, csrc/sampling.cu) --------------------------
+def view_state(pts, X_view, n_elev, n_azim):
+    """pts (B,P,>=3), X_view (V,3) -> (B,P,n_elev*n_azim) fp32 {0,1}."""
+    _require_cuda_f32("pts", pts)
+    _require_cuda_f32("X_view", X_view)
+    if pts.dim() != 3 or pts.shape[-1] < 3 or X_view.dim() != 2 or X_view.shape[-1] != 3:
+        raise ValueError("pts must be (B,P,>=3) and X_view (V,3)")
+    pts, X_view = pts.contiguous(), X_view.contiguous()
+    B, P, D = pts.shape
+    out = torch.empty((B, P, n_elev * n_azim), dtype=torch.float32, device=pts.device)
+    if B * P == 0:
+        return out
+    with torch.cuda.device(pts.device):
+        _lib.check(_lib.load().mac_view_state_f32(pts.data_ptr(), D, X_view.data_ptr(), out.data_ptr(), B, P,
+                                                  X_view.shape[0], int(n_elev), int(n_azim), _stream_ptr(pts.device)))
+    return out
+
+
+def view_harmonics(state, base, h_polar, n_elev, n_azim):
+    """state (B,P,n_bins), base (64,n_bins), h_polar (n_bins) -> (B,P,64)."""
+    for name, t in (("view_state", state), ("base_harmonics", base), ("h_polar", h_polar)):
+        _require_cuda_f32(name, t)
+    n_bins = n_elev * n_azim
+    if state.dim() != 3 or state.shape[-1] != n_bins or tuple(base.shape) != (N_HARMONICS, n_bins) or h_polar.numel() != n_bins:
+        raise ValueError("view_state must be (B,P,%d), base_harmonics (64,%d), h_polar (%d,)" % (n_bins, n_bins, n_bins))
+    state, base, h_polar = state.contiguous(), base.contiguous(), h_polar.contiguous()
+    B, P, _ = state.shape
+    out = torch.empty((B, P, N_HARMONICS), dtype=torch.float32, device=state.device)
+    if B * P == 0:
+        return out
+    with torch.cuda.device(state.device):
+        _lib.check(_lib.load().mac_view_harmonics_f32(state.data_ptr(), base.data_ptr(), h_polar.data_ptr(), out.data_ptr(),
+                                                      B, P, int(n_elev), int(n_azim), _stream_ptr(state.device)))
+    return out
+
+
+def gather_bins(state, index):
+    """state (B,P,n_bins), index (n_bins) int -> state[..., index]."""
+    _require_cuda_f32("view_state", state)
+    state = state.contiguous()
+    index = index.to(device=state.device, dtype=torch.int32).contiguous()
+    B, P, n_bins = state.shape
+    out = torch.empty_like(state)
+    if B * P == 0:
+        return out
+    with torch.cuda.device(state.device):
+        _lib.check(_lib.load().mac_gather_bins_f32(state.data_ptr(), index.data_ptr(), out.data_ptr(), B, P, n_bins,
+                                                   _stream_ptr(state.device)))
+    return out
+
+
+def sample_proxy_points(X_world, preds, view_harmonics, u, min_occ):
+    """(N,3), (N,1), (N,64), u (n_sample,) -> (res (U,4), res_harmonics (U,64), inverse (n_sample,) int64)."""
+    for name, t in (("X_world", X_world), ("preds", preds), ("view_harmonics", view_harmonics), ("u", u)):
+        _require_cuda_f32(name, t)
+    N = X_world.shape[0]
+    n_sample = u.numel()
+    if tuple(X_world.shape) != (N, 3) or preds.numel() != N or tuple(view_harmonics.shape) != (N, N_HARMONICS):
+        raise ValueError("expected X_world (N,3), preds (N,1), view_harmonics (N,64)")
+    dev = X_world.device
+    X_world, preds, view_harmonics, u = X_world.contiguous(), preds.contiguous(), view_harmonics.contiguous(), u.contiguous()
+    res = torch.empty((n_sample, 4), dtype=torch.float32, device=dev)
+    res_h = torch.empty((n_sample, N_HARMONICS), dtype=torch.float32, device=dev)
+    inverse = torch.empty((n_sample,), dtype=torch.int64, device=dev)
+    counts = torch.zeros((2,), dtype=torch.int32, device=dev)
+    if N == 0:
+        return res[:0], res_h[:0], inverse.zero_()
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ws = torch.empty(lib.mac_sample_proxy_workspace_bytes(N), dtype=torch.uint8, device=dev)
+        _lib.check(lib.mac_sample_proxy_points_f32(X_world.data_ptr(), preds.data_ptr(), view_harmonics.data_ptr(),
+                                                   u.data_ptr(), N, n_sample, float(min_occ), res.data_ptr(),
+                                                   res_h.data_ptr(), inverse.data_ptr(), counts.data_ptr(), ws.data_ptr(),
+                                                   ws.numel(), _stream_ptr(dev)))
+    n_unique = int(counts[1].item())   # the result has a data-dependent length (as torch.unique in the reference)
+    return res[:n_unique], res_h[:n_unique], inverse

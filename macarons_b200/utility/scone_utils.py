@@ -1,8 +1,99 @@
-"""Hot-path subset of reference macarons/utility/scone_utils.py, same function names and argument meaning.
+"""Hot-path subset of reference macarons/utility/scone_utils.py: same function names, argument meaning and return
+values; the per-point arithmetic runs in CUDA kernels through the C ABI (CUDA tensors only, no CPU path).
 
+  get_all_harmonics_under_degree  (reference :714-738)   host-side set-up, 98 bin centres once per run
+  get_cameras_on_sphere           (reference :741-785)   host-side set-up
+  normalize_points_in_prediction_box (:788-796)
+  compute_view_state              (reference :799-860)   -> csrc/viewstate.cu
+  move_view_state_to_view_space   (reference :863-930)   98-entry permutation on the host + gather kernel
+  compute_view_harmonics          (reference :934-960)   -> csrc/viewstate.cu
   compute_occupancy_probability   (reference :965-998)   chunked SconeOcc inference
+  sample_proxy_points             (reference :1030-1076) -> csrc/sampling.cu
 """
+import numpy as np
 import torch
+
+from .. import ops
+from .CustomGeometry import get_cartesian_coords, get_spherical_coords
+from .spherical_harmonics import clear_spherical_harmonics_cache, get_spherical_harmonics
+
+
+def get_all_harmonics_under_degree(degree, n_elev, n_azim, device):
+    """-> (base (degree^2, n_elev*n_azim), h_polar, h_azim): the SH basis at the bin centres, bins elevation-major,
+    elev_i = -pi/2 + (i+1) pi / (n_elev+1), azim_j = 2 pi j / n_azim."""
+    h_elev = torch.Tensor([-np.pi / 2 + (i + 1) / (n_elev + 1) * np.pi for i in range(n_elev) for _ in range(n_azim)]).to(device)
+    h_polar = -h_elev + np.pi / 2
+    h_azim = torch.Tensor([2 * np.pi * j / n_azim for _ in range(n_elev) for j in range(n_azim)]).to(device)
+    clear_spherical_harmonics_cache()
+    z = torch.cat([get_spherical_harmonics(l, h_polar, h_azim) for l in range(degree)], dim=-1)
+    return z.transpose(dim0=0, dim1=1), h_polar, h_azim
+
+
+def get_cameras_on_sphere(params, device, pole_cameras=False, n_elev=None, n_azim=None, camera_dist=None):
+    """Candidate camera positions on a sphere -> (X_cam (n,3), dist (n,), elev (n,), azim (n,)) in degrees."""
+    if n_elev is None or n_azim is None:
+        n_elev, n_azim, n_camera = params.n_camera_elev, params.n_camera_azim, params.n_camera
+    else:
+        n_camera = n_elev * n_azim + (2 if pole_cameras else 0)
+    if camera_dist is None:
+        camera_dist = params.camera_dist
+    dist = torch.Tensor([camera_dist for _ in range(n_camera)]).to(device)
+    elev = [-90. + (i + 1) / (n_elev + 1) * 180. for i in range(n_elev) for _ in range(n_azim)]
+    azim = [360. * j / n_azim for _ in range(n_elev) for j in range(n_azim)]
+    if pole_cameras:
+        elev, azim = [-89.9] + elev + [89.9], [0.] + azim + [0.]
+    elev, azim = torch.Tensor(elev).to(device), torch.Tensor(azim).to(device)
+    X_cam = get_cartesian_coords(r=dist.view(-1, 1), elev=elev.view(-1, 1), azim=azim.view(-1, 1), in_degrees=True)
+    return X_cam, dist, elev, azim
+
+
+def normalize_points_in_prediction_box(points, prediction_box_center, prediction_box_diag):
+    return (points - prediction_box_center) / prediction_box_diag
+
+
+def compute_view_state(pts, X_view, n_elev, n_azim):
+    """pts (n_cloud, seq_len, >=3), X_view (n_view, 3) -> (n_cloud, seq_len, n_elev*n_azim): 1.0 in the bin of every
+    visited camera as seen from every point."""
+    return ops.view_state(pts, X_view, n_elev, n_azim)
+
+
+def view_space_bin_permutation(R, n_elev, n_azim):
+    """The n_elev*n_azim gather indices of move_view_state_to_view_space for a camera with rotation R (3,3)
+    (pytorch3d row-vector convention X_view = X_world R + T).  The reference maps the unit bin directions through
+    the inverse world-to-view transform and subtracts the camera centre (:887-897); the translations cancel,
+    (X - T) R^T - (-T R^T) = X R^T, so only the rotation matters.  Binning as in :902-924 (NB the clamps here are
+    +-(n_elev // 2), unlike compute_view_state)."""
+    R = R.detach().to(device="cpu", dtype=torch.float32).view(3, 3)
+    n_view = n_elev * n_azim
+    elev = torch.Tensor([-90. + (i + 1) / (n_elev + 1) * 180. for i in range(n_elev) for _ in range(n_azim)])
+    azim = torch.Tensor([360. * j / n_azim for _ in range(n_elev) for j in range(n_azim)])
+    X_ref = get_cartesian_coords(r=torch.ones(n_view, 1), elev=elev.view(-1, 1), azim=azim.view(-1, 1), in_degrees=True)
+    X_inv = X_ref @ R.transpose(0, 1)
+    elev_step, azim_step = np.pi / (n_elev + 1), 2 * np.pi / n_azim
+    _, ray_elev, ray_azim = get_spherical_coords(X_inv.view(-1, 3))
+    idx_elev = (ray_elev - ray_elev % elev_step) / elev_step
+    idx_azim = (ray_azim - ray_azim % azim_step) / azim_step
+    idx_elev[ray_elev % elev_step > elev_step / 2.] += 1
+    idx_azim[ray_azim % azim_step > azim_step / 2.] += 1
+    idx_elev[idx_elev > n_elev // 2] = n_elev // 2
+    idx_elev[idx_elev < -(n_elev // 2)] = -(n_elev // 2)
+    idx_azim[idx_azim > n_azim // 2] = -(n_azim // 2)
+    idx_elev += n_elev // 2
+    idx_azim[idx_azim < 0] += n_azim
+    return idx_elev.long() * n_azim + idx_azim.long()
+
+
+def move_view_state_to_view_space(view_state, fov_camera, n_elev, n_azim):
+    """'Rotate' view states (n_cloud, seq_len, n_elev*n_azim) into the view space of `fov_camera` (any object with a
+    pytorch3d-style `.R` of shape (1,3,3))."""
+    indices = view_space_bin_permutation(fov_camera.R[0], n_elev, n_azim)
+    return ops.gather_bins(view_state, indices)
+
+
+def compute_view_harmonics(view_state, base_harmonics, h_polar, h_azim, n_elev, n_azim):
+    """(n_cloud, seq_len, n_elev*n_azim) -> (n_cloud, seq_len, n_harmonics): spherical L2 product of the histogram
+    with every basis function (sum over bins of state * base * sin(polar) * polar_step * azim_step)."""
+    return ops.view_harmonics(view_state, base_harmonics, h_polar, n_elev, n_azim)
 
 
 def compute_occupancy_probability(scone_occ, pc, X, view_harmonics, mask=None, max_points_per_pass=20000):
@@ -18,3 +109,23 @@ def compute_occupancy_probability(scone_occ, pc, X, view_harmonics, mask=None, m
         up = min(lo + p, n_sample)
         preds[:, lo:up] = scone_occ(pc, X[:, lo:up], view_harmonics[:, lo:up], verbose=False).view(n_clouds, up - lo, -1)
     return preds
+
+
+def sample_proxy_points(X_world, preds, view_harmonics, n_sample, min_occ, use_occ_to_sample=True, return_index=False,
+                        samples=None):
+    """X_world (n_points, 3), preds (n_points, 1), view_harmonics (n_points, 64) -> (res (U,4), res_harmonics (U,64)
+    [, inverse_idx (n_sample,)]): occupancy-weighted inverse-CDF draw of n_sample points among those with occupancy
+    > min_occ, duplicates merged (sorted unique indices).  The uniforms are `torch.rand(n_sample, 1, device=...)`
+    exactly as in the reference (:1052) unless `samples` injects them (tests)."""
+    if not use_occ_to_sample:
+        mask = preds[..., 0] > min_occ                    # reference :1063-1070, plain truncation, no arithmetic
+        res = torch.cat((X_world[mask][:n_sample], preds[mask][:n_sample]), dim=-1)
+        res_harmonics, inverse_idx = view_harmonics[mask][:n_sample], None
+    else:
+        if samples is None:
+            samples = torch.rand(n_sample, 1, device=X_world.device)
+        res, res_harmonics, inverse_idx = ops.sample_proxy_points(X_world, preds, view_harmonics,
+                                                                  samples.reshape(-1).to(torch.float32), min_occ)
+    if return_index:
+        return res, res_harmonics, inverse_idx
+    return res, res_harmonics

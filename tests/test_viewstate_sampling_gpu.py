@@ -1,0 +1,145 @@
+"""GPU parity of rows a10-a13: view-state binning, histogram -> SH projection, bin permutation and proxy sampling,
+CUDA path through the C ABI vs the oracle and the fixtures generated from the unmodified reference."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from conftest import load_golden
+from macarons_b200 import ops
+from macarons_b200.utility import scone_utils
+from oracle import sampling as o_sampling
+from oracle import view_state as o_vs
+
+pytestmark = pytest.mark.gpu
+
+
+def _boundary_margin(pts, X_view, n_elev, n_azim):
+    """(B,P) smallest float64 distance (rad) of any ray's elevation / azimuth to a bin boundary (half-way between
+    bin centres), i.e. how far the point is from a place where fp32 rounding may legitimately flip a bin."""
+    d = X_view.double().view(1, 1, -1, 3) - pts[..., :3].double().unsqueeze(2)
+    r = d.norm(dim=-1)
+    elev = torch.asin((d[..., 1] / r).clamp(-1, 1))
+    azim = torch.atan2(d[..., 0], d[..., 2])
+    es, az = math.pi / (n_elev + 1), 2 * math.pi / n_azim
+    me = ((elev / es) % 1.0 - 0.5).abs() * es
+    ma = ((azim / az) % 1.0 - 0.5).abs() * az
+    return torch.minimum(me, ma).min(dim=-1)[0]
+
+
+@pytest.mark.parametrize("name", ["view_state_small", "view_state_10views"])
+def test_view_state_and_harmonics(name, cuda_device):
+    g = load_golden(name)
+    B, P, V = int(g["B"]), int(g["P"]), int(g["V"])
+    pts, _ = synth.view_state_inputs(B, P, V, int(g["seed"]))
+    X_view = torch.from_numpy(g["X_view"])
+    want = torch.from_numpy(np.unpackbits(g["state_bits"], axis=-1)[..., :98].astype(np.float32))
+    n0 = ops.launch_count()
+    got = scone_utils.compute_view_state(pts.to(cuda_device), X_view.to(cuda_device), 7, 14)
+    assert ops.launch_count() == n0 + 1
+    got_c = got.cpu()
+    assert got_c.shape == (B, P, 98) and set(got_c.unique().tolist()) <= {0.0, 1.0}
+    # identical bins wherever no ray sits within 1e-5 rad of a bin boundary (fp32 asin / acos differ by an ulp
+    # between libm and CUDA); elsewhere at most a neighbouring bin
+    safe = _boundary_margin(pts, X_view, 7, 14) > 1e-5
+    assert safe.float().mean().item() > 0.99
+    assert torch.equal(got_c[safe], want[safe])
+    assert (got_c != want).any(-1).float().mean().item() <= 1e-3
+    # a11: histogram -> SH coordinates
+    base, h_polar, h_azim = scone_utils.get_all_harmonics_under_degree(8, 7, 14, cuda_device)
+    gb = load_golden("view_base_harmonics")
+    assert np.abs(base.cpu().numpy() - gb["base"]).max() <= 2e-6
+    vh = scone_utils.compute_view_harmonics(got, base, h_polar, h_azim, 7, 14).cpu()
+    same = ~(got_c != want).any(-1)
+    assert np.abs(vh.numpy() - g["view_harmonics"])[same.numpy()].max() <= 2e-6
+    # general (non 0/1) states, e.g. the accumulated states of Scene.update_proxy_view_states
+    acc = torch.rand(B, P, 98, generator=torch.Generator().manual_seed(3))
+    ob, ohp, _ = o_vs.bin_centre_harmonics(8, 7, 14)
+    want_acc = o_vs.view_harmonics(acc, ob, ohp, 7, 14)
+    got_acc = scone_utils.compute_view_harmonics(acc.to(cuda_device), base, h_polar, h_azim, 7, 14).cpu()
+    assert (got_acc - want_acc).abs().max().item() <= 1e-5
+
+
+def test_pole_cameras_wrap_like_the_reference(cuda_device):
+    """A camera straight above lands in bins 0-13, straight below in 84-97."""
+    pts = torch.zeros(1, 4, 3)
+    pts[0, :, 0] = torch.tensor([0.01, -0.02, 0.03, 0.0])
+    pts[0, :, 2] = torch.tensor([0.02, 0.01, -0.03, 0.01])
+    for y, lo, hi in ((1.5, 0, 14), (-1.5, 84, 98)):
+        X_view = torch.tensor([[0.0, y, 0.0]])
+        got = scone_utils.compute_view_state(pts.to(cuda_device), X_view.to(cuda_device), 7, 14).cpu()
+        want = o_vs.view_state(pts, X_view, 7, 14)
+        assert torch.equal(got, want)
+        assert torch.all(got[..., lo:hi].sum(-1) == 1)
+
+
+def test_move_view_state_to_view_space(cuda_device):
+    class Cam:
+        pass
+    state = torch.rand(2, 300, 98, generator=torch.Generator().manual_seed(1))
+    k = 3                                     # rotate about +y by k azimuth bins
+    a = 2 * math.pi * k / 14
+    cam = Cam()
+    cam.R = torch.tensor([[[math.cos(a), 0.0, math.sin(a)], [0.0, 1.0, 0.0], [-math.sin(a), 0.0, math.cos(a)]]])
+    idx = scone_utils.view_space_bin_permutation(cam.R[0], 7, 14)
+    i, j = torch.arange(98) // 14, torch.arange(98) % 14
+    assert torch.equal(idx // 14, i)
+    shift = (idx % 14 - j) % 14
+    assert torch.all(shift == shift[0]) and int(shift[0]) in (k, 14 - k)
+    got = scone_utils.move_view_state_to_view_space(state.to(cuda_device), cam, 7, 14).cpu()
+    assert torch.equal(got, state[..., idx])
+    cam.R = torch.eye(3).view(1, 3, 3)
+    assert torch.equal(scone_utils.move_view_state_to_view_space(state.to(cuda_device), cam, 7, 14).cpu(), state)
+
+
+def test_sample_proxy_points_matches_reference_golden(cuda_device):
+    g = load_golden("sampling_20k")
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    N = int(g["N"])
+    X = torch.rand(N, 3, generator=gen) - 0.5
+    preds = torch.rand(N, 1, generator=gen)
+    vh = torch.randn(N, 64, generator=gen)
+    u = torch.from_numpy(g["u"])
+    res, res_h, inv = scone_utils.sample_proxy_points(X.to(cuda_device), preds.to(cuda_device), vh.to(cuda_device),
+                                                      int(g["n_sample"]), float(g["min_occ"]), return_index=True,
+                                                      samples=u.to(cuda_device))
+    res, res_h, inv = res.cpu(), res_h.cpu(), inv.cpu()
+    want_res, want_h, want_inv = o_sampling.sample_proxy_points(X, preds, vh, int(g["n_sample"]), float(g["min_occ"]), u=u)
+    assert np.array_equal(want_res.numpy(), g["res"]) and np.array_equal(want_inv.numpy(), g["inverse"])
+    # the drawn points (with duplicates) are what SconeVis consumes: compare those, draw by draw.  A draw may differ
+    # only if its uniform sits within rounding distance of a CDF step (the total is summed in another order).
+    drawn, want_drawn = res[inv], want_res[want_inv]
+    differ = (drawn != want_drawn).any(-1)
+    assert differ.float().mean().item() <= 2e-3
+    if not differ.any():
+        assert torch.equal(res, want_res) and torch.equal(inv, want_inv) and torch.equal(res_h, want_h)
+    assert inv.dtype == torch.int64 and res.shape[1] == 4 and res_h.shape == (res.shape[0], 64)
+    assert torch.equal(res_h[inv][~differ], want_h[want_inv][~differ])
+    assert torch.all(res[:, 3] > float(g["min_occ"]))
+
+
+def test_sample_proxy_points_edge_cases(cuda_device):
+    gen = torch.Generator().manual_seed(8)
+    X = torch.rand(50, 3, generator=gen)
+    vh = torch.randn(50, 64, generator=gen)
+    # one point above the threshold: every draw picks it
+    preds = torch.full((50, 1), 0.05)
+    preds[17] = 0.9
+    u = torch.rand(64, generator=gen)
+    res, res_h, inv = scone_utils.sample_proxy_points(X.to(cuda_device), preds.to(cuda_device), vh.to(cuda_device), 64, 0.1,
+                                                      return_index=True, samples=u.to(cuda_device))
+    assert res.shape == (1, 4) and torch.equal(res.cpu()[0, :3], X[17]) and torch.all(inv == 0)
+    # u beyond the last CDF value falls back to index 0 of the kept points (reference: all-negative row -> argmin 0)
+    preds = torch.rand(50, 1, generator=gen) + 0.2
+    u = torch.tensor([1.5, 0.0, 0.999999])
+    res, _, inv = scone_utils.sample_proxy_points(X.to(cuda_device), preds.to(cuda_device), vh.to(cuda_device), 3, 0.1,
+                                                  return_index=True, samples=u.to(cuda_device))
+    want_res, _, want_inv = o_sampling.sample_proxy_points(X, preds, vh, 3, 0.1, u=u)
+    assert torch.equal(res.cpu(), want_res) and torch.equal(inv.cpu(), want_inv)
+    # nothing above the threshold: empty result
+    res, res_h, inv = scone_utils.sample_proxy_points(X.to(cuda_device), torch.zeros(50, 1, device=cuda_device),
+                                                      vh.to(cuda_device), 8, 0.1, return_index=True,
+                                                      samples=torch.rand(8, device=cuda_device))
+    assert res.shape == (0, 4) and res_h.shape == (0, 64)
