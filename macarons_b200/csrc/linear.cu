@@ -71,8 +71,8 @@ constexpr int kBM = 128;
 constexpr int kBK = 32;             // fp32 per k-chunk: one 128-byte swizzle span
 constexpr int kUmmaK = 8;           // tf32 MMA depth (32 bytes)
 constexpr int kATileBytes = kBM * kBK * 4;
-constexpr int kThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-5 X split, warps 6-9 epilogue
-constexpr int kMaxStages = 4;
+constexpr int kThreads = 384;       // warp 0 X TMA, warp 1 MMA, warp 2 W TMA, warps 4-7 X split, warps 8-11 epilogue
+constexpr int kMaxStages = 8;
 constexpr int kEpiLd = 36;          // epilogue staging row stride (floats): 32 columns + 4 pad, conflict-free float4 rows
 constexpr int kEpiBufBytes = kBM * kEpiLd * 4;
 constexpr int kEpiBar = 1;          // named barrier of the 128 epilogue threads
@@ -95,28 +95,38 @@ struct LinearParams {
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-__device__ __forceinline__ float apply_act(float y, int act)
+template <int ACT>
+__device__ __forceinline__ float apply_act(float y)
 {
-    if (act == MAC_LIN_RELU) return fmaxf(y, 0.f);
-    if (act == MAC_LIN_GELU) return gelu_exact(y);
+    if (ACT == MAC_LIN_RELU) return fmaxf(y, 0.f);
+    if (ACT == MAC_LIN_GELU) return gelu_exact(y);
     return y;
 }
 
+// Shared-memory plan.  Three independent rings so that the number of X bytes in flight from HBM is not tied to the
+// (large, L2-resident) weight tiles:
+//   raw X ring   kRawSlots x 16 KB   TMA destination; the split rewrites each slot in place with tf32(x)
+//   lo  X ring   kLoSlots  x 16 KB   tf32(x - tf32(x)), produced by the split warps            [SPLIT only]
+//   W ring       kWSlots x (1 or 2) x BN x 128 B   W_hi (and W_lo) k-chunks
 template <int BN, bool SPLIT>
 struct Cfg {
     static constexpr int kBTileBytes = BN * kBK * 4;
-    static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kATileBytes + kBTileBytes);
+    static constexpr int kWSlotBytes = (SPLIT ? 2 : 1) * kBTileBytes;
     static constexpr int kEpiBufs = (BN <= 128) ? 2 : 1;
-    static constexpr int kBudget = 226 * 1024 - 1024 - 512 - kEpiBufs * kEpiBufBytes;
-    static constexpr int kStages = (kBudget / kStageBytes) < kMaxStages ? (kBudget / kStageBytes) : kMaxStages;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBufs * kEpiBufBytes + 1024 /*alignment*/ + 512 /*barriers*/;
-    static constexpr uint32_t kTxBytes = kATileBytes + (SPLIT ? 2 : 1) * kBTileBytes;
-    static_assert(kStages >= 2, "need at least a double-buffered operand pipeline");
+    static constexpr int kWSlots = 2;
+    static constexpr int kLoSlots = SPLIT ? 2 : 0;
+    static constexpr int kVecBytes = 3 * BN * 4;  // bias | gamma | beta of the tile's columns
+    static constexpr int kBudget = 226 * 1024 - 1024 - 512 - kVecBytes - kEpiBufs * kEpiBufBytes - kWSlots * kWSlotBytes - kLoSlots * kATileBytes;
+    static constexpr int kRawSlots = (kBudget / kATileBytes) < kMaxStages ? (kBudget / kATileBytes) : kMaxStages;
+    static constexpr int kOperandBytes = kRawSlots * kATileBytes + kLoSlots * kATileBytes + kWSlots * kWSlotBytes;
+    static constexpr int kSmemBytes = kOperandBytes + kEpiBufs * kEpiBufBytes + kVecBytes + 1024 /*alignment*/ + 512 /*barriers*/;
+    static constexpr uint32_t kWTxBytes = kWSlotBytes;
+    static_assert(kRawSlots >= 2, "need at least a double-buffered X pipeline");
 };
 
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA and MMA warps run ahead of the
 // epilogue through a ring of operand stages and two TMEM accumulators.
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
               const __grid_constant__ CUtensorMap mapBlo, const LinearParams p)
@@ -125,19 +135,26 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    float *ebuf = reinterpret_cast<float *>(smem + C::kStages * C::kStageBytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes + C::kEpiBufs * kEpiBufBytes);
-    uint64_t *full = bars;                       // TMA landed
-    uint64_t *ready = bars + kMaxStages;         // X split done (SPLIT only)
-    uint64_t *empty = bars + 2 * kMaxStages;     // MMAs that read the stage have completed
-    uint64_t *acc_full = bars + 3 * kMaxStages;  // [2] accumulator complete
-    uint64_t *acc_empty = acc_full + 2;          // [2] accumulator drained by the epilogue
+    uint8_t *raw_base = smem;
+    uint8_t *lo_base = raw_base + C::kRawSlots * kATileBytes;
+    uint8_t *w_base = lo_base + C::kLoSlots * kATileBytes;
+    float *ebuf = reinterpret_cast<float *>(smem + C::kOperandBytes);
+    float *svec = ebuf + C::kEpiBufs * (kBM * kEpiLd);   // [3][BN]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kOperandBytes + C::kEpiBufs * kEpiBufBytes + C::kVecBytes);
+    uint64_t *full_x = bars;                      // [kRawSlots] X chunk landed
+    uint64_t *empty_x = bars + kMaxStages;        // [kRawSlots] MMAs that read the raw slot have completed
+    uint64_t *ready_lo = bars + 2 * kMaxStages;   // [2] split done: hi rewritten in the raw slot, lo written
+    uint64_t *empty_lo = ready_lo + 2;            // [2] MMAs that read the lo slot have completed
+    uint64_t *full_w = empty_lo + 2;              // [2] W chunk landed
+    uint64_t *empty_w = full_w + 2;               // [2]
+    uint64_t *acc_full = empty_w + 2;             // [2] accumulator complete
+    uint64_t *acc_empty = acc_full + 2;           // [2] accumulator drained by the epilogue
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
-    auto a_hi = [&](int s) { return smem + s * C::kStageBytes; };
-    auto b_hi = [&](int s) { return smem + s * C::kStageBytes + kATileBytes; };
-    auto a_lo = [&](int s) { return smem + s * C::kStageBytes + kATileBytes + C::kBTileBytes; };
-    auto b_lo = [&](int s) { return smem + s * C::kStageBytes + 2 * kATileBytes + C::kBTileBytes; };
+    auto a_hi = [&](int s) { return raw_base + s * kATileBytes; };
+    auto a_lo = [&](int s) { return lo_base + s * kATileBytes; };
+    auto b_hi = [&](int s) { return w_base + s * C::kWSlotBytes; };
+    auto b_lo = [&](int s) { return w_base + s * C::kWSlotBytes + C::kBTileBytes; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = (p.K + kBK - 1) / kBK;
@@ -147,10 +164,15 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapBhi);
         if (SPLIT) tma_prefetch_desc(&mapBlo);
-        for (int s = 0; s < C::kStages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&ready[s], 128);
-            mbar_init(&empty[s], 1);
+        for (int s = 0; s < C::kRawSlots; ++s) {
+            mbar_init(&full_x[s], 1);
+            mbar_init(&empty_x[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&ready_lo[s], 128);
+            mbar_init(&empty_lo[s], 1);
+            mbar_init(&full_w[s], 1);
+            mbar_init(&empty_w[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
@@ -165,19 +187,33 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== X producer (TMA): runs up to kRawSlots k-chunks ahead of the tensor core =====
         if (lane == 0) {
-            int kt = 0;  // k-chunks issued so far (ring position)
+            int kt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.n_tiles_n) * kBM, n0 = (tile % p.n_tiles_n) * BN;
+                const int m0 = (tile / p.n_tiles_n) * kBM;
                 for (int kc = 0; kc < nk; ++kc, ++kt) {
-                    const int s = kt % C::kStages;
-                    const uint32_t ph = (kt / C::kStages) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], C::kTxBytes);
-                    tma_load_2d(a_hi(s), &mapA, kc * kBK, m0, &full[s]);
-                    tma_load_2d(b_hi(s), &mapBhi, kc * kBK, n0, &full[s]);
-                    if (SPLIT) tma_load_2d(b_lo(s), &mapBlo, kc * kBK, n0, &full[s]);
+                    const int s = kt % C::kRawSlots;
+                    const uint32_t ph = (kt / C::kRawSlots) & 1;
+                    mbar_wait(&empty_x[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_x[s], kATileBytes);
+                    tma_load_2d(a_hi(s), &mapA, kc * kBK, m0, &full_x[s]);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===== W producer (TMA): weight k-chunks come from L2 =====
+        if (lane == 0) {
+            int kt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int n0 = (tile % p.n_tiles_n) * BN;
+                for (int kc = 0; kc < nk; ++kc, ++kt) {
+                    const int s = kt & 1;
+                    const uint32_t ph = (kt >> 1) & 1;
+                    mbar_wait(&empty_w[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_w[s], C::kWTxBytes);
+                    tma_load_2d(b_hi(s), &mapBhi, kc * kBK, n0, &full_w[s]);
+                    if (SPLIT) tma_load_2d(b_lo(s), &mapBlo, kc * kBK, n0, &full_w[s]);
                 }
             }
         }
@@ -193,12 +229,14 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 tc_fence_after_sync();
                 const uint32_t tacc = tmem_base + ab * BN;
                 for (int kc = 0; kc < nk; ++kc, ++kt) {
-                    const int s = kt % C::kStages;
-                    const uint32_t ph = (kt / C::kStages) & 1;
-                    mbar_wait(SPLIT ? &ready[s] : &full[s], ph);
+                    const int sx = kt % C::kRawSlots, s2 = kt & 1;
+                    const uint32_t phx = (kt / C::kRawSlots) & 1, ph2 = (kt >> 1) & 1;
+                    if (SPLIT) mbar_wait(&ready_lo[s2], ph2);
+                    else mbar_wait(&full_x[sx], phx);
+                    mbar_wait(&full_w[s2], ph2);
                     tc_fence_after_sync();
-                    const uint32_t ah = smem_u32(a_hi(s)), bh = smem_u32(b_hi(s));
-                    const uint32_t al = smem_u32(a_lo(s)), bl = smem_u32(b_lo(s));
+                    const uint32_t ah = smem_u32(a_hi(sx)), bh = smem_u32(b_hi(s2));
+                    const uint32_t al = smem_u32(a_lo(s2)), bl = smem_u32(b_lo(s2));
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         const uint32_t off = k * kUmmaK * 4;
@@ -210,23 +248,26 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                             umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, (kc | k) != 0);
                         }
                     }
-                    umma_commit(&empty[s]);
+                    umma_commit(&empty_x[sx]);
+                    umma_commit(&empty_w[s2]);
+                    if (SPLIT) umma_commit(&empty_lo[s2]);
                 }
                 umma_commit(&acc_full[ab]);
             }
         }
-    } else if (warp < 6) {
+    } else if (warp >= 4 && warp < 8) {
         // ===== X split: x -> (tf32(x), tf32(x - tf32(x))), element-wise in shared memory =====
         if (SPLIT) {
-            const int t = threadIdx.x - 64;  // 0..127
+            const int t = threadIdx.x - 128;  // 0..127
             int kt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int kc = 0; kc < nk; ++kc, ++kt) {
-                    const int s = kt % C::kStages;
-                    const uint32_t ph = (kt / C::kStages) & 1;
-                    mbar_wait(&full[s], ph);
-                    float4 *hi = reinterpret_cast<float4 *>(a_hi(s));
-                    float4 *lo = reinterpret_cast<float4 *>(a_lo(s));
+                    const int sx = kt % C::kRawSlots, s2 = kt & 1;
+                    const uint32_t phx = (kt / C::kRawSlots) & 1, ph2 = (kt >> 1) & 1;
+                    mbar_wait(&full_x[sx], phx);
+                    mbar_wait(&empty_lo[s2], ph2 ^ 1);
+                    float4 *hi = reinterpret_cast<float4 *>(a_hi(sx));
+                    float4 *lo = reinterpret_cast<float4 *>(a_lo(s2));
 #pragma unroll
                     for (int i = 0; i < kATileBytes / 16 / 128; ++i) {
                         const float4 v = hi[t + i * 128];
@@ -237,13 +278,15 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         lo[t + i * 128] = l;
                     }
                     fence_proxy_async_smem();
-                    mbar_arrive(&ready[s]);
+                    mbar_arrive(&ready_lo[s2]);
                 }
             }
         }
+    } else if (warp < 8) {
+        // warp 3: idle (keeps the epilogue warps aligned to TMEM lane quarters)
     } else {
         // ===== epilogue: TMEM -> registers -> (bias, activation, residual, LayerNorm, pool) -> staged, coalesced stores =====
-        const int t = threadIdx.x - 192;        // 0..127
+        const int t = threadIdx.x - 256;        // 0..127
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int rl = q * 32 + lane;           // row of the tile owned by this thread
         float v[32];
@@ -291,7 +334,16 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 }
             };
 
+            // per-column vectors of this tile -> shared memory (broadcast float4 reads instead of one LDG per element)
+            named_bar_sync(kEpiBar, 128);  // previous tile: staging buffers drained, vectors no longer read
+            for (int c = t; c < BN; c += 128) {
+                const bool ok = c < ncols;
+                svec[c] = (ok && p.bias) ? p.bias[n0 + c] : 0.f;
+                svec[BN + c] = (ok && p.ln_out) ? p.ln_g[n0 + c] : 0.f;
+                svec[2 * BN + c] = (ok && p.ln_out) ? p.ln_b[n0 + c] : 0.f;
+            }
             if (p.pool) {
+                named_bar_sync(kEpiBar, 128);
                 mbar_wait(&acc_full[ab], aph);
                 tc_fence_after_sync();
                 // groups of 16 consecutive rows -> out[row/16, col] = max, out[row/16, N + col] = mean
@@ -301,9 +353,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     float mx[2] = {0.f, 0.f}, sm[2] = {0.f, 0.f};
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int col = n0 + c * 32 + j;
-                        float y = 0.f;
-                        if (row_ok && col < p.N) y = apply_act(v[j] + (p.bias ? __ldg(p.bias + col) : 0.f), p.act);
+                        const float y = apply_act<ACT>(v[j] + svec[c * 32 + j]);
                         float a = y, b = y;
 #pragma unroll
                         for (int d = 8; d >= 1; d >>= 1) {
@@ -324,7 +374,6 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     }
                 }
             } else {
-                named_bar_sync(kEpiBar, 128);  // the previous tile's last chunk store has drained the staging buffers
                 if (p.res) fetch_res(0);       // overlaps with the main loop of this tile
                 mbar_wait(&acc_full[ab], aph);
                 tc_fence_after_sync();
@@ -332,25 +381,28 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 for (int c = 0; c < nch; ++c) {
                     float *mine = buf(c) + rl * kEpiLd;
                     if (p.res) cp_async_wait_all();
-                    named_bar_sync(kEpiBar, 128);  // residual chunk c visible; store of chunk c-1 complete
+                    named_bar_sync(kEpiBar, 128);  // residual chunk c (and the vectors) visible; store of chunk c-1 complete
                     if (p.res && C::kEpiBufs == 2 && c + 1 < nch) fetch_res(c + 1);
                     tmem_ld32(taddr + c * 32, v);
+                    const bool has_res = p.res != nullptr;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const int col = n0 + c * 32 + j;
+                        const float4 b4 = *reinterpret_cast<const float4 *>(svec + c * 32 + j);
                         float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.res) r4 = *reinterpret_cast<const float4 *>(mine + j);
-                        const float *re = &r4.x;
+                        if (has_res) r4 = *reinterpret_cast<const float4 *>(mine + j);
                         float4 y4;
-                        float *ye = &y4.x;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float y = 0.f;
-                            if (col + e < p.N) y = apply_act(v[j + e] + (p.bias ? __ldg(p.bias + col + e) : 0.f), p.act) + re[e];
-                            ye[e] = y;
-                            v[j + e] = y;
-                            sum += y;
+                        y4.x = apply_act<ACT>(v[j] + b4.x) + r4.x;
+                        y4.y = apply_act<ACT>(v[j + 1] + b4.y) + r4.y;
+                        y4.z = apply_act<ACT>(v[j + 2] + b4.z) + r4.z;
+                        y4.w = apply_act<ACT>(v[j + 3] + b4.w) + r4.w;
+                        if (c * 32 + j + 3 >= ncols) {  // ragged right edge: columns >= N contribute nothing
+                            if (c * 32 + j >= ncols) y4.x = 0.f;
+                            if (c * 32 + j + 1 >= ncols) y4.y = 0.f;
+                            if (c * 32 + j + 2 >= ncols) y4.z = 0.f;
+                            y4.w = 0.f;
                         }
+                        v[j] = y4.x, v[j + 1] = y4.y, v[j + 2] = y4.z, v[j + 3] = y4.w;
+                        sum += (y4.x + y4.y) + (y4.z + y4.w);
                         *reinterpret_cast<float4 *>(mine + j) = y4;
                     }
                     if (p.ln_out) tmem_st32(taddr + c * 32, v);  // keep y for the LayerNorm passes
@@ -368,11 +420,10 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     for (int c = 0; c < nch; ++c) {
                         tmem_ld32(taddr + c * 32, v);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j < ncols) {
-                                const float d = v[j] - mean;
-                                var = fmaf(d, d, var);
-                            }
+                        for (int j = 0; j < 32; ++j) {
+                            const float d = (c * 32 + j < ncols) ? v[j] - mean : 0.f;
+                            var = fmaf(d, d, var);
+                        }
                     }
                     const float rstd = 1.0f / sqrtf(var / static_cast<float>(p.N) + p.ln_eps);
                     named_bar_sync(kEpiBar, 128);  // the last stores of the first pass have drained the staging buffers
@@ -382,13 +433,13 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         if (C::kEpiBufs == 1) named_bar_sync(kEpiBar, 128);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
+                            const float4 g4 = *reinterpret_cast<const float4 *>(svec + BN + c * 32 + j);
+                            const float4 b4 = *reinterpret_cast<const float4 *>(svec + 2 * BN + c * 32 + j);
                             float4 y4;
-                            float *ye = &y4.x;
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int col = c * 32 + j + e;
-                                ye[e] = col < ncols ? (v[j + e] - mean) * rstd * __ldg(p.ln_g + col) + __ldg(p.ln_b + col) : 0.f;
-                            }
+                            y4.x = (v[j] - mean) * rstd * g4.x + b4.x;
+                            y4.y = (v[j + 1] - mean) * rstd * g4.y + b4.y;
+                            y4.z = (v[j + 2] - mean) * rstd * g4.z + b4.z;
+                            y4.w = (v[j + 3] - mean) * rstd * g4.w + b4.w;
                             *reinterpret_cast<float4 *>(mine + j) = y4;
                         }
                         named_bar_sync(kEpiBar, 128);
@@ -408,14 +459,14 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
 }
 
-template <int BN, bool SPLIT>
-int launch(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap &mapBlo, LinearParams &p,
-           cudaStream_t stream)
+template <int BN, bool SPLIT, int ACT>
+int launch_act(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap &mapBlo, LinearParams &p,
+               cudaStream_t stream)
 {
     using C = Cfg<BN, SPLIT>;
     static bool configured = false;
     if (!configured) {
-        MAC_CUDA(cudaFuncSetAttribute(linear_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        MAC_CUDA(cudaFuncSetAttribute(linear_kernel<BN, SPLIT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         configured = true;
     }
     p.n_tiles_m = (p.M + kBM - 1) / kBM;
@@ -424,10 +475,19 @@ int launch(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap
     MAC_CUDA(cudaGetDevice(&device));
     const int n_tiles = p.n_tiles_m * p.n_tiles_n;
     const int grid = n_tiles < sm_count(device) ? n_tiles : sm_count(device);
-    linear_kernel<BN, SPLIT><<<grid, kThreads, C::kSmemBytes, stream>>>(mapA, mapBhi, mapBlo, p);
+    linear_kernel<BN, SPLIT, ACT><<<grid, kThreads, C::kSmemBytes, stream>>>(mapA, mapBhi, mapBlo, p);
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return MAC_OK;
+}
+
+template <int BN, bool SPLIT>
+int launch(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap &mapBlo, LinearParams &p,
+           cudaStream_t stream)
+{
+    if (p.act == MAC_LIN_GELU) return launch_act<BN, SPLIT, MAC_LIN_GELU>(mapA, mapBhi, mapBlo, p, stream);
+    if (p.act == MAC_LIN_RELU) return launch_act<BN, SPLIT, MAC_LIN_RELU>(mapA, mapBhi, mapBlo, p, stream);
+    return launch_act<BN, SPLIT, MAC_LIN_NONE>(mapA, mapBhi, mapBlo, p, stream);
 }
 
 }  // namespace
