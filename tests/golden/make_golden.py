@@ -31,6 +31,8 @@ from macarons.networks.Macarons import Macarons  # noqa: E402
 from macarons.utility import scone_utils as ref_su  # noqa: E402
 from macarons.networks.SconeOcc import SconeOcc  # noqa: E402
 from macarons.utility import utils as ref_utils  # noqa: E402
+from macarons.networks import ManyDepth as ref_md  # noqa: E402
+from oracle import depth as o_depth  # noqa: E402
 from oracle import sampling as o_sampling  # noqa: E402
 from oracle import scone_nets as o_nets  # noqa: E402
 from oracle import sh_cov as o_cov  # noqa: E402
@@ -186,8 +188,43 @@ def nets_goldens():
              weights_digest=synth.state_dict_digest(occ_sd), input_digest=digest(pc, x, vh), occupancy=out)
 
 
+# (name, B, H, W, seed, stored row stride)
+DEPTH_CASES = [("depth_64x96", 1, 64, 96, 601, 1), ("depth_96x160_b2", 2, 96, 160, 602, 2)]
+
+
+def reference_many_depth(H, W):
+    """The reference's ManyDepth on a locally built resnet18 (torch.hub is unreachable; torchvision's resnet18 has the
+    topology of pytorch/vision:v0.8.2) -- ManyDepth.py:764-790 without the download."""
+    import torchvision
+    resnet = torchvision.models.resnet18(weights=None)
+    fe = ref_md.FeatureExtractor(resnet)
+    dd = ref_md.DepthDecoder(fe, resnet, input_height=H, input_width=W, input_channels=3)
+    return ref_md.ManyDepth(depth_decoder=dd, pose_decoder=None).eval()
+
+
+def depth_goldens():
+    import warnings
+    warnings.filterwarnings("ignore", message="Default grid_sample")
+    for name, B, H, W, seed, stride in DEPTH_CASES:
+        model = reference_many_depth(H, W)
+        sd = synth.seeded_state_dict(model.state_dict(), NET_WEIGHT_SEED)
+        model.load_state_dict(sd)
+        x, x_alpha, R, T, zfar, gt_pose = synth.depth_inputs(B, H, W, seed)
+        with torch.no_grad():
+            pose, d1, d2, d3, d4 = model(x, x_alpha, R, T, zfar, "cpu", gt_pose=gt_pose)
+            o = o_depth.many_depth_forward(sd, x, x_alpha, R, T, zfar, gt_pose)
+        for a, b, what in zip((pose, d1, d2, d3, d4), o, ("pose", "disp1", "disp2", "disp3", "disp4")):
+            must_equal(a, b, name + " " + what)
+        save(name, B=B, H=H, W=W, seed=seed, weight_seed=NET_WEIGHT_SEED, weights_digest=synth.state_dict_digest(sd),
+             input_digest=digest(x, x_alpha, gt_pose), row_stride=stride, disp1=d1[..., ::stride, ::stride], disp2=d2,
+             disp3=d3, disp4=d4)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--depth-only" in sys.argv:
+        depth_goldens()
+        raise SystemExit(0)
     if "--nets-only" in sys.argv:
         nets_goldens()
         raise SystemExit(0)
@@ -195,4 +232,5 @@ if __name__ == "__main__":
     view_state_goldens()
     sampling_goldens()
     nets_goldens()
+    depth_goldens()
     print("all oracle == reference checks passed (bitwise)")

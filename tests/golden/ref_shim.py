@@ -75,6 +75,15 @@ def install():
                     "renderer.cameras", "renderer.lighting", "loss", "transforms"):
             _placeholder_module("pytorch3d." + sub)
         sys.modules["pytorch3d.ops"].knn_gather = _knn_gather
+        # the depth path executes pytorch3d cameras / rotation conversions: restated stand-ins (oracle/cameras.py)
+        root = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+        if root not in sys.path:
+            sys.path.insert(0, root)
+        from oracle import cameras as _cams
+        sys.modules["pytorch3d.renderer.cameras"].FoVPerspectiveCameras = _cams.FoVPerspectiveCameras
+        sys.modules["pytorch3d.renderer"].FoVPerspectiveCameras = _cams.FoVPerspectiveCameras
+        for _name in ("axis_angle_to_matrix", "matrix_to_quaternion", "quaternion_apply", "quaternion_to_matrix"):
+            setattr(sys.modules["pytorch3d.transforms"], _name, getattr(_cams, _name))
     if "matplotlib" not in sys.modules:
         mpl = types.ModuleType("matplotlib")
         mpl.pyplot = _placeholder_module("matplotlib.pyplot")

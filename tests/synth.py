@@ -54,6 +54,24 @@ def seeded_state_dict(template, seed):
         shape = tuple(template[name].shape)
         gen = torch.Generator(device="cpu").manual_seed((int(seed) * 1000003 + zlib.crc32(name.encode())) % (2 ** 31))
         is_norm = ".norm" in name or name.startswith("norm")
+        if name.endswith("num_batches_tracked"):
+            out[name] = torch.zeros(shape, dtype=torch.long)
+            continue
+        if name.endswith("running_mean"):
+            out[name] = (0.1 * torch.randn(shape, generator=gen)).to(torch.float32)
+            continue
+        if name.endswith("running_var"):
+            out[name] = (0.5 + torch.rand(shape, generator=gen)).to(torch.float32)
+            continue
+        is_bn = ".bn" in name or "downsample.1" in name
+        if len(shape) == 4:       # Conv2d (out, in, kh, kw) / ConvTranspose2d (in, out, kh, kw): Kaiming-normal fan-in
+            fan_in = (shape[0] if ".upconv." in name else shape[1]) * shape[2] * shape[3]
+            out[name] = (torch.randn(shape, generator=gen) * math.sqrt(2.0 / fan_in)).to(torch.float32)
+            continue
+        if is_bn:
+            t = 1.0 + 0.1 * torch.randn(shape, generator=gen) if name.endswith("weight") else 0.1 * torch.randn(shape, generator=gen)
+            out[name] = t.to(torch.float32)
+            continue
         if len(shape) == 2:
             fan_out, fan_in = shape
             if name.split(".")[-2] in ("w_q", "w_k", "w_v"):
@@ -66,7 +84,8 @@ def seeded_state_dict(template, seed):
         elif is_norm:
             t = 0.1 * torch.randn(shape, generator=gen)
         else:
-            fan_in = template[name[:-4] + "weight"].shape[1]
+            w = template[name[:-4] + "weight"]
+            fan_in = w[0].numel() if w.dim() != 4 or ".upconv." not in name else w.shape[0] * w.shape[2] * w.shape[3]
             t = (torch.rand(shape, generator=gen) * 2 - 1) / math.sqrt(fan_in)
         out[name] = t.to(torch.float32)
     return out
@@ -130,3 +149,24 @@ def sconevis_inputs(B, S, seed):
     pts[..., 3] = 0.1 + 0.9 * torch.rand(B, S, generator=gen)
     vh = 0.3 * torch.randn(B, S, 64, generator=gen)
     return pts.contiguous(), vh.contiguous()
+
+
+def depth_inputs(B, H, W, seed, n_alpha=2):
+    """Smooth synthetic frames (low-frequency colour fields, so that the plane sweep is not sampling white noise),
+    identity target camera as in apply_depth_model (utility/macarons_utils.py:917-919) and small relative poses:
+    -> x (B,3,H,W), x_alpha (B,n_alpha,3,H,W), R (B,3,3), T (B,3), zfar (B,), gt_pose (B,n_alpha,6)."""
+    gen = torch.Generator(device="cpu").manual_seed(int(seed))
+
+    def frames(n):
+        low = torch.rand(n, 3, H // 16 + 2, W // 16 + 2, generator=gen)
+        img = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear", align_corners=False)
+        return (0.8 * img + 0.2 * torch.rand(n, 3, H, W, generator=gen)).clamp(0, 1)
+
+    x = frames(B)
+    x_alpha = frames(B * n_alpha).view(B, n_alpha, 3, H, W)
+    R = torch.eye(3).view(1, 3, 3).expand(B, -1, -1).contiguous()
+    T = torch.zeros(B, 3)
+    zfar = torch.full((B,), 750.0)
+    gt_pose = torch.cat((0.02 * (torch.rand(B, n_alpha, 3, generator=gen) - 0.5),       # translation / pose_factor
+                         0.002 * (torch.rand(B, n_alpha, 3, generator=gen) - 0.5)), dim=-1)
+    return x.contiguous(), x_alpha.contiguous(), R, T, zfar, gt_pose.contiguous()
