@@ -140,6 +140,8 @@ int mac_gather_wait_argmax(const float *scores, const unsigned int *flags, int w
 #define MAC_LIN_NONE 0
 #define MAC_LIN_RELU 1
 #define MAC_LIN_GELU 2 /* exact (erf) GELU, torch.nn.GELU() default */
+#define MAC_LIN_ELU 3
+#define MAC_LIN_SIGMOID 4
 
 int mac_linear_f32(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias,
                    float *out, int ldo, int M, int N, int K, int act, const float *res, int ldr, float *ln_out,
@@ -253,6 +255,42 @@ size_t mac_sample_proxy_workspace_bytes(int N);
 int mac_sample_proxy_points_f32(const float *X, const float *preds, const float *view_harmonics, const float *u, int N,
                                 int n_sample, float min_occ, float *res, float *res_harmonics, long long *inverse,
                                 int *counts, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ManyDepth.forward (row a14), /root/reference/macarons/networks/ManyDepth.py:719-758 -> DepthDecoder.forward
+ * :474-531 -> CostVolumeBuilder.forward :207-305, inference mode (BatchNorm folded into the convolutions at packing
+ * time, ground-truth relative poses already composed into per-frame cameras by the caller, ManyDepth.py:740-750).
+ *   mac_conv_w_t   one convolution as the (Cout, kh*kw*Cin) matrix of its weights in (ky, kx, c) order (TF32 halves),
+ *                  its bias, geometry, padding mode (reflect = 1 / zeros = 0) and fused activation (MAC_LIN_*)
+ *   x (B, 3, H, W) target frames, x_alpha (B, n_alpha, 3, H, W) source frames, NCHW fp32 as the reference passes them
+ *   cam (B, 1 + n_alpha, 13): per frame R (9, row-major, X_view = X_world R + T), T (3), zfar (1); record 0 = target
+ *   -> disp1 (B, 1, H, W), disp2 (B, 1, H/2, ceil(W/2)), disp3 (.. /4), disp4 (.. /8) sigmoid disparities.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mac_conv_w {
+    mac_linear_w_t lin;
+    int k, stride, pad, reflect, act;
+} mac_conv_w_t;
+typedef struct mac_block_w { /* torchvision BasicBlock */
+    mac_conv_w_t conv1, conv2, down;
+    int has_down;
+} mac_block_w_t;
+typedef struct mac_expansion_w { /* ExpansionLayer, ManyDepth.py:308-365 */
+    mac_conv_w_t upconv, iconv;
+} mac_expansion_w_t;
+typedef struct mac_manydepth_w {
+    mac_conv_w_t conv1;
+    mac_block_w_t layer1[2], layer2[2], layer3[2], layer4[2];
+    mac_conv_w_t conv_reduce;
+    mac_expansion_w_t expansion[5]; /* expansion5 .. expansion1 */
+    mac_conv_w_t disp[4];           /* disp1 .. disp4 */
+    int n_depth;
+    float d_min, d_max;
+} mac_manydepth_w_t;
+
+size_t mac_manydepth_workspace_bytes(const mac_manydepth_w_t *w, int B, int n_alpha, int H, int W);
+int mac_manydepth_forward_f32(const mac_manydepth_w_t *w, const float *x, const float *x_alpha, const float *cam,
+                              float *disp1, float *disp2, float *disp3, float *disp4, int B, int n_alpha, int H, int W,
+                              void *workspace, size_t workspace_bytes, void *stream);
 
 /* Number of kernel launches the library has enqueued since load (for bench.py's gpu_launches). */
 unsigned long long mac_launch_count(void);

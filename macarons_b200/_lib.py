@@ -81,6 +81,14 @@ SYMBOLS["mac_sample_proxy_points_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p,
                                                          ctypes.c_size_t, ctypes.c_void_p])
 
 
+SYMBOLS["mac_manydepth_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                            ctypes.c_int])
+SYMBOLS["mac_manydepth_forward_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                                       _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                                       ctypes.c_void_p])
+
+
 class MacaronsB200Error(RuntimeError):
     pass
 

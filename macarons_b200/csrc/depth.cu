@@ -1,0 +1,439 @@
+// Multi-frame depth network forward (row a14; reference networks/ManyDepth.py:474-531, 207-305, 719-758), inference
+// mode (BatchNorm folded into the convolutions when the weights are packed, ground-truth relative poses).
+//
+// Activations are NHWC fp32 matrices (n*H*W rows, C columns), so that every convolution is
+//     im2col gather (this file)  ->  tcgen05 linear layer (linear.cu) with bias / ReLU / ELU / sigmoid / residual epilogue
+// with K = kh*kw*Cin ordered (ky, kx, c).  The gather also performs, on the fly, what the reference does with separate
+// tensors: zero or reflect padding, stride, the nearest-neighbour up-sampling of the decoder, and the channel
+// concatenation of skip connections (two sources).  Transposed 3x3 stride-1 convolutions are ordinary convolutions with
+// the flipped kernel (done at packing time).
+//
+// The plane-sweep cost volume (ManyDepth.py:207-297) is one kernel: a warp per (image, depth plane, feature pixel)
+// un-projects the 4x4 full-resolution pixels that the reference's bicubic down-sampling would read, projects them into
+// every source camera, forms the bicubic-weighted sampling position, gathers the 64-channel source features bilinearly
+// and reduces |mean_alpha(warped) - target| over channels with warp shuffles.  The 90 M-float warped tensor, the
+// 96 x H x W x 3 world-point tensor and the per-plane camera batches of the reference are never materialised.
+#include <math.h>
+
+#include "nets.h"
+#include "tc_common.h"
+
+namespace mac {
+
+namespace {
+
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct Act {  // NHWC activation
+    float *p;
+    int n, H, W, C, ld;
+    long long rows() const { return static_cast<long long>(n) * H * W; }
+};
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int n, int C,
+                                                           int H, int W, int ld)
+{
+    const long long total = static_cast<long long>(n) * H * W;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const long long img = i / (static_cast<long long>(H) * W);
+        const long long px = i - img * H * W;
+        for (int c = 0; c < ld; ++c) out[i * ld + c] = c < C ? in[(img * C + c) * H * W + px] : 0.f;
+    }
+}
+
+struct Im2colParams {
+    const float *a;   // source A: (n, Ha, Wa, Ca), nearest up-sampled to (H, W) when Ha != H or Wa != W
+    const float *b;   // source B: (n, H, W, Cb) concatenated behind A's channels (may be null)
+    int lda, ldb, Ca, Cb, Ha, Wa;
+    int n, H, W;      // conv input grid
+    int Ho, Wo, k, stride, pad, reflect;
+    float *col;       // (n*Ho*Wo, ldc), K = k*k*(Ca+Cb) valid columns, the rest zero
+    int ldc;
+    float scale_h, scale_w;  // Ha / H, Wa / W as fp32 (torch nearest: src = min(floor(dst * scale), size - 1))
+};
+
+// one thread per (output pixel, tap); it copies the Ca + Cb channels of that tap
+__global__ void __launch_bounds__(256) im2col_kernel(const Im2colParams p)
+{
+    const int taps = p.k * p.k;
+    const int C = p.Ca + p.Cb;
+    const long long total = static_cast<long long>(p.n) * p.Ho * p.Wo * taps;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const long long row = i / taps;
+        const int tap = static_cast<int>(i - row * taps);
+        const int ky = tap / p.k, kx = tap - ky * p.k;
+        const long long img = row / (static_cast<long long>(p.Ho) * p.Wo);
+        const int rem = static_cast<int>(row - img * p.Ho * p.Wo);
+        const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
+        int y = oy * p.stride - p.pad + ky, x = ox * p.stride - p.pad + kx;
+        bool inside = true;
+        if (p.reflect) {
+            y = y < 0 ? -y : (y >= p.H ? 2 * p.H - 2 - y : y);
+            x = x < 0 ? -x : (x >= p.W ? 2 * p.W - 2 - x : x);
+        } else {
+            inside = y >= 0 && y < p.H && x >= 0 && x < p.W;
+        }
+        float *dst = p.col + row * p.ldc + static_cast<long long>(tap) * C;
+        if (!inside) {
+            for (int c = 0; c < C; ++c) dst[c] = 0.f;
+        } else {
+            int ya = y, xa = x;
+            if (p.Ha != p.H || p.Wa != p.W) {
+                ya = min(static_cast<int>(floorf(static_cast<float>(y) * p.scale_h)), p.Ha - 1);
+                xa = min(static_cast<int>(floorf(static_cast<float>(x) * p.scale_w)), p.Wa - 1);
+            }
+            const float *sa = p.a + ((img * p.Ha + ya) * p.Wa + xa) * p.lda;
+            for (int c = 0; c < p.Ca; ++c) dst[c] = sa[c];
+            if (p.b) {
+                const float *sb = p.b + ((img * p.H + y) * p.W + x) * p.ldb;
+                for (int c = 0; c < p.Cb; ++c) dst[p.Ca + c] = sb[c];
+            }
+        }
+        if (tap == taps - 1)
+            for (int c = taps * C; c < p.ldc; ++c) p.col[row * p.ldc + c] = 0.f;
+    }
+}
+
+// 3x3 stride-2 pad-1 max pooling, NHWC; one thread per (output pixel, 4 channels)
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const float *__restrict__ in, float *__restrict__ out, int n, int H,
+                                                           int W, int C, int Ho, int Wo)
+{
+    const int c4 = C / 4;
+    const long long total = static_cast<long long>(n) * Ho * Wo * c4;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const int c = static_cast<int>(i % c4);
+        const long long px = i / c4;
+        const long long img = px / (static_cast<long long>(Ho) * Wo);
+        const int rem = static_cast<int>(px - img * Ho * Wo);
+        const int oy = rem / Wo, ox = rem - oy * Wo;
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int y = 2 * oy + dy, x = 2 * ox + dx;
+                if (y < 0 || y >= H || x < 0 || x >= W) continue;
+                const float4 v = *reinterpret_cast<const float4 *>(in + ((img * H + y) * W + x) * C + 4 * c);
+                m.x = fmaxf(m.x, v.x), m.y = fmaxf(m.y, v.y), m.z = fmaxf(m.z, v.z), m.w = fmaxf(m.w, v.w);
+            }
+        *reinterpret_cast<float4 *>(out + px * C + 4 * c) = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plane-sweep cost volume.
+// cam: per batch element (1 + n_alpha) records of 13 floats: R (9, row-major, X_view = X_world R + T), T (3), zfar.
+// ------------------------------------------------------------------------------------------------
+struct CostVolumeParams {
+    const float *feat_t;  // (B, fh, fw, C) target features
+    const float *feat_s;  // (B*n_alpha, fh, fw, C) source features
+    const float *cam;     // (B, 1 + n_alpha, 13)
+    float *cv;            // (B, fh, fw, n_depth)
+    int B, n_alpha, H, W, fh, fw, C, n_depth;
+    float d_min, d_max;
+    float scale_h, scale_w;  // H / fh, W / fw  (bicubic resize of the sampling grid, align_corners = False)
+};
+
+__device__ __forceinline__ void cubic_weights(float t, float (&w)[4])
+{
+    const float A = -0.75f;
+    const float x0 = t + 1.f, x3 = 2.f - t, u = 1.f - t;
+    w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+    w[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+    w[2] = ((A + 2.f) * u - (A + 3.f)) * u * u + 1.f;
+    w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+__global__ void __launch_bounds__(256) cost_volume_kernel(const CostVolumeParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const long long n_warps = static_cast<long long>(p.B) * p.n_depth * p.fh * p.fw;
+    const float s = 1.7320508075688772f;  // 1 / tan(fov / 2), fov = 60 degrees (FoVPerspectiveCameras default)
+    const int m_full = min(p.W, p.H), m_feat = min(p.fw, p.fh);
+    for (long long wid = blockIdx.x * 8ll + (threadIdx.x >> 5); wid < n_warps; wid += gridDim.x * 8ll) {
+        // consecutive warps share the feature pixel neighbourhood: (b, y, x, d) with d fastest keeps the gathers in L1/L2
+        const int d = static_cast<int>(wid % p.n_depth);
+        long long r = wid / p.n_depth;
+        const int fx = static_cast<int>(r % p.fw);
+        r /= p.fw;
+        const int fy = static_cast<int>(r % p.fh);
+        const int b = static_cast<int>(r / p.fh);
+        const float depth = p.d_min + (p.d_max - p.d_min) * static_cast<float>(d) / static_cast<float>(p.n_depth - 1);
+        const float *cam_t = p.cam + static_cast<size_t>(b) * (1 + p.n_alpha) * 13;
+
+        // bicubic taps of the full-resolution grid that feed this feature pixel
+        const float sy = (static_cast<float>(fy) + 0.5f) * p.scale_h - 0.5f, sx = (static_cast<float>(fx) + 0.5f) * p.scale_w - 0.5f;
+        const int iy = static_cast<int>(floorf(sy)), ix = static_cast<int>(floorf(sx));
+        float wy[4], wx[4];
+        cubic_weights(sy - static_cast<float>(iy), wy);
+        cubic_weights(sx - static_cast<float>(ix), wx);
+        const int ty = (lane & 15) >> 2, tx = lane & 3;       // lanes 0-15 (and 16-31, duplicated) own one tap each
+        const int py = min(max(iy - 1 + ty, 0), p.H - 1), px = min(max(ix - 1 + tx, 0), p.W - 1);
+        // un-project pixel (py, px) at this depth: NDC grid of ManyDepth.py:128-129, then view -> world
+        const float ndc_x = static_cast<float>(p.W) / m_full - (static_cast<float>(px) / (m_full - 1)) * 2.f;
+        const float ndc_y = static_cast<float>(p.H) / m_full - (static_cast<float>(py) / (m_full - 1)) * 2.f;
+        const float vx = ndc_x * depth / s - cam_t[9], vy = ndc_y * depth / s - cam_t[10], vz = depth - cam_t[11];
+        const float X = vx * cam_t[0] + vy * cam_t[1] + vz * cam_t[2];   // (X_view - T) R^T
+        const float Y = vx * cam_t[3] + vy * cam_t[4] + vz * cam_t[5];
+        const float Z = vx * cam_t[6] + vy * cam_t[7] + vz * cam_t[8];
+        const float wtap = wy[ty] * wx[tx];
+
+        float acc0 = 0.f, acc1 = 0.f;  // sum over source frames of the warped features, channels lane and lane + 32
+        for (int a = 0; a < p.n_alpha; ++a) {
+            const float *cs = cam_t + (1 + a) * 13;
+            // world -> source view -> NDC (w clamped away from 0 like transform_points(eps=1e-8)) -> grid_sample coords
+            const float qx = X * cs[0] + Y * cs[3] + Z * cs[6] + cs[9];
+            const float qy = X * cs[1] + Y * cs[4] + Z * cs[7] + cs[10];
+            float qw = X * cs[2] + Y * cs[5] + Z * cs[8] + cs[11];
+            const float sgn = qw < 0.f ? -1.f : 1.f;
+            qw = sgn * fmaxf(fabsf(qw), 1e-8f);
+            float gx = (-static_cast<float>(m_feat) / p.fw) * (s * qx / qw) * wtap;
+            float gy = (-static_cast<float>(m_feat) / p.fh) * (s * qy / qw) * wtap;
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) {
+                gx += __shfl_xor_sync(0xffffffffu, gx, o);
+                gy += __shfl_xor_sync(0xffffffffu, gy, o);
+            }
+            // bilinear gather, zeros padding, align_corners = False
+            const float fxp = ((gx + 1.f) * p.fw - 1.f) * 0.5f, fyp = ((gy + 1.f) * p.fh - 1.f) * 0.5f;
+            const float x0f = floorf(fxp), y0f = floorf(fyp);
+            const float ax = fxp - x0f, ay = fyp - y0f;
+            const float *src = p.feat_s + (static_cast<size_t>(b) * p.n_alpha + a) * p.fh * p.fw * p.C;
+            float v0 = 0.f, v1 = 0.f;
+            // (coordinates far outside the image, inf or NaN contribute nothing, as in grid_sample)
+            if (fxp > -2.f && fxp < p.fw + 1.f && fyp > -2.f && fyp < p.fh + 1.f) {
+                const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+                    const float wgt = ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay);
+                    if (xx >= 0 && xx < p.fw && yy >= 0 && yy < p.fh) {
+                        const float *px_ = src + (static_cast<size_t>(yy) * p.fw + xx) * p.C;
+                        v0 = fmaf(wgt, px_[lane], v0);
+                        if (lane + 32 < p.C) v1 = fmaf(wgt, px_[lane + 32], v1);
+                    }
+                }
+            }
+            acc0 += v0;
+            acc1 += v1;
+        }
+        const float inv_a = 1.f / static_cast<float>(p.n_alpha);
+        const float *tgt = p.feat_t + ((static_cast<size_t>(b) * p.fh + fy) * p.fw + fx) * p.C;
+        float cost = fabsf(acc0 * inv_a - tgt[lane]);
+        if (lane + 32 < p.C) cost += fabsf(acc1 * inv_a - tgt[lane + 32]);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+        if (lane == 0) p.cv[((static_cast<size_t>(b) * p.fh + fy) * p.fw + fx) * p.n_depth + d] = cost / static_cast<float>(p.C);
+    }
+}
+
+int grid_for(long long total, int per_block, int max_blocks)
+{
+    const long long want = (total + per_block - 1) / per_block;
+    return static_cast<int>(want < max_blocks ? (want < 1 ? 1 : want) : max_blocks);
+}
+
+// ---- host-side layer helpers ---------------------------------------------------------------------
+struct Ctx {
+    unsigned char *base;
+    size_t used, cap;
+    float *col;
+    size_t col_floats;
+    cudaStream_t st;
+    bool overflow;
+    float *alloc(size_t n)
+    {
+        float *q = reinterpret_cast<float *>(base + used);
+        used += align256(n * sizeof(float));
+        if (used > cap) overflow = true;
+        return q;
+    }
+    Act act(int n, int H, int W, int C)
+    {
+        Act a{nullptr, n, H, W, C, (C + 3) / 4 * 4};
+        a.p = alloc(static_cast<size_t>(a.rows()) * a.ld);
+        return a;
+    }
+};
+
+// conv(cat(upsample(a), b)) + bias -> activation (+ residual); returns the output activation
+int conv(Ctx &cx, const mac_conv_w_t &w, const Act &a, const Act *b, int H, int W, const Act *res, int res_first, Act &out)
+{
+    const int Ca = a.C, Cb = b ? b->C : 0;
+    MAC_REQUIRE(w.lin.K == w.k * w.k * (Ca + Cb), "conv weight K=%d does not match %dx%dx(%d+%d)", w.lin.K, w.k, w.k, Ca, Cb);
+    const int Ho = (H + 2 * w.pad - w.k) / w.stride + 1, Wo = (W + 2 * w.pad - w.k) / w.stride + 1;
+    out = cx.act(a.n, Ho, Wo, w.lin.N);
+    if (cx.overflow) return MAC_OK;  // sizing pass / error reported by the caller
+    Im2colParams p{};
+    p.a = a.p, p.lda = a.ld, p.Ca = Ca, p.Ha = a.H, p.Wa = a.W;
+    p.b = b ? b->p : nullptr, p.ldb = b ? b->ld : 0, p.Cb = Cb;
+    p.n = a.n, p.H = H, p.W = W, p.Ho = Ho, p.Wo = Wo, p.k = w.k, p.stride = w.stride, p.pad = w.pad, p.reflect = w.reflect;
+    p.ldc = w.lin.ldw;
+    p.col = cx.col;
+    p.scale_h = static_cast<float>(a.H) / static_cast<float>(H), p.scale_w = static_cast<float>(a.W) / static_cast<float>(W);
+    const long long rows = out.rows();
+    MAC_REQUIRE(static_cast<size_t>(rows) * p.ldc <= cx.col_floats, "im2col buffer too small");
+    if (w.k == 1 && w.stride == 1 && !b && a.H == H && a.W == W && a.ld == p.ldc) {
+        // 1x1 stride-1: the activation matrix already is the im2col matrix
+        return linear_forward(a.p, a.ld, w.lin.hi, w.lin.lo, w.lin.ldw, w.lin.bias, out.p, out.ld, static_cast<int>(rows), w.lin.N,
+                              w.lin.K, w.act, res ? res->p : nullptr, res ? res->ld : 0, nullptr, 0, nullptr, nullptr, 0.f, 0,
+                              cx.st, res_first);
+    }
+    im2col_kernel<<<grid_for(rows * w.k * w.k, 256, 148 * 32), 256, 0, cx.st>>>(p);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return linear_forward(cx.col, p.ldc, w.lin.hi, w.lin.lo, w.lin.ldw, w.lin.bias, out.p, out.ld, static_cast<int>(rows), w.lin.N,
+                          w.lin.K, w.act, res ? res->p : nullptr, res ? res->ld : 0, nullptr, 0, nullptr, nullptr, 0.f, 0, cx.st,
+                          res_first);
+}
+
+// torchvision BasicBlock: conv3x3-bn-relu, conv3x3-bn, (+ downsampled) identity, relu
+int basic_block(Ctx &cx, const mac_block_w_t &w, const Act &x, Act &out)
+{
+    Act t, ds;
+    if (int rc = conv(cx, w.conv1, x, nullptr, x.H, x.W, nullptr, 0, t)) return rc;
+    const Act *identity = &x;
+    if (w.has_down) {
+        if (int rc = conv(cx, w.down, x, nullptr, x.H, x.W, nullptr, 0, ds)) return rc;
+        identity = &ds;
+    }
+    return conv(cx, w.conv2, t, nullptr, t.H, t.W, identity, 1, out);
+}
+
+int expansion(Ctx &cx, const mac_expansion_w_t &w, const Act &x, const Act *skip, int Ho, int Wo, Act &out)
+{
+    Act u;
+    if (int rc = conv(cx, w.upconv, x, nullptr, x.H, x.W, nullptr, 0, u)) return rc;
+    return conv(cx, w.iconv, u, skip, Ho, Wo, nullptr, 0, out);   // nearest up-sampling + concat inside the gather
+}
+
+int disparity(Ctx &cx, const mac_conv_w_t &w, const Act &x, float *dst)
+{
+    Act d;
+    if (int rc = conv(cx, w, x, nullptr, x.H, x.W, nullptr, 0, d)) return rc;
+    if (cx.overflow) return MAC_OK;
+    MAC_CUDA(cudaMemcpy2DAsync(dst, sizeof(float), d.p, d.ld * sizeof(float), sizeof(float), d.rows(), cudaMemcpyDeviceToDevice,
+                               cx.st));
+    return MAC_OK;
+}
+
+int forward_impl(Ctx &cx, const mac_manydepth_w_t *w, const float *x, const float *x_alpha, const float *cam, float *disp[4],
+                 int B, int n_alpha, int H, int W)
+{
+    const int n_img = B * (1 + n_alpha);
+    // all frames through the feature extractor as one batch: [targets | sources]
+    Act img = cx.act(n_img, H, W, 3);
+    if (!cx.overflow) {
+        nchw_to_nhwc_kernel<<<grid_for(static_cast<long long>(B) * H * W, 256, 148 * 16), 256, 0, cx.st>>>(x, img.p, B, 3, H, W, img.ld);
+        nchw_to_nhwc_kernel<<<grid_for(static_cast<long long>(B) * n_alpha * H * W, 256, 148 * 16), 256, 0, cx.st>>>(
+            x_alpha, img.p + static_cast<size_t>(B) * H * W * img.ld, B * n_alpha, 3, H, W, img.ld);
+        MAC_CUDA(cudaGetLastError());
+        count_launch(2);
+    }
+    Act c1, mp, l1a, l1;
+    if (int rc = conv(cx, w->conv1, img, nullptr, H, W, nullptr, 0, c1)) return rc;
+    const int Hp = (c1.H + 2 - 3) / 2 + 1, Wp = (c1.W + 2 - 3) / 2 + 1;
+    mp = cx.act(n_img, Hp, Wp, c1.C);
+    if (!cx.overflow) {
+        maxpool3x3s2_kernel<<<grid_for(mp.rows() * (c1.C / 4), 256, 148 * 16), 256, 0, cx.st>>>(c1.p, mp.p, n_img, c1.H, c1.W, c1.C, Hp, Wp);
+        MAC_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    if (int rc = basic_block(cx, w->layer1[0], mp, l1a)) return rc;
+    if (int rc = basic_block(cx, w->layer1[1], l1a, l1)) return rc;
+
+    // views of the target part of the batch
+    Act img_t = img, c1_t = c1, l1_t = l1;
+    img_t.n = c1_t.n = l1_t.n = B;
+    const int fh = l1.H, fw = l1.W;
+    Act cv = cx.act(B, fh, fw, w->n_depth);
+    if (!cx.overflow) {
+        CostVolumeParams p{};
+        p.feat_t = l1.p;
+        p.feat_s = l1.p + static_cast<size_t>(B) * fh * fw * l1.ld;
+        p.cam = cam, p.cv = cv.p;
+        p.B = B, p.n_alpha = n_alpha, p.H = H, p.W = W, p.fh = fh, p.fw = fw, p.C = l1.C, p.n_depth = w->n_depth;
+        p.d_min = w->d_min, p.d_max = w->d_max;
+        p.scale_h = static_cast<float>(H) / static_cast<float>(fh), p.scale_w = static_cast<float>(W) / static_cast<float>(fw);
+        cost_volume_kernel<<<grid_for(static_cast<long long>(B) * w->n_depth * fh * fw, 8, 148 * 32), 256, 0, cx.st>>>(p);
+        MAC_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    Act red, t, l2, l3, l4, i5, i4, i3, i2, i1;
+    if (int rc = conv(cx, w->conv_reduce, l1_t, &cv, fh, fw, nullptr, 0, red)) return rc;
+    if (int rc = basic_block(cx, w->layer2[0], red, t)) return rc;
+    if (int rc = basic_block(cx, w->layer2[1], t, l2)) return rc;
+    if (int rc = basic_block(cx, w->layer3[0], l2, t)) return rc;
+    if (int rc = basic_block(cx, w->layer3[1], t, l3)) return rc;
+    if (int rc = basic_block(cx, w->layer4[0], l3, t)) return rc;
+    if (int rc = basic_block(cx, w->layer4[1], t, l4)) return rc;
+    auto up = [&](int d, int &ho, int &wo) { ho = H / d, wo = W / d + (W % d > 0 ? 1 : 0); };
+    int ho, wo;
+    up(16, ho, wo);
+    if (int rc = expansion(cx, w->expansion[0], l4, &l3, ho, wo, i5)) return rc;
+    up(8, ho, wo);
+    if (int rc = expansion(cx, w->expansion[1], i5, &l2, ho, wo, i4)) return rc;
+    up(4, ho, wo);
+    if (int rc = expansion(cx, w->expansion[2], i4, &l1_t, ho, wo, i3)) return rc;
+    up(2, ho, wo);
+    if (int rc = expansion(cx, w->expansion[3], i3, &c1_t, ho, wo, i2)) return rc;
+    if (int rc = expansion(cx, w->expansion[4], i2, &img_t, H, W, i1)) return rc;
+    if (int rc = disparity(cx, w->disp[0], i1, disp[0])) return rc;
+    if (int rc = disparity(cx, w->disp[1], i2, disp[1])) return rc;
+    if (int rc = disparity(cx, w->disp[2], i3, disp[2])) return rc;
+    if (int rc = disparity(cx, w->disp[3], i4, disp[3])) return rc;
+    return MAC_OK;
+}
+
+size_t col_floats_needed(int B, int n_alpha, int H, int W)
+{
+    // largest im2col matrix: conv1 (all frames, 7x7x3 at half resolution) vs the full-resolution decoder convolutions
+    const size_t n_img = static_cast<size_t>(B) * (1 + n_alpha);
+    const size_t conv1 = n_img * ((H + 1) / 2) * ((W + 1) / 2) * 148;
+    const size_t layer1 = n_img * ((H + 3) / 4) * ((W + 3) / 4) * 576;
+    const size_t dec = static_cast<size_t>(B) * H * W * 172;          // expansion1.iconv: 3x3x(16+3) -> 171
+    const size_t dec2 = static_cast<size_t>(B) * ((H + 1) / 2) * ((W + 1) / 2) * 864;  // expansion2.iconv: 3x3x(32+64)
+    size_t m = conv1 > layer1 ? conv1 : layer1;
+    m = m > dec ? m : dec;
+    return (m > dec2 ? m : dec2) + 1024;
+}
+
+}  // namespace
+
+}  // namespace mac
+
+using namespace mac;
+
+extern "C" size_t mac_manydepth_workspace_bytes(const mac_manydepth_w_t *w, int B, int n_alpha, int H, int W)
+{
+    // dry run of the layer sequence with a zero-capacity arena: nothing is launched, only the allocations are added up
+    if (!w || B <= 0 || n_alpha <= 0 || H < 32 || W < 32) return 0;
+    Ctx cx{nullptr, 0, 0, nullptr, 0, nullptr, false};
+    cx.col_floats = col_floats_needed(B, n_alpha, H, W);
+    cx.col = cx.alloc(cx.col_floats);
+    float *disp[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (forward_impl(cx, w, nullptr, nullptr, nullptr, disp, B, n_alpha, H, W) != MAC_OK) return 0;
+    return cx.used + 4096;
+}
+
+extern "C" int mac_manydepth_forward_f32(const mac_manydepth_w_t *w, const float *x, const float *x_alpha, const float *cam,
+                                         float *disp1, float *disp2, float *disp3, float *disp4, int B, int n_alpha, int H, int W,
+                                         void *workspace, size_t workspace_bytes, void *stream)
+{
+    MAC_REQUIRE(w && x && x_alpha && cam && disp1 && disp2 && disp3 && disp4 && workspace, "null pointer");
+    MAC_REQUIRE(B > 0 && n_alpha > 0 && H >= 32 && W >= 32 && H % 16 == 0, "need B > 0, n_alpha > 0, H, W >= 32 and H %% 16 == 0");
+    MAC_REQUIRE(w->n_depth > 1 && w->n_depth <= 256, "bad number of depth planes %d", w->n_depth);
+    Ctx cx{static_cast<unsigned char *>(workspace), 0, workspace_bytes, nullptr, 0, static_cast<cudaStream_t>(stream), false};
+    cx.col_floats = col_floats_needed(B, n_alpha, H, W);
+    cx.col = cx.alloc(cx.col_floats);
+    float *disp[4] = {disp1, disp2, disp3, disp4};
+    if (cx.overflow) {
+        set_error("workspace too small: need %zu bytes, got %zu", mac_manydepth_workspace_bytes(w, B, n_alpha, H, W), workspace_bytes);
+        return MAC_ERR_WORKSPACE;
+    }
+    const int rc = forward_impl(cx, w, x, x_alpha, cam, disp, B, n_alpha, H, W);
+    if (rc == MAC_OK && cx.overflow) {
+        set_error("workspace too small: need %zu bytes, got %zu (enqueued work is incomplete)", cx.used, workspace_bytes);
+        return MAC_ERR_WORKSPACE;
+    }
+    return rc;
+}

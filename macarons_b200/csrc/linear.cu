@@ -90,7 +90,8 @@ struct LinearParams {
     const float *ln_g, *ln_b;
     float ln_eps;
     int act;
-    int pool;  // 0, or 16: max | mean over groups of 16 rows -> out (M/16, 2N)
+    int pool;       // 0, or 16: max | mean over groups of 16 rows -> out (M/16, 2N)
+    int res_first;  // 1: out = act(acc + bias + res) (ResNet blocks); 0: out = act(acc + bias) + res (transformer residuals)
 };
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -100,6 +101,8 @@ __device__ __forceinline__ float apply_act(float y)
 {
     if (ACT == MAC_LIN_RELU) return fmaxf(y, 0.f);
     if (ACT == MAC_LIN_GELU) return gelu_exact(y);
+    if (ACT == MAC_LIN_ELU) return y > 0.f ? y : expf(y) - 1.0f;
+    if (ACT == MAC_LIN_SIGMOID) return 1.0f / (1.0f + expf(-y));
     return y;
 }
 
@@ -385,16 +388,17 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     if (p.res && C::kEpiBufs == 2 && c + 1 < nch) fetch_res(c + 1);
                     tmem_ld32(taddr + c * 32, v);
                     const bool has_res = p.res != nullptr;
+                    const float pre = p.res_first ? 1.f : 0.f, post = 1.f - pre;   // where the residual enters
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b4 = *reinterpret_cast<const float4 *>(svec + c * 32 + j);
                         float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (has_res) r4 = *reinterpret_cast<const float4 *>(mine + j);
                         float4 y4;
-                        y4.x = apply_act<ACT>(v[j] + b4.x) + r4.x;
-                        y4.y = apply_act<ACT>(v[j + 1] + b4.y) + r4.y;
-                        y4.z = apply_act<ACT>(v[j + 2] + b4.z) + r4.z;
-                        y4.w = apply_act<ACT>(v[j + 3] + b4.w) + r4.w;
+                        y4.x = apply_act<ACT>(v[j] + b4.x + pre * r4.x) + post * r4.x;
+                        y4.y = apply_act<ACT>(v[j + 1] + b4.y + pre * r4.y) + post * r4.y;
+                        y4.z = apply_act<ACT>(v[j + 2] + b4.z + pre * r4.z) + post * r4.z;
+                        y4.w = apply_act<ACT>(v[j + 3] + b4.w + pre * r4.w) + post * r4.w;
                         if (c * 32 + j + 3 >= ncols) {  // ragged right edge: columns >= N contribute nothing
                             if (c * 32 + j >= ncols) y4.x = 0.f;
                             if (c * 32 + j + 1 >= ncols) y4.y = 0.f;
@@ -487,6 +491,8 @@ int launch(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap
 {
     if (p.act == MAC_LIN_GELU) return launch_act<BN, SPLIT, MAC_LIN_GELU>(mapA, mapBhi, mapBlo, p, stream);
     if (p.act == MAC_LIN_RELU) return launch_act<BN, SPLIT, MAC_LIN_RELU>(mapA, mapBhi, mapBlo, p, stream);
+    if (p.act == MAC_LIN_ELU) return launch_act<BN, SPLIT, MAC_LIN_ELU>(mapA, mapBhi, mapBlo, p, stream);
+    if (p.act == MAC_LIN_SIGMOID) return launch_act<BN, SPLIT, MAC_LIN_SIGMOID>(mapA, mapBhi, mapBlo, p, stream);
     return launch_act<BN, SPLIT, MAC_LIN_NONE>(mapA, mapBhi, mapBlo, p, stream);
 }
 
@@ -494,11 +500,11 @@ int launch(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap
 
 int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias, float *out,
                    int ldo, int M, int N, int K, int act, const float *res, int ldr, float *ln_out, int ldl,
-                   const float *ln_g, const float *ln_b, float ln_eps, int pool, cudaStream_t stream)
+                   const float *ln_g, const float *ln_b, float ln_eps, int pool, cudaStream_t stream, int res_first)
 {
     MAC_REQUIRE(X && W_hi && (out || ln_out), "null tensor pointer");
     MAC_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive (got %d, %d, %d)", M, N, K);
-    MAC_REQUIRE(act == MAC_LIN_NONE || act == MAC_LIN_RELU || act == MAC_LIN_GELU, "bad activation %d", act);
+    MAC_REQUIRE(act >= MAC_LIN_NONE && act <= MAC_LIN_SIGMOID, "bad activation %d", act);
     MAC_REQUIRE(pool == 0 || pool == 16, "pool must be 0 or 16");
     MAC_REQUIRE(!pool || (M % 16 == 0 && out && !ln_out), "pooling needs M %% 16 == 0 and no LayerNorm output");
     MAC_REQUIRE(!ln_out || (N <= 256 && ln_g && ln_b && ldl % 4 == 0), "fused LayerNorm needs N <= 256, gamma and beta");
@@ -527,7 +533,7 @@ int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo
     p.out = out, p.ldo = ldo;
     p.res = res, p.ldr = ldr;
     p.ln_out = ln_out, p.ldl = ldl, p.ln_g = ln_g, p.ln_b = ln_b, p.ln_eps = ln_eps;
-    p.act = act, p.pool = pool;
+    p.act = act, p.pool = pool, p.res_first = res_first;
 
     if (split) {
         if (bn == 64) return launch<64, true>(mapA, mapBhi, mapBlo, p, stream);

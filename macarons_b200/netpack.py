@@ -161,3 +161,99 @@ def pack_sconeocc(occ):
         pk.linear(occ.linear3.weight, occ.linear3.bias, w.lin3)
         return w, pk
     return _cached(occ, build)
+
+
+# ---- ManyDepth (include/macarons_b200.h: mac_conv_w_t ... mac_manydepth_w_t) ------------------------
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3, 4
+
+
+class ConvW(ctypes.Structure):
+    _fields_ = [("lin", LinearW), ("k", ctypes.c_int), ("stride", ctypes.c_int), ("pad", ctypes.c_int),
+                ("reflect", ctypes.c_int), ("act", ctypes.c_int)]
+
+
+class BlockW(ctypes.Structure):
+    _fields_ = [("conv1", ConvW), ("conv2", ConvW), ("down", ConvW), ("has_down", ctypes.c_int)]
+
+
+class ExpansionW(ctypes.Structure):
+    _fields_ = [("upconv", ConvW), ("iconv", ConvW)]
+
+
+class ManyDepthW(ctypes.Structure):
+    _fields_ = [("conv1", ConvW), ("layer1", BlockW * 2), ("layer2", BlockW * 2), ("layer3", BlockW * 2),
+                ("layer4", BlockW * 2), ("conv_reduce", ConvW), ("expansion", ExpansionW * 5), ("disp", ConvW * 4),
+                ("n_depth", ctypes.c_int), ("d_min", ctypes.c_float), ("d_max", ctypes.c_float)]
+
+
+def _fold_bn(weight, bias, bn):
+    """Conv weight (Cout, Cin, kh, kw) followed by an eval-mode BatchNorm2d -> equivalent weight and bias (float64 math)."""
+    w = weight.detach().double()
+    b = torch.zeros(w.shape[0], dtype=torch.float64, device=w.device) if bias is None else bias.detach().double()
+    if bn is not None:
+        scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = (b - bn.running_mean.detach().double()) * scale + bn.bias.detach().double()
+    return w, b
+
+
+def _pack_conv(pk, dst, conv, bn, act, transposed=False):
+    weight = conv.weight
+    k = weight.shape[-1]
+    if transposed:   # ConvTranspose2d(k, stride 1, padding p) == Conv2d with the flipped kernel, padding k - 1 - p
+        if conv.stride != (1, 1) or conv.output_padding != (0, 0):
+            raise NotImplementedError("only stride-1 transposed convolutions are on the depth path")
+        weight = weight.detach().flip(-1, -2).transpose(0, 1)
+        pad, stride, reflect = k - 1 - conv.padding[0], 1, 0
+    else:
+        pad, stride = conv.padding[0], conv.stride[0]
+        reflect = 1 if conv.padding_mode == "reflect" else 0
+        if conv.padding_mode not in ("zeros", "reflect"):
+            raise NotImplementedError("padding mode %s" % conv.padding_mode)
+    w, b = _fold_bn(weight, conv.bias, bn)
+    mat = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.float32)   # (Cout, ky, kx, c)
+    pk.linear(mat, b.to(torch.float32), dst.lin)
+    dst.k, dst.stride, dst.pad, dst.reflect, dst.act = k, stride, pad, reflect, act
+
+
+def _pack_block(pk, dst, block):
+    _pack_conv(pk, dst.conv1, block.conv1, block.bn1, ACT_RELU)
+    _pack_conv(pk, dst.conv2, block.conv2, block.bn2, ACT_RELU)     # ReLU after the residual add (res_first)
+    dst.has_down = 0
+    if getattr(block, "downsample", None) is not None:
+        _pack_conv(pk, dst.down, block.downsample[0], block.downsample[1], ACT_NONE)
+        dst.has_down = 1
+
+
+def pack_manydepth(model):
+    """-> ManyDepthW (kept alive on the module).  BatchNorm is folded with its running statistics (inference)."""
+    def build():
+        dd = model.depth_decoder
+        pk, w = _Packer(), ManyDepthW()
+        fe = dd.feature_extractor
+        _pack_conv(pk, w.conv1, fe.conv1, fe.bn1, ACT_RELU)
+        for dst, layer in ((w.layer1, fe.layer), (w.layer2, dd.resnet_layer_2), (w.layer3, dd.resnet_layer_3),
+                           (w.layer4, dd.resnet_layer_4)):
+            if len(layer) != 2:
+                raise NotImplementedError("the depth path is built for ResNet-18 (2 blocks per layer)")
+            for i in range(2):
+                _pack_block(pk, dst[i], layer[i])
+        cvb = dd.cost_volume_builder
+        _pack_conv(pk, w.conv_reduce, cvb.conv_reduce, None, ACT_RELU)
+        for i, exp in enumerate((dd.expansion5, dd.expansion4, dd.expansion3, dd.expansion2, dd.expansion1)):
+            _pack_conv(pk, w.expansion[i].upconv, exp.upconv, None, ACT_ELU, transposed=True)
+            _pack_conv(pk, w.expansion[i].iconv, exp.iconv, None, ACT_ELU)
+        for i, disp in enumerate((dd.disp1, dd.disp2, dd.disp3, dd.disp4)):
+            _pack_conv(pk, w.disp[i], disp.conv, None, ACT_SIGMOID)
+        w.n_depth, w.d_min, w.d_max = int(cvb.n_depth), float(cvb.d_min), float(cvb.d_max)
+        return w, pk
+
+    def fingerprint():
+        return tuple((t.data_ptr(), t._version, t.device.index) for t in list(model.parameters()) + list(model.buffers()))
+
+    cache = model.__dict__.get("_mac_pack")
+    fp = fingerprint()
+    if cache is None or cache[0] != fp:
+        cache = (fp,) + build()
+        model.__dict__["_mac_pack"] = cache
+    return cache[1]

@@ -349,3 +349,30 @@ def sample_proxy_points(X_world, preds, view_harmonics, u, min_occ):
                                                    ws.numel(), _stream_ptr(dev)))
     n_unique = int(counts[1].item())   # the result has a data-dependent length (as torch.unique in the reference)
     return res[:n_unique], res_h[:n_unique], inverse
+
+
+def manydepth_forward(w, x, x_alpha, cam):
+    """Packed weights (netpack.ManyDepthW); x (B,3,H,W), x_alpha (B,n_alpha,3,H,W), cam (B,1+n_alpha,13)
+    -> (disp1 (B,1,H,W), disp2, disp3, disp4)."""
+    import ctypes
+    for name, t in (("x", x), ("x_alpha", x_alpha), ("cam", cam)):
+        _require_cuda_f32(name, t)
+    B, C, H, W = x.shape
+    n_alpha = x_alpha.shape[1]
+    if C != 3 or tuple(x_alpha.shape) != (B, n_alpha, 3, H, W) or tuple(cam.shape) != (B, 1 + n_alpha, 13):
+        raise ValueError("expected x (B,3,H,W), x_alpha (B,n_alpha,3,H,W), cam (B,1+n_alpha,13)")
+    x, x_alpha, cam = x.contiguous(), x_alpha.contiguous(), cam.contiguous()
+    dev = x.device
+    sizes = [(H, W)] + [(H // d, W // d + (1 if W % d else 0)) for d in (2, 4, 8)]
+    disps = [torch.empty((B, 1, h, w_), dtype=torch.float32, device=dev) for h, w_ in sizes]
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        need = lib.mac_manydepth_workspace_bytes(ctypes.byref(w), B, n_alpha, H, W)
+        if need == 0:
+            raise ValueError("unsupported depth input shape %s" % (tuple(x.shape),))
+        ws = _net_workspace(dev, need)
+        _lib.check(lib.mac_manydepth_forward_f32(ctypes.byref(w), x.data_ptr(), x_alpha.data_ptr(), cam.data_ptr(),
+                                                 disps[0].data_ptr(), disps[1].data_ptr(), disps[2].data_ptr(),
+                                                 disps[3].data_ptr(), B, n_alpha, H, W, ws.data_ptr(), ws.numel(),
+                                                 _stream_ptr(dev)))
+    return tuple(disps)

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--skip-occ", action="store_true")
+    ap.add_argument("--depth", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     res = {}
@@ -66,6 +67,16 @@ def main():
             res["sconeocc_forward"] = {"N": args.n, "Q": args.q, "chunk": args.chunk, "ms": ms, "launches": launches,
                                        "tflop": flop / 1e12, "tflops": flop / 1e9 / ms,
                                        "queries_per_s": args.q / ms * 1e3}
+        if args.depth:
+            from macarons_b200.networks import ManyDepth as MD
+            resnet = MD.ResNet18Trunk()
+            depth = MD.ManyDepth(MD.DepthDecoder(MD.FeatureExtractor(resnet), resnet), None)
+            depth.load_state_dict(synth.seeded_state_dict(depth.state_dict(), 5))
+            depth = depth.to(dev).eval()
+            t = [v.to(dev) for v in synth.depth_inputs(1, 256, 456, 7)]
+            ms, launches = timed(lambda: depth(t[0], t[1], t[2], t[3], t[4], dev, gt_pose=t[5]), args.iters)
+            res["manydepth_forward"] = {"H": 256, "W": 456, "n_alpha": 2, "ms": ms, "launches": launches,
+                                        "gflop": 22.2, "tflops": 22.2e-3 / ms}
     print(json.dumps(res))
 
 
