@@ -64,3 +64,57 @@ def test_subsample_helper_draws_like_the_forward():
     torch.manual_seed(7)
     assert torch.equal(gi, torch.randperm(700)[:2048])
     assert [len(s) for s in si] == [350, 175]
+
+
+# ---- depth (row a14) ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["depth_64x96", "depth_96x160_b2"])
+def test_depth_oracle_matches_reference_golden(name):
+    from macarons_b200.networks import ManyDepth as MD
+    from oracle import depth as o_depth
+    g = load_golden(name)
+    B, H, W = int(g["B"]), int(g["H"]), int(g["W"])
+    resnet = MD.ResNet18Trunk()
+    model = MD.ManyDepth(MD.DepthDecoder(MD.FeatureExtractor(resnet), resnet, input_height=H, input_width=W), None)
+    sd = synth.seeded_state_dict(model.state_dict(), int(g["weight_seed"]))
+    assert synth.state_dict_digest(sd) == str(g["weights_digest"])      # same keys / shapes as the reference model
+    x, x_alpha, R, T, zfar, gt_pose = synth.depth_inputs(B, H, W, int(g["seed"]))
+    with torch.no_grad():
+        out = o_depth.many_depth_forward(sd, x, x_alpha, R, T, zfar, gt_pose)
+    s = int(g["row_stride"])
+    assert np.abs(out[1].numpy()[..., ::s, ::s] - g["disp1"]).max() <= 2e-5
+    for k, key in enumerate(("disp2", "disp3", "disp4")):
+        assert np.abs(out[2 + k].numpy() - g[key]).max() <= 2e-5
+
+
+def test_batchnorm_folding_and_transposed_conv_packing_are_exact():
+    """netpack: conv + eval BatchNorm == folded conv; ConvTranspose2d(k3,s1,p1) == conv with the flipped kernel, in the
+    (ky, kx, c) im2col order the CUDA gather uses."""
+    import torch.nn.functional as F
+    from macarons_b200 import netpack
+    gen = torch.Generator().manual_seed(0)
+    conv = torch.nn.Conv2d(5, 7, 3, 2, 1, bias=False)
+    bn = torch.nn.BatchNorm2d(7).eval()
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=gen))
+        bn.weight.copy_(torch.rand(7, generator=gen) + 0.5)
+        bn.bias.copy_(torch.randn(7, generator=gen))
+        bn.running_mean.copy_(torch.randn(7, generator=gen))
+        bn.running_var.copy_(torch.rand(7, generator=gen) + 0.5)
+    x = torch.randn(2, 5, 9, 11, generator=gen)
+    w, b = netpack._fold_bn(conv.weight, None, bn)
+    with torch.no_grad():
+        want = bn(conv(x))
+        got = F.conv2d(x.double(), w, b, 2, 1)
+    assert (got - want.double()).abs().max().item() <= 1e-5
+
+    up = torch.nn.ConvTranspose2d(4, 6, 3, 1, 1)
+    dst = netpack.ConvW()
+    pk = netpack._Packer()
+    netpack._pack_conv(pk, dst, up, None, netpack.ACT_ELU, transposed=True)
+    assert (dst.k, dst.stride, dst.pad, dst.reflect, dst.act) == (3, 1, 1, 0, netpack.ACT_ELU)
+    assert (dst.lin.N, dst.lin.K) == (6, 36)
+    mat = (pk.keep[-1].hi + pk.keep[-1].lo)[:, :36]                     # (Cout, ky, kx, c)
+    wconv = mat.view(6, 3, 3, 4).permute(0, 3, 1, 2)
+    xin = torch.randn(1, 4, 8, 8, generator=gen)
+    with torch.no_grad():
+        assert (F.conv2d(xin, wconv, up.bias, 1, 1) - up(xin)).abs().max().item() <= 1e-5
