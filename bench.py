@@ -166,6 +166,56 @@ def cpu_baseline(cfg, budget_s=15.0):
                       % (n_cam, cfg["C"], cfg["P"])}
 
 
+def path_stages(dev):
+    """Device times (CUDA events, 1 warm-up + mean of 3) of the other stages of the NBV path at their BASELINE.json
+    shapes, on rank 0 at N = 1 only; informational (the headline metric is the coverage-gain scoring stage)."""
+    import contextlib
+    import io
+    import torch
+    import synth
+    from macarons_b200.networks import ManyDepth as MD
+    from macarons_b200.networks.SconeOcc import SconeOcc
+    from macarons_b200.networks.SconeVis import SconeVis
+    from macarons_b200.utility import scone_utils
+
+    def timed(fn, iters=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    out = {}
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        vis, occ = SconeVis(), SconeOcc()
+        vis.load_state_dict(synth.seeded_state_dict(vis.state_dict(), 5))
+        occ.load_state_dict(synth.seeded_state_dict(occ.state_dict(), 5))
+        vis, occ = vis.to(dev).eval(), occ.to(dev).eval()
+        pts, vh = (t.to(dev) for t in synth.sconevis_inputs(1, 2048, 1))
+        out["sconevis_forward_2048_tokens_ms"] = timed(lambda: vis(pts, view_harmonics=vh))
+        pc = synth.sconeocc_inputs(1, 4096, 8, 2)[0].to(dev)
+        x = (torch.rand(1, 64 ** 3, 3) - 0.5).to(dev)
+        xvh = (0.3 * torch.randn(1, 64 ** 3, 64)).to(dev)
+        out["sconeocc_forward_64cube_queries_ms"] = timed(lambda: occ(pc, x, xvh), iters=2)
+        base, h_polar, h_azim = scone_utils.get_all_harmonics_under_degree(8, 7, 14, dev)
+        big = (torch.rand(1, 200704, 3) - 0.5).to(dev)
+        views = synth.sphere_cameras(10, 1.5, torch.Generator().manual_seed(1)).to(dev)
+        out["view_state_plus_harmonics_200704_pts_10_views_ms"] = timed(lambda: scone_utils.compute_view_harmonics(
+            scone_utils.compute_view_state(big, views, 7, 14), base, h_polar, h_azim, 7, 14))
+        resnet = MD.ResNet18Trunk()
+        depth = MD.ManyDepth(MD.DepthDecoder(MD.FeatureExtractor(resnet), resnet), None)
+        depth.load_state_dict(synth.seeded_state_dict(depth.state_dict(), 5))
+        depth = depth.to(dev).eval()
+        d = [t.to(dev) for t in synth.depth_inputs(1, 256, 456, 7)]
+        out["manydepth_forward_256x456_ms"] = timed(lambda: depth(d[0], d[1], d[2], d[3], d[4], dev, gt_pose=d[5]))
+    out["note"] = "fp32-accurate (3xTF32) tcgen05 linear layers; reference on 8 CPU threads: SconeVis 140 ms, SconeOcc 64^3 ~77 s (SURVEY section 6)"
+    return out
+
+
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
@@ -333,6 +383,11 @@ def run_ours(args, cfg):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg)
+        if world == 1 and not args.no_stages:
+            try:
+                line["path_stages"] = path_stages(dev)
+            except Exception as exc:  # informational only: never lose the headline line
+                line["path_stages"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -346,6 +401,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the informational timings of the other path stages")
     ap.add_argument("--nccl-gather", action="store_true", help="use the NCCL all_gather instead of the fused peer push")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
