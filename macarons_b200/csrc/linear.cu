@@ -71,7 +71,7 @@ constexpr int kBM = 128;
 constexpr int kBK = 32;             // fp32 per k-chunk: one 128-byte swizzle span
 constexpr int kUmmaK = 8;           // tf32 MMA depth (32 bytes)
 constexpr int kATileBytes = kBM * kBK * 4;
-constexpr int kThreads = 384;       // warp 0 X TMA, warp 1 MMA, warp 2 W TMA, warps 4-7 X split, warps 8-11 epilogue
+constexpr int kBaseThreads = 256;   // warp 0 X TMA, warp 1 MMA, warp 2 W TMA, warps 4-7 X split; then 4 warps per epilogue group
 constexpr int kMaxStages = 8;
 constexpr int kEpiLd = 36;          // epilogue staging row stride (floats): 32 columns + 4 pad, conflict-free float4 rows
 constexpr int kEpiBufBytes = kBM * kEpiLd * 4;
@@ -118,7 +118,8 @@ struct Cfg {
     static constexpr int kEpiBufs = (BN <= 128) ? 2 : 1;
     static constexpr int kWSlots = 2;
     static constexpr int kLoSlots = SPLIT ? 2 : 0;
-    static constexpr int kVecBytes = 3 * BN * 4;  // bias | gamma | beta of the tile's columns
+    static constexpr int kVecBytes = 3 * BN * 4 + 2 * 128 * 4;  // bias | gamma | beta of the tile's columns, LayerNorm partials
+    static constexpr int kThreads = kBaseThreads + 128 * ((BN <= 128) ? 2 : 1);
     static constexpr int kBudget = 226 * 1024 - 1024 - 512 - kVecBytes - kEpiBufs * kEpiBufBytes - kWSlots * kWSlotBytes - kLoSlots * kATileBytes;
     static constexpr int kRawSlots = (kBudget / kATileBytes) < kMaxStages ? (kBudget / kATileBytes) : kMaxStages;
     static constexpr int kOperandBytes = kRawSlots * kATileBytes + kLoSlots * kATileBytes + kWSlots * kWSlotBytes;
@@ -130,7 +131,7 @@ struct Cfg {
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA and MMA warps run ahead of the
 // epilogue through a ring of operand stages and two TMEM accumulators.
 template <int BN, bool SPLIT, int ACT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((Cfg<BN, SPLIT>::kThreads), 1)
 linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
               const __grid_constant__ CUtensorMap mapBlo, const LinearParams p)
 {
@@ -179,7 +180,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 128);
+            mbar_init(&acc_empty[a], 128 * C::kEpiBufs);
         }
         fence_mbar_init();
     }
@@ -289,9 +290,15 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         // warp 3: idle (keeps the epilogue warps aligned to TMEM lane quarters)
     } else {
         // ===== epilogue: TMEM -> registers -> (bias, activation, residual, LayerNorm, pool) -> staged, coalesced stores =====
-        const int t = threadIdx.x - 256;        // 0..127
+        // kEpiGroups groups of 4 warps; group g owns staging buffer g and the 32-column chunks g, g + G, ... of a tile.
+        constexpr int G = C::kEpiBufs;
+        const int g = (warp - 8) >> 2;          // group of this warp
+        const int t = threadIdx.x - 256 - g * 128;  // 0..127 within the group
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int rl = q * 32 + lane;           // row of the tile owned by this thread
+        const int gbar = kEpiBar + g;           // named barrier of this group
+        float *mybuf = ebuf + g * (kBM * kEpiLd);
+        float *red = svec + 3 * BN;             // [G][128] cross-group LayerNorm partials
         float v[32];
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -303,29 +310,26 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const int ncols = min(BN, p.N - n0);          // valid columns of this tile
             const int nch = (ncols + 31) / 32;
             const uint32_t taddr = tmem_base + ab * BN + (static_cast<uint32_t>(q * 32) << 16);
-            auto buf = [&](int c) { return ebuf + (C::kEpiBufs == 2 ? (c & 1) : 0) * (kBM * kEpiLd); };
 
             // residual chunk c (128 rows x 32 columns) -> staging buffer, 16-byte async copies, coalesced
             auto fetch_res = [&](int c) {
-                float *dst = buf(c);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int piece = t + i * 128, r = piece >> 3, sg = piece & 7;
                     const int col = n0 + c * 32 + sg * 4;
                     if (m0 + r < p.M && col < p.N)
-                        cp_async16(dst + r * kEpiLd + sg * 4, p.res + static_cast<size_t>(m0 + r) * p.ldr + col);
+                        cp_async16(mybuf + r * kEpiLd + sg * 4, p.res + static_cast<size_t>(m0 + r) * p.ldr + col);
                 }
                 cp_async_commit();
             };
             // staging buffer -> global, coalesced (8 threads cover one 128-byte row segment)
             auto store_chunk = [&](int c, float *base, int ld) {
-                const float *src = buf(c);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int piece = t + i * 128, r = piece >> 3, sg = piece & 7;
                     const int col = n0 + c * 32 + sg * 4;
                     if (m0 + r < p.M && col < p.N) {
-                        const float4 y = *reinterpret_cast<const float4 *>(src + r * kEpiLd + sg * 4);
+                        const float4 y = *reinterpret_cast<const float4 *>(mybuf + r * kEpiLd + sg * 4);
                         float *dst = base + static_cast<size_t>(m0 + r) * ld + col;
                         if (col + 3 < p.N) *reinterpret_cast<float4 *>(dst) = y;
                         else {
@@ -336,22 +340,24 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     }
                 }
             };
+            auto all_groups_sync = [&]() { named_bar_sync(kEpiBar + G, 128 * G); };
 
             // per-column vectors of this tile -> shared memory (broadcast float4 reads instead of one LDG per element)
-            named_bar_sync(kEpiBar, 128);  // previous tile: staging buffers drained, vectors no longer read
-            for (int c = t; c < BN; c += 128) {
+            all_groups_sync();  // previous tile: staging buffers drained, vectors and partials no longer read
+            for (int c = t + g * 128; c < BN; c += 128 * G) {
                 const bool ok = c < ncols;
                 svec[c] = (ok && p.bias) ? p.bias[n0 + c] : 0.f;
                 svec[BN + c] = (ok && p.ln_out) ? p.ln_g[n0 + c] : 0.f;
                 svec[2 * BN + c] = (ok && p.ln_out) ? p.ln_b[n0 + c] : 0.f;
             }
+            if (p.res && g < nch) fetch_res(g);   // overlaps with the main loop of this tile
+            all_groups_sync();
+            mbar_wait(&acc_full[ab], aph);
+            tc_fence_after_sync();
             if (p.pool) {
-                named_bar_sync(kEpiBar, 128);
-                mbar_wait(&acc_full[ab], aph);
-                tc_fence_after_sync();
                 // groups of 16 consecutive rows -> out[row/16, col] = max, out[row/16, N + col] = mean
-                const int g = row >> 4, gl = lane & 15;
-                for (int c = 0; c < nch; ++c) {
+                const int grp = row >> 4, gl = lane & 15;
+                for (int c = g; c < nch; c += G) {
                     tmem_ld32(taddr + c * 32, v);
                     float mx[2] = {0.f, 0.f}, sm[2] = {0.f, 0.f};
 #pragma unroll
@@ -370,25 +376,23 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         for (int h = 0; h < 2; ++h) {
                             const int col = n0 + c * 32 + h * 16 + gl;
                             if (col < p.N) {
-                                p.out[static_cast<size_t>(g) * p.ldo + col] = mx[h];
-                                p.out[static_cast<size_t>(g) * p.ldo + p.N + col] = sm[h] * (1.0f / 16.0f);
+                                p.out[static_cast<size_t>(grp) * p.ldo + col] = mx[h];
+                                p.out[static_cast<size_t>(grp) * p.ldo + p.N + col] = sm[h] * (1.0f / 16.0f);
                             }
                         }
                     }
                 }
             } else {
-                if (p.res) fetch_res(0);       // overlaps with the main loop of this tile
-                mbar_wait(&acc_full[ab], aph);
-                tc_fence_after_sync();
+                float *mine = mybuf + rl * kEpiLd;
+                const bool has_res = p.res != nullptr;
+                const float pre = p.res_first ? 1.f : 0.f, post = 1.f - pre;   // where the residual enters
                 float sum = 0.f;
-                for (int c = 0; c < nch; ++c) {
-                    float *mine = buf(c) + rl * kEpiLd;
-                    if (p.res) cp_async_wait_all();
-                    named_bar_sync(kEpiBar, 128);  // residual chunk c (and the vectors) visible; store of chunk c-1 complete
-                    if (p.res && C::kEpiBufs == 2 && c + 1 < nch) fetch_res(c + 1);
+                for (int c = g; c < nch; c += G) {
+                    if (has_res) {
+                        cp_async_wait_all();
+                        named_bar_sync(gbar, 128);  // residual chunk c visible to the whole group
+                    }
                     tmem_ld32(taddr + c * 32, v);
-                    const bool has_res = p.res != nullptr;
-                    const float pre = p.res_first ? 1.f : 0.f, post = 1.f - pre;   // where the residual enters
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b4 = *reinterpret_cast<const float4 *>(svec + c * 32 + j);
@@ -410,18 +414,23 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         *reinterpret_cast<float4 *>(mine + j) = y4;
                     }
                     if (p.ln_out) tmem_st32(taddr + c * 32, v);  // keep y for the LayerNorm passes
-                    named_bar_sync(kEpiBar, 128);                // the 128 x 32 chunk of y is staged
+                    named_bar_sync(gbar, 128);                   // the 128 x 32 chunk of y is staged
                     if (p.out) store_chunk(c, p.out, p.ldo);
-                    if (C::kEpiBufs == 1) {
-                        named_bar_sync(kEpiBar, 128);
-                        if (p.res && c + 1 < nch) fetch_res(c + 1);
-                    }
+                    named_bar_sync(gbar, 128);                   // staging buffer drained
+                    if (has_res && c + G < nch) fetch_res(c + G);
                 }
                 if (p.ln_out) {
-                    // LayerNorm over the N columns of this row (the tile spans all of N): mean, then centred variance
+                    // LayerNorm over the N columns of this row (the tile spans all of N): mean, then centred variance;
+                    // the groups hold disjoint column chunks and combine their partial sums through shared memory
+                    if (G > 1) {
+                        red[g * 128 + rl] = sum;
+                        all_groups_sync();
+                        sum = red[rl] + red[128 + rl];
+                        all_groups_sync();
+                    }
                     const float mean = sum / static_cast<float>(p.N);
                     float var = 0.f;
-                    for (int c = 0; c < nch; ++c) {
+                    for (int c = g; c < nch; c += G) {
                         tmem_ld32(taddr + c * 32, v);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -429,12 +438,14 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                             var = fmaf(d, d, var);
                         }
                     }
+                    if (G > 1) {
+                        red[g * 128 + rl] = var;
+                        all_groups_sync();
+                        var = red[rl] + red[128 + rl];
+                    }
                     const float rstd = 1.0f / sqrtf(var / static_cast<float>(p.N) + p.ln_eps);
-                    named_bar_sync(kEpiBar, 128);  // the last stores of the first pass have drained the staging buffers
-                    for (int c = 0; c < nch; ++c) {
-                        float *mine = buf(c) + rl * kEpiLd;
+                    for (int c = g; c < nch; c += G) {
                         tmem_ld32(taddr + c * 32, v);
-                        if (C::kEpiBufs == 1) named_bar_sync(kEpiBar, 128);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 g4 = *reinterpret_cast<const float4 *>(svec + BN + c * 32 + j);
@@ -446,8 +457,9 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                             y4.w = (v[j + 3] - mean) * rstd * g4.w + b4.w;
                             *reinterpret_cast<float4 *>(mine + j) = y4;
                         }
-                        named_bar_sync(kEpiBar, 128);
+                        named_bar_sync(gbar, 128);
                         store_chunk(c, p.ln_out, p.ldl);
+                        named_bar_sync(gbar, 128);
                     }
                 }
             }
@@ -479,7 +491,7 @@ int launch_act(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtenso
     MAC_CUDA(cudaGetDevice(&device));
     const int n_tiles = p.n_tiles_m * p.n_tiles_n;
     const int grid = n_tiles < sm_count(device) ? n_tiles : sm_count(device);
-    linear_kernel<BN, SPLIT, ACT><<<grid, kThreads, C::kSmemBytes, stream>>>(mapA, mapBhi, mapBlo, p);
+    linear_kernel<BN, SPLIT, ACT><<<grid, C::kThreads, C::kSmemBytes, stream>>>(mapA, mapBhi, mapBlo, p);
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return MAC_OK;
