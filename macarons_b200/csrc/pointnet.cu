@@ -233,93 +233,150 @@ __global__ void __launch_bounds__(256) attn16_kernel(const float *__restrict__ q
 }
 
 // ------------------------------------------------------------------------------------------------
-// attn_dense: block = 64 queries of one (cloud, head), 128 threads = (query, half of the value dims);
-// keys / values staged through shared memory 64 at a time, online softmax.
+// attn_dense: CTA = 64 queries of one (cloud, head), 8 warps = (value-dim half) x (4 key splits); lane = a PAIR of
+// queries, so every K / V row read from shared memory (a warp-wide broadcast) feeds 2 x (DQK + DV/2) FMAs.  Each
+// key split runs its own online softmax (flash style); the 4 partial (max, sum, accumulator) triples of a query are
+// merged through shared memory at the end.
 // ------------------------------------------------------------------------------------------------
 template <int DQK, int DV>
-__global__ void __launch_bounds__(128) attn_dense_kernel(const float *__restrict__ qkv, int ldq, float *__restrict__ out,
+__global__ void __launch_bounds__(256) attn_dense_kernel(const float *__restrict__ qkv, int ldq, float *__restrict__ out,
                                                          int ldo, int S)
 {
-    constexpr int H = 4, KT = 64, DH = DV / 2;
-    __shared__ __align__(16) float sk[KT * DQK];
-    __shared__ __align__(16) float sv[KT * DV];
+    constexpr int H = 4, KT = 32, NS = 4, DH = DV / 2;
+    extern __shared__ __align__(16) float sm[];
+    float *sk = sm;                       // [NS][KT][DQK]
+    float *sv = sm + NS * KT * DQK;       // [NS][KT][DV]
     const int b = blockIdx.z, h = blockIdx.y;
-    const int qi = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int half = threadIdx.x >> 6;
-    const bool live = qi < S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = warp & 1, ks = warp >> 1;
+    const int qa = blockIdx.x * 64 + 2 * lane;
     const float *base = qkv + static_cast<size_t>(b) * S * ldq;
-    const float scale = rsqrtf(static_cast<float>(DQK)) * 1.4426950408889634f;
+    const float scale = rsqrtf(static_cast<float>(DQK)) * 1.4426950408889634f;   // 1/sqrt(d) * log2(e)
 
-    float q[DQK];
-    {
-        const float *qp = base + static_cast<size_t>(live ? qi : 0) * ldq + h * DQK;
+    float q[2][DQK];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const float *qp = base + static_cast<size_t>(min(qa + u, S - 1)) * ldq + h * DQK;
 #pragma unroll
         for (int c = 0; c < DQK; c += 4) {
             const float4 v = *reinterpret_cast<const float4 *>(qp + c);
-            q[c] = v.x * scale, q[c + 1] = v.y * scale, q[c + 2] = v.z * scale, q[c + 3] = v.w * scale;
+            q[u][c] = v.x * scale, q[u][c + 1] = v.y * scale, q[u][c + 2] = v.z * scale, q[u][c + 3] = v.w * scale;
         }
     }
-    float acc[DH];
+    float acc[2][DH];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) acc[d] = 0.f;
-    float m = -FLT_MAX, l = 0.f;
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int d = 0; d < DH; ++d) acc[u][d] = 0.f;
+    float m[2] = {-FLT_MAX, -FLT_MAX}, l[2] = {0.f, 0.f};
 
-    for (int k0 = 0; k0 < S; k0 += KT) {
-        const int nk = min(KT, S - k0);
+    const int per = ((S + NS - 1) / NS + KT - 1) / KT * KT;   // keys per split, a multiple of the staging tile
+    const int k_begin = ks * per, k_end = min(k_begin + per, S);
+    for (int it = 0; it < per / KT; ++it) {
         __syncthreads();
-        for (int e = threadIdx.x; e < KT * (DQK / 4); e += 128) {
+        // stage KT keys of every split: K rows then V rows, zero beyond the end of the cloud
+        for (int e = threadIdx.x; e < NS * KT * (DQK / 4); e += 256) {
             const int r = e / (DQK / 4), c = e % (DQK / 4);
+            const int key = (r / KT) * per + it * KT + (r % KT);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nk) v = *reinterpret_cast<const float4 *>(base + static_cast<size_t>(k0 + r) * ldq + H * DQK + h * DQK + c * 4);
+            if (key < S) v = *reinterpret_cast<const float4 *>(base + static_cast<size_t>(key) * ldq + H * DQK + h * DQK + c * 4);
             *reinterpret_cast<float4 *>(sk + r * DQK + c * 4) = v;
         }
-        for (int e = threadIdx.x; e < KT * (DV / 4); e += 128) {
+        for (int e = threadIdx.x; e < NS * KT * (DV / 4); e += 256) {
             const int r = e / (DV / 4), c = e % (DV / 4);
+            const int key = (r / KT) * per + it * KT + (r % KT);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nk) v = *reinterpret_cast<const float4 *>(base + static_cast<size_t>(k0 + r) * ldq + 2 * H * DQK + h * DV + c * 4);
+            if (key < S) v = *reinterpret_cast<const float4 *>(base + static_cast<size_t>(key) * ldq + 2 * H * DQK + h * DV + c * 4);
             *reinterpret_cast<float4 *>(sv + r * DV + c * 4) = v;
         }
         __syncthreads();
+        const int nvalid = min(KT, k_end - (k_begin + it * KT));   // valid keys of this warp's tile (may be <= 0)
+        const float *wk = sk + ks * KT * DQK, *wv = sv + ks * KT * DV + half * DH;
+#pragma unroll 1
+        for (int j0 = 0; j0 < KT; j0 += 8) {
+            if (j0 >= nvalid) break;
+            float sc[2][8];
+            float tm0 = m[0], tm1 = m[1];
 #pragma unroll
-        for (int j0 = 0; j0 < KT; j0 += 16) {
-            if (j0 >= nk) break;
-            float sc[16];
-            float tm = m;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float a = 0.f;
+            for (int j = 0; j < 8; ++j) {
+                float a0 = 0.f, a1 = 0.f;
 #pragma unroll
                 for (int c = 0; c < DQK; c += 4) {
-                    const float4 k = *reinterpret_cast<const float4 *>(sk + (j0 + j) * DQK + c);
-                    a = fmaf(q[c], k.x, a), a = fmaf(q[c + 1], k.y, a), a = fmaf(q[c + 2], k.z, a), a = fmaf(q[c + 3], k.w, a);
+                    const float4 k = *reinterpret_cast<const float4 *>(wk + (j0 + j) * DQK + c);
+                    a0 = fmaf(q[0][c], k.x, a0), a0 = fmaf(q[0][c + 1], k.y, a0), a0 = fmaf(q[0][c + 2], k.z, a0), a0 = fmaf(q[0][c + 3], k.w, a0);
+                    a1 = fmaf(q[1][c], k.x, a1), a1 = fmaf(q[1][c + 1], k.y, a1), a1 = fmaf(q[1][c + 2], k.z, a1), a1 = fmaf(q[1][c + 3], k.w, a1);
                 }
-                sc[j] = (j0 + j < nk) ? a : -FLT_MAX;
-                tm = fmaxf(tm, sc[j]);
+                const bool ok = j0 + j < nvalid;
+                sc[0][j] = ok ? a0 : -FLT_MAX;
+                sc[1][j] = ok ? a1 : -FLT_MAX;
+                tm0 = fmaxf(tm0, sc[0][j]);
+                tm1 = fmaxf(tm1, sc[1][j]);
             }
-            const float corr = exp2f(m - tm);
-            m = tm;
-            l *= corr;
+            const float c0 = exp2f(m[0] - tm0), c1 = exp2f(m[1] - tm1);
+            m[0] = tm0, m[1] = tm1;
+            l[0] *= c0, l[1] *= c1;
 #pragma unroll
-            for (int d = 0; d < DH; ++d) acc[d] *= corr;
+            for (int d = 0; d < DH; ++d) acc[0][d] *= c0, acc[1][d] *= c1;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float pj = (j0 + j < nk) ? exp2f(sc[j] - m) : 0.f;
-                l += pj;
+            for (int j = 0; j < 8; ++j) {
+                const bool ok = j0 + j < nvalid;
+                const float p0 = ok ? exp2f(sc[0][j] - m[0]) : 0.f, p1 = ok ? exp2f(sc[1][j] - m[1]) : 0.f;
+                l[0] += p0, l[1] += p1;
 #pragma unroll
                 for (int d = 0; d < DH; d += 4) {
-                    const float4 v = *reinterpret_cast<const float4 *>(sv + (j0 + j) * DV + half * DH + d);
-                    acc[d] = fmaf(pj, v.x, acc[d]), acc[d + 1] = fmaf(pj, v.y, acc[d + 1]);
-                    acc[d + 2] = fmaf(pj, v.z, acc[d + 2]), acc[d + 3] = fmaf(pj, v.w, acc[d + 3]);
+                    const float4 v = *reinterpret_cast<const float4 *>(wv + (j0 + j) * DV + d);
+                    acc[0][d] = fmaf(p0, v.x, acc[0][d]), acc[0][d + 1] = fmaf(p0, v.y, acc[0][d + 1]);
+                    acc[0][d + 2] = fmaf(p0, v.z, acc[0][d + 2]), acc[0][d + 3] = fmaf(p0, v.w, acc[0][d + 3]);
+                    acc[1][d] = fmaf(p1, v.x, acc[1][d]), acc[1][d + 1] = fmaf(p1, v.y, acc[1][d + 1]);
+                    acc[1][d + 2] = fmaf(p1, v.z, acc[1][d + 2]), acc[1][d + 3] = fmaf(p1, v.w, acc[1][d + 3]);
                 }
             }
         }
     }
-    if (live) {
-        const float inv = 1.0f / l;
-        float *dst = out + (static_cast<size_t>(b) * S + qi) * ldo + h * DV + half * DH;
+
+    // merge the 4 key splits: (2,3) -> (0,1), then 1 -> 0; record = [m, l, acc[DH]] per (query of the pair), lane-major
+    constexpr int REC = DH + 2;
+    float *mg = sm;   // [2 splits][2 halves][2 queries][REC][32 lanes]  (fits in the staging area)
+    auto slot = [&](int sp, int u, int f) { return mg + (((sp * 2 + half) * 2 + u) * REC + f) * 32 + lane; };
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+        const int senders_from = round == 0 ? 2 : 1, n_send = round == 0 ? 2 : 1;
+        __syncthreads();
+        if (ks >= senders_from && ks < senders_from + n_send) {
 #pragma unroll
-        for (int d = 0; d < DH; d += 4)
-            *reinterpret_cast<float4 *>(dst + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+            for (int u = 0; u < 2; ++u) {
+                *slot(ks - senders_from, u, 0) = m[u];
+                *slot(ks - senders_from, u, 1) = l[u];
+#pragma unroll
+                for (int d = 0; d < DH; ++d) *slot(ks - senders_from, u, 2 + d) = acc[u][d];
+            }
+        }
+        __syncthreads();
+        if (ks < n_send) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float mo = *slot(ks, u, 0), lo = *slot(ks, u, 1);
+                const float mn = fmaxf(m[u], mo);
+                const float ca = exp2f(m[u] - mn), cb = exp2f(mo - mn);
+                l[u] = l[u] * ca + lo * cb;
+#pragma unroll
+                for (int d = 0; d < DH; ++d) acc[u][d] = acc[u][d] * ca + *slot(ks, u, 2 + d) * cb;
+                m[u] = mn;
+            }
+        }
+    }
+    if (ks == 0) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (qa + u < S) {
+                const float inv = 1.0f / l[u];
+                float *dst = out + (static_cast<size_t>(b) * S + qa + u) * ldo + h * DV + half * DH;
+#pragma unroll
+                for (int d = 0; d < DH; d += 4)
+                    *reinterpret_cast<float4 *>(dst + d) =
+                        make_float4(acc[u][d] * inv, acc[u][d + 1] * inv, acc[u][d + 2] * inv, acc[u][d + 3] * inv);
+            }
+        }
     }
 }
 
@@ -487,8 +544,13 @@ int attn_dense(const float *qkv, int ldq, float *out, int ldo, int B, int S, int
     MAC_REQUIRE(qkv && out && B > 0 && S > 0, "null tensor pointer");
     MAC_REQUIRE(ldq % 4 == 0 && ldo % 4 == 0, "attention rows must be 16-byte aligned");
     dim3 grid((S + 63) / 64, 4, B);
-    if (dqk == 8 && dv == 32) attn_dense_kernel<8, 32><<<grid, 128, 0, stream>>>(qkv, ldq, out, ldo, S);
-    else if (dqk == 16 && dv == 64) attn_dense_kernel<16, 64><<<grid, 128, 0, stream>>>(qkv, ldq, out, ldo, S);
+    static bool configured = false;
+    if (!configured) {
+        MAC_CUDA(cudaFuncSetAttribute(attn_dense_kernel<16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32 * (16 + 64) * 4));
+        configured = true;
+    }
+    if (dqk == 8 && dv == 32) attn_dense_kernel<8, 32><<<grid, 256, 4 * 32 * (8 + 32) * 4, stream>>>(qkv, ldq, out, ldo, S);
+    else if (dqk == 16 && dv == 64) attn_dense_kernel<16, 64><<<grid, 256, 4 * 32 * (16 + 64) * 4, stream>>>(qkv, ldq, out, ldo, S);
     else {
         set_error("attn_dense is built for 4 heads of (8, 32) or (16, 64) dims, got (%d, %d)", dqk, dv);
         return MAC_ERR_UNSUPPORTED;
