@@ -55,6 +55,8 @@ struct CovgainParams {
     int pts_dim;
     int B, P, C;
     int cam_begin, cam_end;
+    int mean_count;            // divisor of the mean (P, or the total point count when the points arrive in slices)
+    int finalize;              // 0: leave the partial sums in the workspace (more point slices follow)
     int cams_per_task;         // multiple of 32, <= kCamChunkMax
     int n_cam_chunks;
     int tiles_per_cloud;       // ceil(P / 32)
@@ -287,7 +289,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
             is_last = (atomicAdd(prm.done, 1u) == gridDim.x - 1);
         }
         __syncthreads();
-        if (is_last) {
+        if (is_last && !prm.finalize) {
+            if (threadIdx.x == 0) *prm.done = 0u;   // partial sums stay in the workspace for the next point slice
+        } else if (is_last) {
             __threadfence();
             const int nloc = prm.cam_end - prm.cam_begin;
             const double unfix = 1.0 / static_cast<double>(SIGMOID ? kFixSigmoid : kFixRelu);
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
                 const long long q = static_cast<long long>(atomicExch(prm.acc + idx, 0ull));
                 const unsigned int bad = atomicExch(prm.flags + idx, 0u);
                 const float total = static_cast<float>(static_cast<double>(q) * unfix);
-                const float score = bad ? __int_as_float(0x7fc00000) : __fdiv_rn(total, static_cast<float>(prm.P));
+                const float score = bad ? __int_as_float(0x7fc00000) : __fdiv_rn(total, static_cast<float>(prm.mean_count));
                 if (prm.out) prm.out[idx] = score;
                 for (int r = 0; r < prm.push_world; ++r) prm.push_dst[r][idx] = score;  // peer-mapped stores
             }
@@ -348,7 +352,8 @@ int make_harmonics_map(CUtensorMap *map, const float *harm, int B, int P)
 
 int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *harm, const float *cams, float *out,
                     int B, int P, int C, int cam_begin, int cam_end, int act, void *workspace,
-                    size_t workspace_bytes, void *stream, const mac_peer_board_t *board = nullptr)
+                    size_t workspace_bytes, void *stream, const mac_peer_board_t *board = nullptr, int mean_count = 0,
+                    int finalize = 1)
 {
     MAC_REQUIRE(pts && harm && cams && (out || board), "null tensor pointer");
     if (board) {
@@ -377,6 +382,8 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
     prm.C = C;
     prm.cam_begin = cam_begin;
     prm.cam_end = cam_end;
+    prm.mean_count = mean_count > 0 ? mean_count : P;
+    prm.finalize = finalize;
     if (board) {
         prm.push_world = board->world;
         prm.push_rank = board->rank;
@@ -494,6 +501,18 @@ extern "C" int mac_covgain_f32(const float *pts, int pts_dim, const float *harmo
     return mac::plan_and_launch(true, pts, pts_dim, harmonics, cams, out, B, P, C, cam_begin, cam_end, act,
                                 workspace, workspace_bytes, stream);
 }
+
+namespace mac {
+// Point-sliced form used by the host-buffer entry point: accumulate the slice [pts, pts + P) of a cloud of `p_total`
+// points into the workspace; the call with finalize = 1 converts the sums to the mean over p_total.
+int covgain_accumulate(const float *pts, int pts_dim, const float *harmonics, const float *cams, float *out, int P, int C,
+                       int cam_begin, int cam_end, int act, void *workspace, size_t workspace_bytes, int p_total,
+                       int finalize, cudaStream_t stream)
+{
+    return plan_and_launch(true, pts, pts_dim, harmonics, cams, out, 1, P, C, cam_begin, cam_end, act, workspace,
+                                workspace_bytes, stream, nullptr, p_total, finalize);
+}
+}  // namespace mac
 
 extern "C" int mac_visibility_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams,
                                   float *out, int B, int P, int C, int cam_begin, int cam_end, int act, void *stream)

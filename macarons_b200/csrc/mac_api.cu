@@ -14,7 +14,9 @@ struct HostCache {  // per-thread device staging for the *_host entry points
     int device = -1;
     void *buf = nullptr;
     size_t bytes = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t copy_stream = nullptr;  // host -> device slices
+    cudaEvent_t landed[8] = {};
 };
 thread_local HostCache g_cache;
 }  // namespace
@@ -59,6 +61,9 @@ extern "C" void mac_host_release(void)
         cudaFree(c.buf);
     }
     if (c.stream) cudaStreamDestroy(c.stream);
+    if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    for (cudaEvent_t e : c.landed)
+        if (e) cudaEventDestroy(e);
     c = mac::HostCache();
 }
 
@@ -84,6 +89,8 @@ extern "C" int mac_covgain_host(const float *pts, int pts_dim, const float *harm
         MAC_CUDA(cudaSetDevice(device));
         MAC_CUDA(cudaMalloc(&c.buf, need));
         MAC_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        MAC_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : c.landed) MAC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c.device = device;
         c.bytes = need;
     }
@@ -94,15 +101,38 @@ extern "C" int mac_covgain_host(const float *pts, int pts_dim, const float *harm
     float *d_out = reinterpret_cast<float *>(base + n_pts + n_harm + n_cams);
     void *d_ws = base + n_pts + n_harm + n_cams + n_out;
     MAC_CUDA(cudaMemsetAsync(d_ws, 0, n_ws, c.stream));
-    MAC_CUDA(cudaMemcpyAsync(d_pts, pts, sizeof(float) * B * static_cast<size_t>(P) * pts_dim, cudaMemcpyHostToDevice,
-                             c.stream));
-    MAC_CUDA(cudaMemcpyAsync(d_harm, harmonics, sizeof(float) * B * static_cast<size_t>(P) * MAC_N_HARMONICS,
-                             cudaMemcpyHostToDevice, c.stream));
     MAC_CUDA(cudaMemcpyAsync(d_cams, cams, sizeof(float) * B * static_cast<size_t>(C) * 3, cudaMemcpyHostToDevice,
                              c.stream));
-    const int rc = mac_covgain_f32(d_pts, pts_dim, d_harm, d_cams, d_out, B, P, C, cam_begin, cam_end, act, d_ws, n_ws,
-                                   c.stream);
-    if (rc != MAC_OK) return rc;
+    // One cloud with many points: the points arrive in slices on a copy stream while the kernel integrates the
+    // previous slice (the partial sums stay in the fixed-point workspace between the slice launches).
+    const int n_slices = (B == 1 && P >= (1 << 16)) ? 8 : 1;
+    if (n_slices > 1) {
+        const int per = ((P + n_slices - 1) / n_slices + 31) / 32 * 32;
+        int k = 0;
+        for (int p0 = 0; p0 < P; p0 += per, ++k) {
+            const int np = P - p0 < per ? P - p0 : per;
+            MAC_CUDA(cudaMemcpyAsync(d_pts + static_cast<size_t>(p0) * pts_dim, pts + static_cast<size_t>(p0) * pts_dim,
+                                     sizeof(float) * np * static_cast<size_t>(pts_dim), cudaMemcpyHostToDevice, c.copy_stream));
+            MAC_CUDA(cudaMemcpyAsync(d_harm + static_cast<size_t>(p0) * MAC_N_HARMONICS,
+                                     harmonics + static_cast<size_t>(p0) * MAC_N_HARMONICS,
+                                     sizeof(float) * np * static_cast<size_t>(MAC_N_HARMONICS), cudaMemcpyHostToDevice,
+                                     c.copy_stream));
+            MAC_CUDA(cudaEventRecord(c.landed[k], c.copy_stream));
+            MAC_CUDA(cudaStreamWaitEvent(c.stream, c.landed[k], 0));
+            const int rc = covgain_accumulate(d_pts + static_cast<size_t>(p0) * pts_dim, pts_dim,
+                                              d_harm + static_cast<size_t>(p0) * MAC_N_HARMONICS, d_cams, d_out, np, C, cam_begin,
+                                              cam_end, act, d_ws, n_ws, P, p0 + np >= P ? 1 : 0, c.stream);
+            if (rc != MAC_OK) return rc;
+        }
+    } else {
+        MAC_CUDA(cudaMemcpyAsync(d_pts, pts, sizeof(float) * B * static_cast<size_t>(P) * pts_dim, cudaMemcpyHostToDevice,
+                                 c.stream));
+        MAC_CUDA(cudaMemcpyAsync(d_harm, harmonics, sizeof(float) * B * static_cast<size_t>(P) * MAC_N_HARMONICS,
+                                 cudaMemcpyHostToDevice, c.stream));
+        const int rc = mac_covgain_f32(d_pts, pts_dim, d_harm, d_cams, d_out, B, P, C, cam_begin, cam_end, act, d_ws, n_ws,
+                                       c.stream);
+        if (rc != MAC_OK) return rc;
+    }
     if (cam_end > cam_begin) {
         MAC_CUDA(cudaMemcpy2DAsync(out + cam_begin, sizeof(float) * C, d_out + cam_begin, sizeof(float) * C,
                                    sizeof(float) * (cam_end - cam_begin), B, cudaMemcpyDeviceToHost, c.stream));

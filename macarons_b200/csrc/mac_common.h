@@ -12,6 +12,10 @@ namespace mac {
 void set_error(const char *fmt, ...);
 void count_launch(unsigned n = 1);
 int sm_count(int device);
+// covgain.cu: accumulate one slice of the points of a single cloud (see mac_covgain_host)
+int covgain_accumulate(const float *pts, int pts_dim, const float *harmonics, const float *cams, float *out, int P, int C,
+                       int cam_begin, int cam_end, int act, void *workspace, size_t workspace_bytes, int p_total,
+                       int finalize, cudaStream_t stream);
 
 #define MAC_REQUIRE(cond, ...)                 \
     do {                                       \

@@ -175,6 +175,20 @@ def test_host_buffer_entry_point(cuda_device):
     assert np.array_equal(part[:, 4:9], dev[:, 4:9]) and not part[:, :4].any() and not part[:, 9:].any()
 
 
+def test_host_buffer_entry_point_sliced_pipeline(cuda_device):
+    """One large cloud goes through mac_covgain_host in 8 point slices (H2D copies overlapped with the kernel, partial
+    sums kept in the fixed-point workspace): same scores as the single device call, pinned or pageable host memory."""
+    pts, harm, cams = synth.covgain_inputs(1, 70001, 40, seed=12)
+    dev = ops.coverage_gain(pts.to(cuda_device), harm.to(cuda_device), cams.to(cuda_device)).cpu().numpy()
+    got = ops.coverage_gain_host(pts, harm, cams, device=0)
+    assert np.abs(got - dev).max() <= 1e-7
+    pinned = ops.coverage_gain_host(pts.pin_memory().numpy(), harm.pin_memory().numpy(), cams.numpy(), device=0)
+    assert np.array_equal(pinned, got)
+    part = ops.coverage_gain_host(pts, harm, cams, cam_range=(7, 33), device=0)
+    assert np.abs(part[:, 7:33] - dev[:, 7:33]).max() <= 1e-7 and not part[:, :7].any() and not part[:, 33:].any()
+    assert np.array_equal(ops.coverage_gain_host(pts, harm, cams, device=0), got)   # the workspace is left clean
+
+
 def test_full_size_cfg5_properties(cuda_device):
     """BASELINE config 5 shape (200 704 points x 512 cameras): checked through properties that do not
     need the full oracle -- a random subset of cameras against the float64 closed form over ALL points,
