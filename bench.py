@@ -229,6 +229,11 @@ def run_ours(args, cfg):
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # NCCL prints its version banner on the process' stdout: keep stdout clean for the ONE JSON line by sending
+    # everything else to stderr until the line is printed.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, P, C = cfg["B"], cfg["P"], cfg["C"]
@@ -398,7 +403,10 @@ def run_ours(args, cfg):
                 line["path_stages"] = path_stages(dev)
             except Exception as exc:  # informational only: never lose the headline line
                 line["path_stages"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
