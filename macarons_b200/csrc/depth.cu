@@ -53,15 +53,20 @@ struct Im2colParams {
     float scale_h, scale_w;  // Ha / H, Wa / W as fp32 (torch nearest: src = min(floor(dst * scale), size - 1))
 };
 
-// one thread per (output pixel, tap); it copies the Ca + Cb channels of that tap
+// one thread per (output pixel, tap, group of VEC channels): VEC = 4 (128-bit copies) when every channel count and row
+// stride is a multiple of 4, else 1
+template <int VEC>
 __global__ void __launch_bounds__(256) im2col_kernel(const Im2colParams p)
 {
     const int taps = p.k * p.k;
     const int C = p.Ca + p.Cb;
-    const long long total = static_cast<long long>(p.n) * p.Ho * p.Wo * taps;
+    const int groups = C / VEC;
+    const long long total = static_cast<long long>(p.n) * p.Ho * p.Wo * taps * groups;
     for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
-        const long long row = i / taps;
-        const int tap = static_cast<int>(i - row * taps);
+        const int c = static_cast<int>(i % groups) * VEC;
+        const long long rt = i / groups;
+        const long long row = rt / taps;
+        const int tap = static_cast<int>(rt - row * taps);
         const int ky = tap / p.k, kx = tap - ky * p.k;
         const long long img = row / (static_cast<long long>(p.Ho) * p.Wo);
         const int rem = static_cast<int>(row - img * p.Ho * p.Wo);
@@ -74,24 +79,24 @@ __global__ void __launch_bounds__(256) im2col_kernel(const Im2colParams p)
         } else {
             inside = y >= 0 && y < p.H && x >= 0 && x < p.W;
         }
-        float *dst = p.col + row * p.ldc + static_cast<long long>(tap) * C;
-        if (!inside) {
-            for (int c = 0; c < C; ++c) dst[c] = 0.f;
-        } else {
-            int ya = y, xa = x;
-            if (p.Ha != p.H || p.Wa != p.W) {
-                ya = min(static_cast<int>(floorf(static_cast<float>(y) * p.scale_h)), p.Ha - 1);
-                xa = min(static_cast<int>(floorf(static_cast<float>(x) * p.scale_w)), p.Wa - 1);
-            }
-            const float *sa = p.a + ((img * p.Ha + ya) * p.Wa + xa) * p.lda;
-            for (int c = 0; c < p.Ca; ++c) dst[c] = sa[c];
-            if (p.b) {
-                const float *sb = p.b + ((img * p.H + y) * p.W + x) * p.ldb;
-                for (int c = 0; c < p.Cb; ++c) dst[p.Ca + c] = sb[c];
+        const float *src = nullptr;
+        if (inside) {
+            if (c < p.Ca) {
+                int ya = y, xa = x;
+                if (p.Ha != p.H || p.Wa != p.W) {
+                    ya = min(static_cast<int>(floorf(static_cast<float>(y) * p.scale_h)), p.Ha - 1);
+                    xa = min(static_cast<int>(floorf(static_cast<float>(x) * p.scale_w)), p.Wa - 1);
+                }
+                src = p.a + ((img * p.Ha + ya) * p.Wa + xa) * p.lda + c;
+            } else {
+                src = p.b + ((img * p.H + y) * p.W + x) * p.ldb + (c - p.Ca);
             }
         }
-        if (tap == taps - 1)
-            for (int c = taps * C; c < p.ldc; ++c) p.col[row * p.ldc + c] = 0.f;
+        float *dst = p.col + row * p.ldc + static_cast<long long>(tap) * C + c;
+        if (VEC == 4) *reinterpret_cast<float4 *>(dst) = src ? *reinterpret_cast<const float4 *>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        else *dst = src ? *src : 0.f;
+        if (tap == taps - 1 && c == 0)   // zero the K padding of this row (K -> ldc)
+            for (int z = taps * C; z < p.ldc; ++z) p.col[row * p.ldc + z] = 0.f;
     }
 }
 
@@ -278,7 +283,9 @@ int conv(Ctx &cx, const mac_conv_w_t &w, const Act &a, const Act *b, int H, int 
                               w.lin.K, w.act, res ? res->p : nullptr, res ? res->ld : 0, nullptr, 0, nullptr, nullptr, 0.f, 0,
                               cx.st, res_first);
     }
-    im2col_kernel<<<grid_for(rows * w.k * w.k, 256, 148 * 32), 256, 0, cx.st>>>(p);
+    const bool vec = Ca % 4 == 0 && Cb % 4 == 0 && a.ld % 4 == 0 && (!b || b->ld % 4 == 0) && p.ldc % 4 == 0;
+    if (vec) im2col_kernel<4><<<grid_for(rows * w.k * w.k * ((Ca + Cb) / 4), 256, 148 * 32), 256, 0, cx.st>>>(p);
+    else im2col_kernel<1><<<grid_for(rows * w.k * w.k * (Ca + Cb), 256, 148 * 32), 256, 0, cx.st>>>(p);
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return linear_forward(cx.col, p.ldc, w.lin.hi, w.lin.lo, w.lin.ldw, w.lin.bias, out.p, out.ld, static_cast<int>(rows), w.lin.N,

@@ -28,7 +28,7 @@ __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f +
 constexpr int kKnn = 16;
 constexpr int kKnnTile = 1024;
 
-__global__ void __launch_bounds__(128) knn16_kernel(const float *__restrict__ x, const float *__restrict__ pc,
+__global__ void __launch_bounds__(64) knn16_kernel(const float *__restrict__ x, const float *__restrict__ pc,
                                                     int *__restrict__ idx_out, float *__restrict__ dist_out, int Q, int N)
 {
     __shared__ float sp[kKnnTile * 3];
@@ -488,8 +488,8 @@ int knn16(const float *x, const float *pc, int *idx, float *dist, int B, int Q, 
     MAC_REQUIRE(x && pc && idx, "null tensor pointer");
     MAC_REQUIRE(B > 0 && Q > 0 && N >= kKnn, "kNN needs B > 0, Q > 0 and at least 16 cloud points (got B=%d Q=%d N=%d)", B, Q, N);
     MAC_REQUIRE((reinterpret_cast<uintptr_t>(idx) & 15u) == 0, "idx must be 16-byte aligned");
-    dim3 grid((Q + 127) / 128, B);
-    knn16_kernel<<<grid, 128, 0, stream>>>(x, pc, idx, dist, Q, N);
+    dim3 grid((Q + 63) / 64, B);   // 64 queries per CTA: 16384-query passes still fill the 148 SMs
+    knn16_kernel<<<grid, 64, 0, stream>>>(x, pc, idx, dist, Q, N);
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return MAC_OK;
