@@ -1,6 +1,8 @@
 // Forward passes of SconeOcc and SconeVis assembled from the tensor-core linear layer (linear.cu) and the
 // CUDA-core kernels of pointnet.cu.  Reference: networks/SconeOcc.py:250-347, networks/SconeVis.py:121-162,
 // networks/Attention.py.  Everything is enqueued on one stream; the caller owns weights and workspace.
+#include <stdlib.h>
+
 #include "nets.h"
 #include "tc_common.h"
 
@@ -34,15 +36,27 @@ int lin(const float *X, int ldx, const mac_linear_w_t &w, const float *bias, flo
 // Buffers of one encoder stack over T tokens of width D.
 struct EncBufs {
     float *x, *x2, *ln, *qkv, *att, *ff;
+    float *attn_scratch;  // tensor-core attention operands (dense attention only)
     int ldqkv;
 };
+
+// MAC_ATTN_CUDA_CORES=1 selects the CUDA-core dense attention kernel (A/B knob for tools/bench_nets.py and the tests)
+bool use_tc_attention(int S)
+{
+    static const bool force_cuda_cores = [] {
+        const char *e = getenv("MAC_ATTN_CUDA_CORES");
+        return e && atoi(e) != 0;
+    }();
+    return !force_cuda_cores && S >= 64;
+}
 size_t enc_floats_per_token(int D, int qkv_n) { return 3 * static_cast<size_t>(D) + qkv_n + D + 2 * D; }
 
-EncBufs carve_enc(Bump &ws, long long T, int D, int qkv_n)
+EncBufs carve_enc(Bump &ws, long long T, int D, int qkv_n, size_t attn_scratch_floats = 0)
 {
     EncBufs e;
     e.x = ws.f(T * D), e.x2 = ws.f(T * D), e.ln = ws.f(T * D);
     e.qkv = ws.f(T * qkv_n), e.att = ws.f(T * D), e.ff = ws.f(T * 2 * D);
+    e.attn_scratch = attn_scratch_floats ? ws.f(attn_scratch_floats) : nullptr;
     e.ldqkv = qkv_n;
     return e;
 }
@@ -59,7 +73,11 @@ int encoder_stack(const mac_encoder_w_t *enc, int n_enc, const float *fin_g, con
         if (seq16) {
             if (int rc = attn16(e.qkv, e.ldqkv, e.att, D, T / 16, dqk, dv, st)) return rc;
         } else {
-            if (int rc = attn_dense(e.qkv, e.ldqkv, e.att, D, B, S, dqk, dv, st)) return rc;
+            if (use_tc_attention(S) && e.attn_scratch) {
+                if (int rc = attn_dense_tc(e.qkv, e.ldqkv, e.att, D, B, S, dqk, dv, e.attn_scratch, st)) return rc;
+            } else {
+                if (int rc = attn_dense(e.qkv, e.ldqkv, e.att, D, B, S, dqk, dv, st)) return rc;
+            }
         }
         // x2 = x + out(att);  ln = norm2(x2)
         if (int rc = lin(e.att, D, w.out, w.out.bias, e.x2, D, T, MAC_LIN_NONE, e.x, D, e.ln, D, w.ln2_g, w.ln2_b, 0, st)) return rc;
@@ -99,6 +117,7 @@ extern "C" size_t mac_sconevis_workspace_bytes(int B, int S)
     n += align256(static_cast<size_t>(B) * 128 * 4);  // gmax
     n += 6 * align256(T * 512 * 4);                   // encoder buffers (upper bound: D = 256, qkv 384, ff 512)
     n += align256(T * 256 * 4) + align256(T * 128 * 4);
+    n += align256(attn_dense_tc_scratch_floats(B, S, 64) * 4);
     return n + 4096;
 }
 
@@ -121,7 +140,7 @@ extern "C" int mac_sconevis_forward_f32(const mac_sconevis_w_t *w, const float *
     Bump ws{static_cast<unsigned char *>(workspace), 0, workspace_bytes};
     float *h = ws.f(T * 128);
     float *gmax = ws.f(static_cast<size_t>(B) * 128);
-    EncBufs e = carve_enc(ws, T, D, w->enc[0].qkv.N);
+    EncBufs e = carve_enc(ws, T, D, w->enc[0].qkv.N, attn_dense_tc_scratch_floats(B, S, 64));
     float *hb = ws.f(T * 256);
     float *h2 = ws.f(T * 128);
 
@@ -160,6 +179,7 @@ extern "C" size_t mac_sconeocc_workspace_bytes(int B, int Sg, int chunk)
     n += align256(Tm * 128 * 4);                                  // h
     n += 3 * align256(Tm * 128 * 4) + align256(Tm * 192 * 4) + align256(Tm * 128 * 4) + align256(Tm * 256 * 4);  // encoder
     n += align256(Tg * 256 * 4);                                  // global linear0 output
+    n += align256(attn_dense_tc_scratch_floats(B, Sg, 32) * 4);   // tensor-core attention operands (global transformer)
     n += 2 * align256(static_cast<size_t>(B) * 512 * 4);          // global feature, per-cloud bias
     n += align256(static_cast<size_t>(chunk) * 16 * 4);           // kNN indices
     n += align256(static_cast<size_t>(chunk) * kFeat * 4);        // feature rows
@@ -195,7 +215,7 @@ extern "C" int mac_sconeocc_forward_f32(const mac_sconeocc_w_t *w, const float *
     const long long Tm = Tg > Tl ? Tg : Tl;
     Bump ws{static_cast<unsigned char *>(workspace), 0, workspace_bytes};
     float *h = ws.f(Tm * 128);
-    EncBufs e = carve_enc(ws, Tm, D, 192);
+    EncBufs e = carve_enc(ws, Tm, D, 192, attn_dense_tc_scratch_floats(B, Sg, 32));
     float *g0 = ws.f(Tg * 256);
     float *gfeat = ws.f(static_cast<size_t>(B) * 512);
     float *bias1 = ws.f(static_cast<size_t>(B) * 512);
