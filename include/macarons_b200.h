@@ -211,6 +211,12 @@ typedef struct mac_sconevis_w {
 size_t mac_sconevis_workspace_bytes(int B, int S);
 int mac_sconevis_forward_f32(const mac_sconevis_w_t *w, const float *pts, const float *view_harmonics, float *out, int B,
                              int S, void *workspace, size_t workspace_bytes, void *stream);
+/* Ragged batch: cloud b holds lens[b] <= S tokens in rows [b*S, b*S + lens[b]) (lens: device, B ints); the padding rows
+ * must hold finite values (zeros), are excluded from the global max feature and masked as attention keys; their outputs
+ * are unspecified.  One call replaces B separate forwards of different lengths: the per-candidate
+ * `macarons(mode='visibility', ...)` calls of /root/reference/macarons/utility/macarons_utils.py:1663. */
+int mac_sconevis_forward_ragged_f32(const mac_sconevis_w_t *w, const float *pts, const float *view_harmonics, float *out,
+                                    int B, int S, const int *lens, void *workspace, size_t workspace_bytes, void *stream);
 
 /* SconeOcc.forward, /root/reference/macarons/networks/SconeOcc.py:250-347, after the caller has drawn the
  * random sub-samples (torch.randperm, :269 and :311, stays on the host so that the RNG stream matches):
@@ -255,6 +261,26 @@ size_t mac_sample_proxy_workspace_bytes(int N);
 int mac_sample_proxy_points_f32(const float *X, const float *preds, const float *view_harmonics, const float *u, int N,
                                 int n_sample, float min_occ, float *res, float *res_harmonics, long long *inverse,
                                 int *counts, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Field-of-view / occupancy selection + proxy sampling for C candidate cameras at once: the first half of
+ * predict_coverage_gain_for_single_camera, /root/reference/macarons/utility/macarons_utils.py:1603-1628, i.e.
+ * Camera.get_points_in_fov (:2400-2435: NDC bounds, view z > 0, distance to the camera centre < fov_range),
+ * the occupancy threshold (:1610-1613) and sample_proxy_points (scone_utils.py:1030-1076) per candidate.
+ *   X (N, 3), preds (N, 1), view_harmonics (N, 64): the scene's proxy points (shared by all candidates)
+ *   cams (C, 36): per candidate [full projection 4x4 | world-to-view 4x4 | camera centre 3 | pad], matrices row-major in
+ *                 the row-vector convention of pytorch3d (`Transform3d.get_matrix()`: p' = [p, 1] @ M)
+ *   ndc_bounds: HOST array (min_x, max_x, min_y, max_y); fov_range < 0 disables the range test
+ *   u (C, n_sample) uniforms in [0, 1)
+ *   -> per candidate c: res (C, n_sample, 4), res_harmonics (C, n_sample, 64), inverse (C, n_sample) as in
+ *      mac_sample_proxy_points_f32 (rows >= counts[2c+1] are left untouched), counts (C, 2) = (points kept, unique
+ *      picks), volume (C) = sum of the kept occupancies (`fov_proxy_volume`, :1621; may be null).
+ * ------------------------------------------------------------------------------------------- */
+size_t mac_fov_sample_proxy_workspace_bytes(int N, int C);
+int mac_fov_sample_proxy_f32(const float *X, const float *preds, const float *view_harmonics, const float *cams,
+                             const float *ndc_bounds, float fov_range, float min_occ, const float *u, int N, int C,
+                             int n_sample, float *res, float *res_harmonics, long long *inverse, int *counts, float *volume,
+                             void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * ManyDepth.forward (row a14), /root/reference/macarons/networks/ManyDepth.py:719-758 -> DepthDecoder.forward

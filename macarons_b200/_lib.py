@@ -61,6 +61,9 @@ SYMBOLS["mac_knn16_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void
 SYMBOLS["mac_sconevis_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int])
 SYMBOLS["mac_sconevis_forward_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
                                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])
+SYMBOLS["mac_sconevis_forward_ragged_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
+                                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                             ctypes.c_void_p])
 SYMBOLS["mac_sconeocc_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
 SYMBOLS["mac_sconeocc_forward_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_void_p,
                                                       ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
@@ -79,6 +82,11 @@ SYMBOLS["mac_sample_proxy_points_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p,
                                                          ctypes.c_int, ctypes.c_float, _c_float_p, _c_float_p,
                                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                          ctypes.c_size_t, ctypes.c_void_p])
+SYMBOLS["mac_fov_sample_proxy_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int])
+SYMBOLS["mac_fov_sample_proxy_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p,
+                                                      ctypes.c_float, ctypes.c_float, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                                      ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                      _c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])
 
 
 SYMBOLS["mac_manydepth_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,

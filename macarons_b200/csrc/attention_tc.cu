@@ -94,6 +94,7 @@ struct AttnCfg {
 struct AttnParams {
     float *out;
     int ldo, S, n_qt;
+    const int *lens;   // optional (B): ragged batches, cloud b holds lens[b] <= S tokens (rows beyond are padding)
 };
 
 template <int DV>
@@ -125,7 +126,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x % p.n_qt, bh = blockIdx.x / p.n_qt;   // bh = b * H + h
     const int q0 = qt * kQT;
-    const int nb = (p.S + kKB - 1) / kKB;
+    const int len = p.lens ? p.lens[bh / kH] : p.S;   // tokens of this cloud (keys >= len are masked, queries skipped)
+    if (q0 >= len) {   // padding-only tile (whole CTA, before any barrier / TMEM allocation): keep the rows finite
+        for (int e = threadIdx.x; e < kQT * (DV / 4); e += blockDim.x) {
+            const int qi = q0 + e / (DV / 4);
+            if (qi < p.S)
+                *reinterpret_cast<float4 *>(p.out + (static_cast<size_t>(bh / kH) * p.S + qi) * p.ldo + (bh % kH) * DV +
+                                            (e % (DV / 4)) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
+    const int nb = (len + kKB - 1) / kKB;
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
@@ -225,7 +236,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant
             for (int i = 0; i < 32; ++i) s[32 + i] = v[i];
             tc_fence_before_sync();
             mbar_arrive(s_free);
-            const int nvalid = p.S - j * kKB;   // keys of this block inside the cloud
+            const int nvalid = len - j * kKB;   // keys of this block inside the cloud
             float bm = m;
 #pragma unroll
             for (int i = 0; i < kKB; ++i) {
@@ -280,11 +291,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant
 #pragma unroll
         for (int c0 = 0; c0 < DV; c0 += 32) {
             tmem_ld32(t_o + lane_addr + c0, v);
-            if (qi < p.S) {
+            if (qi < p.S) {   // padding rows (qi >= len) are written as zeros so that later layers stay finite
                 float *dst = p.out + (static_cast<size_t>(b) * p.S + qi) * p.ldo + h * DV + c0;
+                const float sc = qi < len ? inv : 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4 *>(dst + i) = make_float4(v[i] * inv, v[i + 1] * inv, v[i + 2] * inv, v[i + 3] * inv);
+                    *reinterpret_cast<float4 *>(dst + i) = make_float4(v[i] * sc, v[i + 1] * sc, v[i + 2] * sc, v[i + 3] * sc);
             }
         }
         tc_fence_before_sync();
@@ -297,7 +309,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant
 }
 
 template <int DQK, int DV>
-int run(const float *qkv, int ldq, float *out, int ldo, int B, int S, float *scratch, cudaStream_t stream)
+int run(const float *qkv, int ldq, float *out, int ldo, int B, int S, float *scratch, cudaStream_t stream, const int *lens)
 {
     using C = AttnCfg<DV>;
     const int Sp = (S + 3) / 4 * 4;
@@ -321,7 +333,7 @@ int run(const float *qkv, int ldq, float *out, int ldo, int B, int S, float *scr
         MAC_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
         configured = true;
     }
-    AttnParams p{out, ldo, S, (S + kQT - 1) / kQT};
+    AttnParams p{out, ldo, S, (S + kQT - 1) / kQT, lens};
     attn_tc_kernel<DV><<<B * kH * p.n_qt, 192, C::kSmem, stream>>>(mQh, mQl, mKh, mKl, mVh, mVl, p);
     MAC_CUDA(cudaGetLastError());
     count_launch(2);
@@ -337,12 +349,12 @@ size_t attn_dense_tc_scratch_floats(int B, int S, int dv)
 }
 
 int attn_dense_tc(const float *qkv, int ldq, float *out, int ldo, int B, int S, int dqk, int dv, float *scratch,
-                  cudaStream_t stream)
+                  cudaStream_t stream, const int *lens)
 {
     MAC_REQUIRE(qkv && out && scratch && B > 0 && S > 0, "null tensor pointer");
     MAC_REQUIRE(ldq % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(scratch) & 15u) == 0, "attention buffers must be 16-byte aligned");
-    if (dqk == 8 && dv == 32) return run<8, 32>(qkv, ldq, out, ldo, B, S, scratch, stream);
-    if (dqk == 16 && dv == 64) return run<16, 64>(qkv, ldq, out, ldo, B, S, scratch, stream);
+    if (dqk == 8 && dv == 32) return run<8, 32>(qkv, ldq, out, ldo, B, S, scratch, stream, lens);
+    if (dqk == 16 && dv == 64) return run<16, 64>(qkv, ldq, out, ldo, B, S, scratch, stream, lens);
     set_error("attn_dense_tc is built for 4 heads of (8, 32) or (16, 64) dims, got (%d, %d)", dqk, dv);
     return MAC_ERR_UNSUPPORTED;
 }

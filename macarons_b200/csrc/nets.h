@@ -11,12 +11,15 @@ int embed_first(const float *in, int ld_in, int in_dim, const float *pc, const f
                 const float *w, const float *b, int inner, int append, float *out, int ldo, long long T,
                 cudaStream_t stream);
 int attn16(const float *qkv, int ldq, float *out, int ldo, long long n_seq, int dqk, int dv, cudaStream_t stream);
-int attn_dense(const float *qkv, int ldq, float *out, int ldo, int B, int S, int dqk, int dv, cudaStream_t stream);
+// `lens` (optional, device, B ints): ragged batches -- cloud b holds lens[b] <= S tokens in rows [b*S, b*S + lens[b])
+int attn_dense(const float *qkv, int ldq, float *out, int ldo, int B, int S, int dqk, int dv, cudaStream_t stream,
+               const int *lens = nullptr);
 // attention_tc.cu: the same contract on tcgen05 tensor cores; `scratch` holds attn_dense_tc_scratch_floats() floats
 size_t attn_dense_tc_scratch_floats(int B, int S, int dv);
 int attn_dense_tc(const float *qkv, int ldq, float *out, int ldo, int B, int S, int dqk, int dv, float *scratch,
-                  cudaStream_t stream);
-int colpool(const float *in, int ld, int B, int S, int N, float *out_max, float *out_mean, int ldo, cudaStream_t stream);
+                  cudaStream_t stream, const int *lens = nullptr);
+int colpool(const float *in, int ld, int B, int S, int N, float *out_max, float *out_mean, int ldo, cudaStream_t stream,
+            const int *lens = nullptr);
 int vis_embed_finish(float *x0, int ld, const float *gmax, int ldg, const float *pts, int ldp, int F, int in_dim, int S,
                      long long T, const float *g, const float *b, float eps, float *ln, int ldl, cudaStream_t stream);
 int bias_gemv(const float *W, int ldw, const float *bias, const float *g, int ldg, int N, int K, float *out, int B,

@@ -240,17 +240,28 @@ __global__ void __launch_bounds__(256) attn16_kernel(const float *__restrict__ q
 // ------------------------------------------------------------------------------------------------
 template <int DQK, int DV>
 __global__ void __launch_bounds__(256) attn_dense_kernel(const float *__restrict__ qkv, int ldq, float *__restrict__ out,
-                                                         int ldo, int S)
+                                                         int ldo, int S_stride, const int *__restrict__ lens)
 {
     constexpr int H = 4, KT = 32, NS = 4, DH = DV / 2;
     extern __shared__ __align__(16) float sm[];
     float *sk = sm;                       // [NS][KT][DQK]
     float *sv = sm + NS * KT * DQK;       // [NS][KT][DV]
     const int b = blockIdx.z, h = blockIdx.y;
+    // ragged batches: cloud b occupies rows [b * S_stride, b * S_stride + S); rows beyond S are padding
+    const int S = lens ? lens[b] : S_stride;
+    if (blockIdx.x * 64 >= S) {   // padding-only tile: keep the rows finite for the layers that follow
+        for (int e = threadIdx.x; e < 64 * (DV / 4); e += 256) {
+            const int qi = blockIdx.x * 64 + e / (DV / 4);
+            if (qi < S_stride)
+                *reinterpret_cast<float4 *>(out + (static_cast<size_t>(b) * S_stride + qi) * ldo + h * DV + (e % (DV / 4)) * 4) =
+                    make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int half = warp & 1, ks = warp >> 1;
     const int qa = blockIdx.x * 64 + 2 * lane;
-    const float *base = qkv + static_cast<size_t>(b) * S * ldq;
+    const float *base = qkv + static_cast<size_t>(b) * S_stride * ldq;
     const float scale = rsqrtf(static_cast<float>(DQK)) * 1.4426950408889634f;   // 1/sqrt(d) * log2(e)
 
     float q[2][DQK];
@@ -368,9 +379,9 @@ __global__ void __launch_bounds__(256) attn_dense_kernel(const float *__restrict
     if (ks == 0) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            if (qa + u < S) {
-                const float inv = 1.0f / l[u];
-                float *dst = out + (static_cast<size_t>(b) * S + qa + u) * ldo + h * DV + half * DH;
+            if (qa + u < S_stride) {
+                const float inv = qa + u < S ? 1.0f / l[u] : 0.f;   // padding rows of a ragged batch: zeros
+                float *dst = out + (static_cast<size_t>(b) * S_stride + qa + u) * ldo + h * DV + half * DH;
 #pragma unroll
                 for (int d = 0; d < DH; d += 4)
                     *reinterpret_cast<float4 *>(dst + d) =
@@ -384,16 +395,18 @@ __global__ void __launch_bounds__(256) attn_dense_kernel(const float *__restrict
 // colpool: out_max[b, c] = max_s in[b, s, c]; out_mean[b, c] = mean_s in[b, s, c]   (either may be null)
 // block = 32 columns x 8 row lanes
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colpool_kernel(const float *__restrict__ in, int ld, int S, int N,
-                                                      float *__restrict__ out_max, float *__restrict__ out_mean, int ldo)
+__global__ void __launch_bounds__(256) colpool_kernel(const float *__restrict__ in, int ld, int S_stride, int N,
+                                                      float *__restrict__ out_max, float *__restrict__ out_mean, int ldo,
+                                                      const int *__restrict__ lens)
 {
     __shared__ float smax[8][33], ssum[8][33];
     const int b = blockIdx.y;
+    const int S = lens ? lens[b] : S_stride;   // ragged batches: only the first lens[b] rows of cloud b are tokens
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int ry = threadIdx.x >> 5;
     float mx = -FLT_MAX, sm = 0.f;
     if (c < N) {
-        const float *p = in + static_cast<size_t>(b) * S * ld + c;
+        const float *p = in + static_cast<size_t>(b) * S_stride * ld + c;
         for (int s = ry; s < S; s += 8) {
             const float v = p[static_cast<size_t>(s) * ld];
             mx = fmaxf(mx, v);
@@ -409,8 +422,8 @@ __global__ void __launch_bounds__(256) colpool_kernel(const float *__restrict__ 
             mx = fmaxf(mx, smax[r][threadIdx.x]);
             sm += ssum[r][threadIdx.x];
         }
-        if (out_max) out_max[static_cast<size_t>(b) * ldo + c] = mx;
-        if (out_mean) out_mean[static_cast<size_t>(b) * ldo + c] = sm / static_cast<float>(S);
+        if (out_max) out_max[static_cast<size_t>(b) * ldo + c] = S > 0 ? mx : 0.f;
+        if (out_mean) out_mean[static_cast<size_t>(b) * ldo + c] = S > 0 ? sm / static_cast<float>(S) : 0.f;
     }
 }
 
@@ -539,7 +552,8 @@ int attn16(const float *qkv, int ldq, float *out, int ldo, long long n_seq, int 
     return MAC_OK;
 }
 
-int attn_dense(const float *qkv, int ldq, float *out, int ldo, int B, int S, int dqk, int dv, cudaStream_t stream)
+int attn_dense(const float *qkv, int ldq, float *out, int ldo, int B, int S, int dqk, int dv, cudaStream_t stream,
+               const int *lens)
 {
     MAC_REQUIRE(qkv && out && B > 0 && S > 0, "null tensor pointer");
     MAC_REQUIRE(ldq % 4 == 0 && ldo % 4 == 0, "attention rows must be 16-byte aligned");
@@ -549,8 +563,8 @@ int attn_dense(const float *qkv, int ldq, float *out, int ldo, int B, int S, int
         MAC_CUDA(cudaFuncSetAttribute(attn_dense_kernel<16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32 * (16 + 64) * 4));
         configured = true;
     }
-    if (dqk == 8 && dv == 32) attn_dense_kernel<8, 32><<<grid, 256, 4 * 32 * (8 + 32) * 4, stream>>>(qkv, ldq, out, ldo, S);
-    else if (dqk == 16 && dv == 64) attn_dense_kernel<16, 64><<<grid, 256, 4 * 32 * (16 + 64) * 4, stream>>>(qkv, ldq, out, ldo, S);
+    if (dqk == 8 && dv == 32) attn_dense_kernel<8, 32><<<grid, 256, 4 * 32 * (8 + 32) * 4, stream>>>(qkv, ldq, out, ldo, S, lens);
+    else if (dqk == 16 && dv == 64) attn_dense_kernel<16, 64><<<grid, 256, 4 * 32 * (16 + 64) * 4, stream>>>(qkv, ldq, out, ldo, S, lens);
     else {
         set_error("attn_dense is built for 4 heads of (8, 32) or (16, 64) dims, got (%d, %d)", dqk, dv);
         return MAC_ERR_UNSUPPORTED;
@@ -560,11 +574,12 @@ int attn_dense(const float *qkv, int ldq, float *out, int ldo, int B, int S, int
     return MAC_OK;
 }
 
-int colpool(const float *in, int ld, int B, int S, int N, float *out_max, float *out_mean, int ldo, cudaStream_t stream)
+int colpool(const float *in, int ld, int B, int S, int N, float *out_max, float *out_mean, int ldo, cudaStream_t stream,
+            const int *lens)
 {
     MAC_REQUIRE(in && (out_max || out_mean) && B > 0 && S > 0 && N > 0, "null tensor pointer");
     dim3 grid((N + 31) / 32, B);
-    colpool_kernel<<<grid, 256, 0, stream>>>(in, ld, S, N, out_max, out_mean, ldo);
+    colpool_kernel<<<grid, 256, 0, stream>>>(in, ld, S, N, out_max, out_mean, ldo, lens);
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return MAC_OK;

@@ -7,6 +7,9 @@
 //   kernel 2 (one CTA): binary search of every uniform (first CDF entry >= u, "none" -> 0), bitonic sort of the
 //                       picks in shared memory, unique + inverse map (torch.unique semantics: sorted values),
 //                       and the gather of the selected rows [xyz, occupancy] and their 64 view harmonics.
+// Batched form (MACARONS candidate scoring, reference utility/macarons_utils.py:1603-1628 + Camera.get_points_in_fov
+// :2400-2435): one CTA per candidate camera; a point is kept when it projects inside the camera's image, lies in front
+// of it and within the sensor range, AND its occupancy exceeds min_occ.  Everything else is the same code.
 #include "mac_common.h"
 
 namespace mac {
@@ -30,20 +33,70 @@ struct SampleParams {
     float *res_h;        // (n_sample, 64)
     long long *inverse;  // (n_sample)
     long long *picks;    // (n_sample) picked index into the compacted list, unsorted (optional)
+    // batched form: blockIdx.x = candidate camera; u / kept / cdf / n_kept / res / res_h / inverse advance per candidate
+    const float *cams;   // (C, kCamFloats) or null: [full projection 4x4 | world-to-view 4x4 | centre 3 | pad], row-vector
+    float ndc[4];        // min_x, max_x, min_y, max_y
+    float fov_range;     // < 0: no range test
+    float *volume;       // (C) sum of the kept occupancies (optional)
 };
+
+constexpr int kCamFloats = 36;
+
+struct Selector {   // keep(i): occupancy above the threshold and (batched form) inside the candidate's field of view
+    const float *X, *preds;
+    float min_occ;
+    bool use_cam;
+    float P[16], Vz[4], centre[3], ndc[4], range;
+    __device__ bool operator()(int i, float &v) const
+    {
+        v = preds[i];
+        if (!(v > min_occ)) return false;
+        if (!use_cam) return true;
+        const float x = X[3 * i], y = X[3 * i + 1], z = X[3 * i + 2];
+        // [x y z 1] @ M, M row-major (pytorch3d Transform3d.transform_points), then the perspective divide
+        const float px = fmaf(x, P[0], fmaf(y, P[4], fmaf(z, P[8], P[12])));
+        const float py = fmaf(x, P[1], fmaf(y, P[5], fmaf(z, P[9], P[13])));
+        const float pw = fmaf(x, P[3], fmaf(y, P[7], fmaf(z, P[11], P[15])));
+        const float vz = fmaf(x, Vz[0], fmaf(y, Vz[1], fmaf(z, Vz[2], Vz[3])));
+        const float nx = __fdiv_rn(px, pw), ny = __fdiv_rn(py, pw);
+        bool in = nx >= ndc[0] && nx <= ndc[1] && ny >= ndc[2] && ny <= ndc[3] && vz > 0.f;
+        if (range >= 0.f) {
+            const float dx = x - centre[0], dy = y - centre[1], dz = z - centre[2];
+            in = in && sqrtf(dx * dx + dy * dy + dz * dz) < range;
+        }
+        return in;
+    }
+};
+
+__device__ Selector make_selector(const SampleParams &p, int cand)
+{
+    Selector s;
+    s.X = p.X, s.preds = p.preds, s.min_occ = p.min_occ, s.use_cam = p.cams != nullptr, s.range = p.fov_range;
+    if (s.use_cam) {
+        const float *c = p.cams + static_cast<size_t>(cand) * kCamFloats;
+        for (int i = 0; i < 16; ++i) s.P[i] = c[i];
+        for (int i = 0; i < 4; ++i) s.Vz[i] = c[16 + 4 * i + 2], s.ndc[i] = p.ndc[i];
+        for (int i = 0; i < 3; ++i) s.centre[i] = c[32 + i];
+    }
+    return s;
+}
 
 __global__ void __launch_bounds__(kScanThreads) sample_scan_kernel(const SampleParams p)
 {
     __shared__ int s_cnt[kScanThreads];
     __shared__ double s_sum[kScanThreads];
     const int t = threadIdx.x;
+    const int cand = blockIdx.x;
+    const Selector keep = make_selector(p, cand);
+    int *kept = p.kept + static_cast<size_t>(cand) * p.N;
+    float *cdf = p.cdf + static_cast<size_t>(cand) * p.N;
     const int per = (p.N + kScanThreads - 1) / kScanThreads;
     const int lo = min(t * per, p.N), hi = min(lo + per, p.N);
     int cnt = 0;
     double sum = 0.0;
     for (int i = lo; i < hi; ++i) {
-        const float v = p.preds[i];
-        if (v > p.min_occ) {
+        float v;
+        if (keep(i, v)) {
             ++cnt;
             sum += static_cast<double>(v);
         }
@@ -67,8 +120,8 @@ __global__ void __launch_bounds__(kScanThreads) sample_scan_kernel(const SampleP
     __shared__ double s_psum[kScanThreads];
     double psum = 0.0;
     for (int i = lo; i < hi; ++i) {
-        const float v = p.preds[i];
-        if (v > p.min_occ) psum += static_cast<double>(v / total);
+        float v;
+        if (keep(i, v)) psum += static_cast<double>(v / total);
     }
     s_psum[t] = psum;
     __syncthreads();
@@ -80,25 +133,34 @@ __global__ void __launch_bounds__(kScanThreads) sample_scan_kernel(const SampleP
     }
     double run = s_psum[t] - psum;
     for (int i = lo; i < hi; ++i) {
-        const float v = p.preds[i];
-        if (v > p.min_occ) {
+        float v;
+        if (keep(i, v)) {
             run += static_cast<double>(v / total);
-            p.kept[pos] = i;
-            p.cdf[pos] = static_cast<float>(run);
+            kept[pos] = i;
+            cdf[pos] = static_cast<float>(run);
             ++pos;
         }
     }
-    if (t == kScanThreads - 1) p.n_kept[0] = s_cnt[t];
+    if (t == kScanThreads - 1) {
+        p.n_kept[2 * cand] = s_cnt[t];
+        if (p.volume) p.volume[cand] = total;
+    }
 }
 
-__global__ void __launch_bounds__(1024) sample_pick_kernel(const SampleParams p)
+__global__ void __launch_bounds__(1024) sample_pick_kernel(SampleParams p)
 {
     __shared__ int s_pick[kMaxSamples];   // sorted picks
     __shared__ int s_flag[kMaxSamples];   // unique flags -> positions
     __shared__ int s_total;
     const int t = threadIdx.x;
-    const int n_kept = p.n_kept[0];
     const int n = p.n_sample;
+    {   // batched form: this CTA's candidate
+        const size_t cand = blockIdx.x;
+        p.kept += cand * p.N, p.cdf += cand * p.N, p.n_kept += 2 * cand, p.u += cand * n;
+        p.res += cand * n * 4, p.res_h += cand * n * 64, p.inverse += cand * n;
+        if (p.picks) p.picks += cand * n;
+    }
+    const int n_kept = p.n_kept[0];
     if (n_kept == 0) {  // nothing above the occupancy threshold: empty result (the reference divides by zero here)
         if (t == 0) p.n_kept[1] = 0;
         for (int i = t; i < n; i += blockDim.x) p.inverse[i] = 0;
@@ -226,10 +288,44 @@ extern "C" int mac_sample_proxy_points_f32(const float *X, const float *preds, c
     p.cdf = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) + static_cast<size_t>(N) * 4);
     p.n_kept = counts;
     p.res = res, p.res_h = res_harmonics, p.inverse = inverse, p.picks = nullptr;
+    p.cams = nullptr, p.fov_range = -1.f, p.volume = nullptr;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     sample_scan_kernel<<<1, kScanThreads, 0, st>>>(p);
     MAC_CUDA(cudaGetLastError());
     sample_pick_kernel<<<1, 1024, 0, st>>>(p);
+    MAC_CUDA(cudaGetLastError());
+    count_launch(2);
+    return MAC_OK;
+}
+
+extern "C" size_t mac_fov_sample_proxy_workspace_bytes(int N, int C) { return static_cast<size_t>(N) * C * 8 + 256; }
+
+extern "C" int mac_fov_sample_proxy_f32(const float *X, const float *preds, const float *view_harmonics, const float *cams,
+                                        const float *ndc_bounds, float fov_range, float min_occ, const float *u, int N, int C,
+                                        int n_sample, float *res, float *res_harmonics, long long *inverse, int *counts,
+                                        float *volume, void *workspace, size_t workspace_bytes, void *stream)
+{
+    MAC_REQUIRE(X && preds && view_harmonics && cams && ndc_bounds && u && res && res_harmonics && inverse && counts && workspace,
+                "null pointer");
+    MAC_REQUIRE(N > 0 && C > 0 && n_sample > 0 && n_sample <= kMaxSamples, "need N, C > 0 and 0 < n_sample <= %d", kMaxSamples);
+    MAC_REQUIRE((reinterpret_cast<uintptr_t>(view_harmonics) & 15u) == 0 && (reinterpret_cast<uintptr_t>(res_harmonics) & 15u) == 0,
+                "harmonics must be 16-byte aligned");
+    if (workspace_bytes < mac_fov_sample_proxy_workspace_bytes(N, C)) {
+        set_error("workspace too small: need %zu bytes, got %zu", mac_fov_sample_proxy_workspace_bytes(N, C), workspace_bytes);
+        return MAC_ERR_WORKSPACE;
+    }
+    SampleParams p{};
+    p.X = X, p.preds = preds, p.vh = view_harmonics, p.u = u, p.N = N, p.n_sample = n_sample, p.min_occ = min_occ;
+    p.kept = static_cast<int *>(workspace);
+    p.cdf = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) + static_cast<size_t>(N) * C * 4);
+    p.n_kept = counts;
+    p.res = res, p.res_h = res_harmonics, p.inverse = inverse, p.picks = nullptr;
+    p.cams = cams, p.fov_range = fov_range, p.volume = volume;
+    for (int i = 0; i < 4; ++i) p.ndc[i] = ndc_bounds[i];   // host array
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    sample_scan_kernel<<<C, kScanThreads, 0, st>>>(p);
+    MAC_CUDA(cudaGetLastError());
+    sample_pick_kernel<<<C, 1024, 0, st>>>(p);
     MAC_CUDA(cudaGetLastError());
     count_launch(2);
     return MAC_OK;

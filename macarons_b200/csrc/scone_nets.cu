@@ -64,7 +64,7 @@ EncBufs carve_enc(Bump &ws, long long T, int D, int qkv_n, size_t attn_scratch_f
 // On entry e.x = residual stream, e.ln = norm1 of encoder 0 applied to it.  On exit e.ln = final LayerNorm(x).
 // seq16: attention over groups of 16 tokens; otherwise over B clouds of S tokens.
 int encoder_stack(const mac_encoder_w_t *enc, int n_enc, const float *fin_g, const float *fin_b, EncBufs &e, long long T,
-                  int D, int dqk, int dv, bool seq16, int B, int S, cudaStream_t st)
+                  int D, int dqk, int dv, bool seq16, int B, int S, cudaStream_t st, const int *lens = nullptr)
 {
     for (int i = 0; i < n_enc; ++i) {
         const mac_encoder_w_t &w = enc[i];
@@ -74,9 +74,9 @@ int encoder_stack(const mac_encoder_w_t *enc, int n_enc, const float *fin_g, con
             if (int rc = attn16(e.qkv, e.ldqkv, e.att, D, T / 16, dqk, dv, st)) return rc;
         } else {
             if (use_tc_attention(S) && e.attn_scratch) {
-                if (int rc = attn_dense_tc(e.qkv, e.ldqkv, e.att, D, B, S, dqk, dv, e.attn_scratch, st)) return rc;
+                if (int rc = attn_dense_tc(e.qkv, e.ldqkv, e.att, D, B, S, dqk, dv, e.attn_scratch, st, lens)) return rc;
             } else {
-                if (int rc = attn_dense(e.qkv, e.ldqkv, e.att, D, B, S, dqk, dv, st)) return rc;
+                if (int rc = attn_dense(e.qkv, e.ldqkv, e.att, D, B, S, dqk, dv, st, lens)) return rc;
             }
         }
         // x2 = x + out(att);  ln = norm2(x2)
@@ -121,8 +121,9 @@ extern "C" size_t mac_sconevis_workspace_bytes(int B, int S)
     return n + 4096;
 }
 
-extern "C" int mac_sconevis_forward_f32(const mac_sconevis_w_t *w, const float *pts, const float *vh, float *out, int B, int S,
-                                        void *workspace, size_t workspace_bytes, void *stream)
+namespace {
+int sconevis_forward(const mac_sconevis_w_t *w, const float *pts, const float *vh, float *out, int B, int S, const int *lens,
+                     void *workspace, size_t workspace_bytes, void *stream)
 {
     MAC_REQUIRE(w && pts && vh && out && workspace, "null pointer");
     MAC_REQUIRE(B > 0 && S > 0, "B and S must be positive (got %d, %d)", B, S);
@@ -147,10 +148,10 @@ extern "C" int mac_sconevis_forward_f32(const mac_sconevis_w_t *w, const float *
     // embedding: h = GELU(W1 p + b1); e = W2 h + b2 -> x[:, :F]; global max; concat + norm1
     if (int rc = embed_first(pts, 4, 4, nullptr, nullptr, nullptr, 0, 0, w->emb1_w, w->emb1_b, F, 0, h, 128, T, st)) return rc;
     if (int rc = lin(h, 128, w->emb2, w->emb2.bias, e.x, D, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st)) return rc;
-    if (int rc = colpool(e.x, D, B, S, F, gmax, nullptr, 128, st)) return rc;
+    if (int rc = colpool(e.x, D, B, S, F, gmax, nullptr, 128, st, lens)) return rc;
     if (int rc = vis_embed_finish(e.x, D, gmax, 128, pts, 4, F, 4, S, T, w->enc[0].ln1_g, w->enc[0].ln1_b, kLnEps, e.ln, D, st))
         return rc;
-    if (int rc = encoder_stack(w->enc, w->n_enc, w->ln_g, w->ln_b, e, T, D, w->dqk, w->dv, false, B, S, st)) return rc;
+    if (int rc = encoder_stack(w->enc, w->n_enc, w->ln_g, w->ln_b, e, T, D, w->dqk, w->dv, false, B, S, st, lens)) return rc;
     // head: fc1 + GELU | view harmonics -> fc2 + GELU -> fc3
     if (int rc = lin(e.ln, D, w->fc1, w->fc1.bias, hb, 256, T, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st)) return rc;
     MAC_CUDA(cudaMemcpy2DAsync(hb + 192, 256 * sizeof(float), vh, 64 * sizeof(float), 64 * sizeof(float), T,
@@ -158,6 +159,20 @@ extern "C" int mac_sconevis_forward_f32(const mac_sconevis_w_t *w, const float *
     if (int rc = lin(hb, 256, w->fc2, w->fc2.bias, h2, 128, T, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st)) return rc;
     if (int rc = lin(h2, 128, w->fc3, w->fc3.bias, out, 64, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st)) return rc;
     return MAC_OK;
+}
+}  // namespace
+
+extern "C" int mac_sconevis_forward_f32(const mac_sconevis_w_t *w, const float *pts, const float *vh, float *out, int B, int S,
+                                        void *workspace, size_t workspace_bytes, void *stream)
+{
+    return sconevis_forward(w, pts, vh, out, B, S, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int mac_sconevis_forward_ragged_f32(const mac_sconevis_w_t *w, const float *pts, const float *vh, float *out, int B,
+                                               int S, const int *lens, void *workspace, size_t workspace_bytes, void *stream)
+{
+    MAC_REQUIRE(lens, "lens is null");
+    return sconevis_forward(w, pts, vh, out, B, S, lens, workspace, workspace_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

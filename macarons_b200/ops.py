@@ -223,8 +223,9 @@ def knn16(x, pc, return_dists=True):
     return (idx, dists) if return_dists else idx
 
 
-def sconevis_forward(w, pts, view_harmonics):
-    """Packed weights (netpack.SconeVisW), pts (B,S,4), view_harmonics (B,S,64) -> (B,S,64)."""
+def sconevis_forward(w, pts, view_harmonics, lens=None):
+    """Packed weights (netpack.SconeVisW), pts (B,S,4), view_harmonics (B,S,64) -> (B,S,64).
+    `lens` (B,) int32 CUDA tensor: ragged batch, cloud b holds lens[b] tokens followed by zero padding rows."""
     import ctypes
     _require_cuda_f32("pts", pts)
     _require_cuda_f32("view_harmonics", view_harmonics)
@@ -239,8 +240,16 @@ def sconevis_forward(w, pts, view_harmonics):
     lib = _lib.load()
     with torch.cuda.device(pts.device):
         ws = _net_workspace(pts.device, lib.mac_sconevis_workspace_bytes(B, S))
-        _lib.check(lib.mac_sconevis_forward_f32(ctypes.byref(w), pts.data_ptr(), view_harmonics.data_ptr(), out.data_ptr(),
-                                                B, S, ws.data_ptr(), ws.numel(), _stream_ptr(pts.device)))
+        if lens is None:
+            _lib.check(lib.mac_sconevis_forward_f32(ctypes.byref(w), pts.data_ptr(), view_harmonics.data_ptr(), out.data_ptr(),
+                                                    B, S, ws.data_ptr(), ws.numel(), _stream_ptr(pts.device)))
+        else:
+            if lens.dtype != torch.int32 or lens.device != pts.device or lens.numel() != B:
+                raise ValueError("lens must be an int32 tensor of %d entries on %s" % (B, pts.device))
+            lens = lens.contiguous()
+            _lib.check(lib.mac_sconevis_forward_ragged_f32(ctypes.byref(w), pts.data_ptr(), view_harmonics.data_ptr(),
+                                                           out.data_ptr(), B, S, lens.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                           _stream_ptr(pts.device)))
     return out
 
 
@@ -349,6 +358,40 @@ def sample_proxy_points(X_world, preds, view_harmonics, u, min_occ):
                                                    ws.numel(), _stream_ptr(dev)))
     n_unique = int(counts[1].item())   # the result has a data-dependent length (as torch.unique in the reference)
     return res[:n_unique], res_h[:n_unique], inverse
+
+
+def fov_sample_proxy(X_world, preds, view_harmonics, cams, ndc_bounds, fov_range, min_occ, u):
+    """Batched field-of-view / occupancy selection + proxy sampling for C candidate cameras (mac_fov_sample_proxy_f32).
+    X_world (N,3), preds (N,1), view_harmonics (N,64), cams (C,36) [full projection | world-to-view | centre | pad],
+    ndc_bounds 4 floats, u (C,n_sample) -> res (C,n_sample,4) and res_harmonics (C,n_sample,64) zero-padded after the
+    unique picks, inverse (C,n_sample) int64, counts (C,2) int32 [kept, unique], volume (C,)."""
+    import ctypes
+    for name, t in (("X_world", X_world), ("preds", preds), ("view_harmonics", view_harmonics), ("cams", cams), ("u", u)):
+        _require_cuda_f32(name, t)
+    N = X_world.shape[0]
+    C, n_sample = u.shape
+    if tuple(X_world.shape) != (N, 3) or preds.numel() != N or tuple(view_harmonics.shape) != (N, N_HARMONICS) or \
+            tuple(cams.shape) != (C, 36):
+        raise ValueError("expected X_world (N,3), preds (N,1), view_harmonics (N,64), cams (C,36), u (C,n_sample)")
+    dev = X_world.device
+    X_world, preds, view_harmonics, cams, u = (t.contiguous() for t in (X_world, preds, view_harmonics, cams, u))
+    res = torch.zeros((C, n_sample, 4), dtype=torch.float32, device=dev)
+    res_h = torch.zeros((C, n_sample, N_HARMONICS), dtype=torch.float32, device=dev)
+    inverse = torch.zeros((C, n_sample), dtype=torch.int64, device=dev)
+    counts = torch.zeros((C, 2), dtype=torch.int32, device=dev)
+    volume = torch.zeros((C,), dtype=torch.float32, device=dev)
+    if N == 0 or C == 0:
+        return res, res_h, inverse, counts, volume
+    ndc = (ctypes.c_float * 4)(*[float(v) for v in ndc_bounds])
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ws = _net_workspace(dev, lib.mac_fov_sample_proxy_workspace_bytes(N, C))
+        _lib.check(lib.mac_fov_sample_proxy_f32(X_world.data_ptr(), preds.data_ptr(), view_harmonics.data_ptr(), cams.data_ptr(),
+                                                ctypes.cast(ndc, ctypes.c_void_p), -1.0 if fov_range is None else float(fov_range),
+                                                float(min_occ), u.data_ptr(), N, C, n_sample, res.data_ptr(), res_h.data_ptr(),
+                                                inverse.data_ptr(), counts.data_ptr(), volume.data_ptr(), ws.data_ptr(),
+                                                ws.numel(), _stream_ptr(dev)))
+    return res, res_h, inverse, counts, volume
 
 
 def manydepth_forward(w, x, x_alpha, cam):

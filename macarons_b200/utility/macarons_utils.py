@@ -1,0 +1,179 @@
+"""The functions of reference macarons/utility/macarons_utils.py that sit on the NBV scoring path, over the CUDA
+kernels of this package (same names, argument meaning and return values):
+
+    compute_occupancy_probability               reference :1194-1230
+    predict_coverage_gain_for_single_camera     reference :1580-1738
+    get_distance_factor / _threshold / _smooth  reference :1741-1788
+
+plus `predict_coverage_gains_for_cameras`, the batched form the reference does not have: the testers / trainers call
+`predict_coverage_gain_for_single_camera` once per neighbouring pose (testers/scene.py:434-456,
+trainers/train_macarons.py:291-315); here all C candidates go through ONE field-of-view / occupancy selection +
+sampling launch (csrc/sampling.cu), ONE ragged SconeVis forward (C clouds of <= seq_len unique points each) and ONE
+per-point visibility launch.  The single-camera function is the C = 1 case of it.
+
+Everything outside those functions (Camera / Scene / Memory classes, renderers, data loading, optimisers) is the
+reference's control plane and is not mirrored; the functions below only need duck-typed
+arguments: `camera` with `min_ndc_x/max_ndc_x/min_ndc_y/max_ndc_y` and `fov_camera_0`, cameras with pytorch3d's
+`get_full_projection_transform() / get_world_to_view_transform() / get_camera_center()` and `.fov`.
+"""
+import numpy as np
+import torch
+
+from .. import netpack, ops
+from .scone_utils import normalize_points_in_prediction_box
+
+
+def compute_occupancy_probability(macarons, pc, X, view_harmonics, mask=None, max_points_per_pass=20000):
+    """pc (n_clouds, seq_len, 3), X (n_clouds, n_sample, 3), view_harmonics (n_clouds, n_sample, 64)
+    -> (n_clouds, n_sample, 1) through `macarons(mode='occupancy', ...)`, `max_points_per_pass // n_clouds` queries per
+    forward as in the reference (:1211-1228; the O(passes^2) torch.cat growth is replaced by one output buffer)."""
+    n_clouds, n_sample = pc.shape[0], X.shape[1]
+    p = max_points_per_pass // n_clouds
+    preds = torch.empty(n_clouds, n_sample, 1, dtype=torch.float32, device=X.device)
+    for lo in range(0, n_sample, p):
+        up = min(lo + p, n_sample)
+        preds[:, lo:up] = macarons(mode='occupancy', partial_point_cloud=pc, proxy_points=X[:, lo:up],
+                                   view_harmonics=view_harmonics[:, lo:up]).view(n_clouds, up - lo, -1)
+    return preds
+
+
+# ---- distance factors (reference :1741-1788); pts (..., n_points, 3), X_cam broadcastable (..., 1, 3) ----
+def _pixel_distance_threshold(params, fov_camera, cell_resolution):
+    fov = fov_camera.fov if isinstance(fov_camera.fov, torch.Tensor) else torch.tensor(float(fov_camera.fov))
+    focal_length = 1. / torch.tan(np.pi / 180. * fov / 2.)
+    pixel_size = 2. / min(params.image_height, params.image_width)
+    epsilon = np.sqrt(np.pi) / 2. * cell_resolution
+    return focal_length, pixel_size, epsilon, focal_length * epsilon / pixel_size
+
+
+def get_distance_factor(params, pts, X_cam, fov_camera, cell_resolution):
+    """1 up to the distance at which one surface cell covers one pixel, (threshold / d)^2 beyond.  pts (n_points, 3),
+    X_cam (1, 3) -> (n_points, 1)."""
+    focal_length, pixel_size, epsilon, distance_th = _pixel_distance_threshold(params, fov_camera, cell_resolution)
+    focal_length, distance_th = focal_length.to(pts.device), distance_th.to(pts.device)
+    dists = torch.linalg.norm(pts - X_cam.view(1, 3), dim=-1, keepdim=True)
+    far = epsilon ** 2 * (focal_length / pixel_size / dists) ** 2
+    return torch.where(dists > distance_th, far, torch.ones_like(dists))
+
+
+def get_distance_factor_threshold(pts, X_cam, distance_th=17.):
+    dists = torch.linalg.norm(pts - X_cam.view(1, 3), dim=-1, keepdim=True)
+    return torch.where(dists > distance_th, distance_th ** 2 / dists ** 2, torch.ones_like(dists))
+
+
+def get_distance_factor_smooth(params, pts, X_cam, fov_camera, cell_resolution):
+    _, _, _, distance_th = _pixel_distance_threshold(params, fov_camera, cell_resolution)
+    dists = torch.linalg.norm(pts - X_cam.view(1, 3), dim=-1, keepdim=True)
+    return 1. / (1. + (dists / distance_th.to(pts.device)) ** 2)
+
+
+def _distance_factors(params, world_xyz, X_cam_world, fov_cameras, cell_resolution):
+    """Batched: world_xyz (C, S, 3), X_cam_world (C, 3) -> (C, S), selecting the rule like the reference (:1685-1701)."""
+    out = []
+    for c in range(world_xyz.shape[0]):
+        if params.distance_factor_th is None:
+            f = get_distance_factor(params, world_xyz[c], X_cam_world[c:c + 1], fov_cameras[c], cell_resolution)
+        elif params.distance_factor_th == 'smooth':
+            f = get_distance_factor_smooth(params, world_xyz[c], X_cam_world[c:c + 1], fov_cameras[c], cell_resolution)
+        else:
+            f = get_distance_factor_threshold(world_xyz[c], X_cam_world[c:c + 1], distance_th=params.distance_factor_th)
+        out.append(f.view(1, -1))
+    return torch.cat(out, dim=0)
+
+
+def _camera_rows(fov_cameras, device):
+    """(C, 36) rows [full projection 4x4 | world-to-view 4x4 | centre 3 | 0] of C single pytorch3d-style cameras."""
+    rows = []
+    for cam in fov_cameras:
+        proj = cam.get_full_projection_transform().get_matrix().reshape(-1)[:16]
+        view = cam.get_world_to_view_transform().get_matrix().reshape(-1)[:16]
+        centre = cam.get_camera_center().reshape(-1)[:3]
+        rows.append(torch.cat((proj, view, centre, centre.new_zeros(1))).view(1, 36))
+    return torch.cat(rows, dim=0).to(device=device, dtype=torch.float32).contiguous()
+
+
+def _scone_vis(macarons, params):
+    model = macarons.module if (getattr(params, "jz", False) or getattr(params, "ddp", False)) else macarons
+    return model.visibility
+
+
+def predict_coverage_gains_for_cameras(params, macarons, proxy_scene, surface_scene, X_world, proxy_view_harmonics,
+                                       occ_probs, camera, X_cams_world, fov_cameras, prediction_camera=None, samples=None):
+    """Coverage gains of C candidate cameras in one pass (see the module docstring).
+
+    X_world (N,3), proxy_view_harmonics (N,64), occ_probs (N,1): the scene's proxy points; X_cams_world (C,3) and
+    `fov_cameras` (sequence of C cameras): the candidates; `samples` (C, seq_len) injects the uniforms of the proxy
+    sampling (default: torch.rand on the device, like the reference per call).
+    -> dict with coverage_gain (C,1), visibility_gains (C,1,seq_len), proxy_points_world (C,seq_len,4),
+       view_harmonics (C,seq_len,64), n_points_in_fov (C,) int32, n_unique (C,) int32, fov_proxy_volume (C,)."""
+    if not params.use_occ_to_sample_proxy_points:
+        raise NotImplementedError("the batched path implements occupancy-weighted sampling (the reference default)")
+    dev = X_world.device
+    C = len(fov_cameras)
+    S = int(params.seq_len)
+    vis_model = _scone_vis(macarons, params)
+    if not vis_model.use_sigmoid:
+        raise NameError("WARNING! ReLU has been used in visibility model.")     # Macarons.compute_visibility_gains :176
+    if prediction_camera is None:
+        if camera is None:
+            raise NameError("Both camera and prediction_camera are equal to None.")
+        prediction_camera = camera.fov_camera_0
+    if samples is None:
+        samples = torch.rand(C, S, device=dev)
+    ndc = [float(v) for v in (camera.min_ndc_x, camera.max_ndc_x, camera.min_ndc_y, camera.max_ndc_y)]
+    X_cams_world = X_cams_world.view(C, 3).to(torch.float32)
+
+    # field of view + occupancy threshold + inverse-CDF sampling + unique, all candidates at once  (:1603-1628)
+    res, res_h, inverse, counts, volume = ops.fov_sample_proxy(
+        X_world, occ_probs, proxy_view_harmonics, _camera_rows(fov_cameras, dev), ndc, params.sensor_range,
+        params.min_occ_for_proxy_points, samples.reshape(C, S).to(torch.float32))
+    n_unique = counts[:, 1].contiguous()
+    valid = torch.arange(S, device=dev).view(1, S) < n_unique.view(C, 1)
+
+    # prediction box: centre of the unique points, everything moved to the prediction camera's view space (:1632-1659)
+    xyz = res[..., :3]
+    big = torch.finfo(torch.float32).max
+    hi = torch.where(valid[..., None], xyz, xyz.new_full((), -big)).amax(dim=1)
+    lo = torch.where(valid[..., None], xyz, xyz.new_full((), big)).amin(dim=1)
+    centre = torch.where((n_unique > 0).view(C, 1), (hi + lo) / 2., torch.zeros_like(hi))
+    view_transform = prediction_camera.get_world_to_view_transform()
+    box_centre = view_transform.transform_points(centre).view(C, 3)
+    diag = torch.linalg.norm(proxy_scene.x_max - proxy_scene.x_min).item()
+    pts = torch.cat((normalize_points_in_prediction_box(view_transform.transform_points(xyz.reshape(-1, 3)).view(C, S, 3),
+                                                        box_centre.view(C, 1, 3), diag), res[..., 3:]), dim=-1)
+    pts = torch.where(valid[..., None], pts, torch.zeros_like(pts))      # padding rows must be finite (zeros)
+    X_cam = normalize_points_in_prediction_box(view_transform.transform_points(X_cams_world).view(C, 3), box_centre, diag)
+
+    # visibility-gain harmonics of every candidate's point set: one ragged forward  (:1663)
+    harm = ops.sconevis_forward(netpack.pack_sconevis(vis_model), pts, res_h, lens=n_unique)
+
+    # Monte-Carlo set with duplicates (:1669-1672), per-point gains (:1676-1683), distance factor, integration (:1685-1703)
+    gather = lambda t: torch.gather(t, 1, inverse[..., None].expand(-1, -1, t.shape[-1]))
+    pts_s, harm_s, world_s, vh_s = gather(pts), gather(harm), gather(res), gather(res_h)
+    gains = ops.visibility_gains(pts_s, harm_s, X_cam.view(C, 1, 3), use_sigmoid=True)
+    gains = gains * _distance_factors(params, world_s[..., :3], X_cams_world, fov_cameras,
+                                      getattr(surface_scene, "cell_resolution", None)).view(C, 1, S)
+    empty = (counts[:, 0] == 0).view(C, 1)
+    coverage = torch.where(empty, torch.zeros(C, 1, device=dev), torch.mean(gains, dim=-1) * volume.view(C, 1))
+    return {"coverage_gain": coverage, "visibility_gains": gains, "proxy_points_world": world_s, "view_harmonics": vh_s,
+            "n_points_in_fov": counts[:, 0], "n_unique": n_unique, "fov_proxy_volume": volume,
+            "proxy_points": pts, "harmonics": harm, "sample_idx": inverse, "X_cam": X_cam}
+
+
+def predict_coverage_gain_for_single_camera(params, macarons, proxy_scene, surface_scene, X_world, proxy_view_harmonics,
+                                            occ_probs, camera, X_cam_world, fov_camera, prediction_camera=None):
+    """Reference signature and return values (:1580-1738): (proxy_points_world (1,seq_len,4), view_harmonics
+    (1,seq_len,64), visibility_gains (1,1,seq_len), coverage_gain (1,1)); when no proxy point with occupancy above
+    the threshold is in the field of view, the reference's dummy 16-point pass with a zero gain."""
+    out = predict_coverage_gains_for_cameras(params, macarons, proxy_scene, surface_scene, X_world, proxy_view_harmonics,
+                                             occ_probs, camera, X_cam_world.view(1, 3), [fov_camera],
+                                             prediction_camera=prediction_camera)
+    if int(out["n_points_in_fov"][0].item()) > 0:
+        return out["proxy_points_world"], out["view_harmonics"], out["visibility_gains"], out["coverage_gain"].view(-1, 1)
+    dev = X_world.device
+    model = macarons.module if (getattr(params, "jz", False) or getattr(params, "ddp", False)) else macarons
+    dummy_pts = torch.zeros(1, params.k_for_knn, 4, device=dev)
+    dummy_vh = torch.zeros(1, params.k_for_knn, params.n_harmonics, device=dev)
+    dummy_harm = macarons(mode='visibility', proxy_points=dummy_pts, view_harmonics=dummy_vh)
+    gains = model.compute_visibility_gains(pts=dummy_pts, harmonics=dummy_harm, X_cam=X_cam_world.view(1, -1, 3))
+    return dummy_pts, dummy_vh, gains, (torch.mean(gains, dim=-1) * 0.).view(-1, 1)

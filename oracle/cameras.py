@@ -35,7 +35,10 @@ class Transform3d:
         if eps is not None:
             denom_sign = denom.sign() + (denom == 0.0).type_as(denom)
             denom = denom_sign * torch.clamp(denom.abs(), eps)
-        return out[..., :3] / denom
+        res = out[..., :3] / denom
+        if res.shape[0] == 1 and points.dim() == 2:   # pytorch3d: a (P,3) input with one transform comes back as (P,3)
+            res = res.reshape(points.shape)
+        return res
 
 
 class FoVPerspectiveCameras:

@@ -32,7 +32,9 @@ from macarons.utility import scone_utils as ref_su  # noqa: E402
 from macarons.networks.SconeOcc import SconeOcc  # noqa: E402
 from macarons.utility import utils as ref_utils  # noqa: E402
 from macarons.networks import ManyDepth as ref_md  # noqa: E402
+from oracle import cameras as o_cams  # noqa: E402
 from oracle import depth as o_depth  # noqa: E402
+from oracle import macarons_cov as o_mcov  # noqa: E402
 from oracle import sampling as o_sampling  # noqa: E402
 from oracle import scone_nets as o_nets  # noqa: E402
 from oracle import sh_cov as o_cov  # noqa: E402
@@ -188,6 +190,64 @@ def nets_goldens():
              weights_digest=synth.state_dict_digest(occ_sd), input_digest=digest(pc, x, vh), occupancy=out)
 
 
+
+# (name, N proxy points, C candidate cameras, seed, distance_factor_th, seq_len)
+MACARONS_COV_CASES = [("macarons_cov_th17", 20000, 6, 701, 17.0, 2048), ("macarons_cov_smooth", 6000, 4, 702, "smooth", 512),
+                      ("macarons_cov_pixel", 6000, 3, 703, None, 512)]
+
+
+def macarons_cov_goldens():
+    """`predict_coverage_gain_for_single_camera` of the reference (utility/macarons_utils.py:1580-1738) with its own
+    `Camera.get_points_in_fov`, `Macarons` wrapper and `SconeVis`, per candidate camera of a synthetic scene; the last
+    candidate of every case is moved far outside the scene so that the empty-field-of-view branch runs too."""
+    import types
+    from macarons.utility import macarons_utils as ref_mu
+    vis = SconeVis()
+    vis_sd = synth.seeded_state_dict(vis.state_dict(), NET_WEIGHT_SEED)
+    vis.load_state_dict(vis_sd)
+    vis.eval()
+    macarons = Macarons(None, None, vis)
+    H, W = 256, 456
+    nb = synth.ndc_bounds(H, W)
+    for name, N, C, seed, th, seq_len in MACARONS_COV_CASES:
+        s = synth.macarons_scene(N, C, seed)
+        s["T"][-1] = s["T"][-1] + 500.0     # candidate C-1 sees nothing
+        params = types.SimpleNamespace(sensor_range=70., min_occ_for_proxy_points=0.1, seq_len=seq_len,
+                                       use_occ_to_sample_proxy_points=True, jz=False, ddp=False, distance_factor_th=th,
+                                       image_height=H, image_width=W, k_for_knn=16, n_harmonics=64)
+        fake_camera = types.SimpleNamespace(min_ndc_x=nb[0], max_ndc_x=nb[1], min_ndc_y=nb[2], max_ndc_y=nb[3], device="cpu")
+        fake_camera.get_points_in_fov = types.MethodType(ref_mu.Camera.get_points_in_fov, fake_camera)
+        proxy_scene = types.SimpleNamespace(x_min=s["x_min"], x_max=s["x_max"])
+        surface_scene = types.SimpleNamespace(cell_resolution=0.5)
+        pred_cam = o_cams.FoVPerspectiveCameras(R=s["pred_R"], T=s["pred_T"], zfar=1000.)
+        diag = torch.linalg.norm(s["x_max"] - s["x_min"]).item()
+        cov_all, vis_sum, nuniq = [], [], []
+        with torch.no_grad():
+            for c in range(C):
+                cam = o_cams.FoVPerspectiveCameras(R=s["R"][c:c + 1], T=s["T"][c:c + 1], zfar=1000.)
+                X_cam = cam.get_camera_center()
+                state = torch.get_rng_state()
+                torch.manual_seed(9000 + c)
+                u = torch.rand(seq_len, 1)
+                torch.manual_seed(9000 + c)
+                ref = ref_mu.predict_coverage_gain_for_single_camera(
+                    params, macarons, proxy_scene, surface_scene, s["X_world"].clone(), s["vh"].clone(), s["occ"].clone(),
+                    fake_camera, X_cam, cam, prediction_camera=pred_cam)
+                torch.set_rng_state(state)
+                got = o_mcov.predict_coverage_gain_for_single_camera(
+                    vis_sd, s["X_world"], s["vh"], s["occ"], X_cam, cam, pred_cam, nb, diag, sensor_range=70., min_occ=0.1,
+                    seq_len=seq_len, distance_factor_th=th, image_height=H, image_width=W, cell_resolution=0.5, u=u)
+                for a, b, what in zip(ref, got, ("proxy points", "view harmonics", "visibility gains", "coverage gain")):
+                    must_equal(a, b, "%s camera %d %s" % (name, c, what))
+                cov_all.append(ref[3].view(-1))
+                vis_sum.append(ref[2].double().sum().view(1))
+                nuniq.append(ref[0].shape[1])
+        save(name, N=N, C=C, seed=seed, seq_len=seq_len, distance_factor_th=-1.0 if th is None else (0.0 if th == "smooth" else th),
+             weight_seed=NET_WEIGHT_SEED, weights_digest=synth.state_dict_digest(vis_sd),
+             input_digest=digest(s["X_world"], s["vh"], s["occ"], s["R"], s["T"]), coverage=torch.cat(cov_all),
+             visibility_sum=torch.cat(vis_sum), n_returned=np.asarray(nuniq))
+
+
 # (name, B, H, W, seed, stored row stride)
 DEPTH_CASES = [("depth_64x96", 1, 64, 96, 601, 1), ("depth_96x160_b2", 2, 96, 160, 602, 2)]
 
@@ -225,6 +285,9 @@ if __name__ == "__main__":
     if "--depth-only" in sys.argv:
         depth_goldens()
         raise SystemExit(0)
+    if "--macarons-only" in sys.argv:
+        macarons_cov_goldens()
+        raise SystemExit(0)
     if "--nets-only" in sys.argv:
         nets_goldens()
         raise SystemExit(0)
@@ -232,5 +295,6 @@ if __name__ == "__main__":
     view_state_goldens()
     sampling_goldens()
     nets_goldens()
+    macarons_cov_goldens()
     depth_goldens()
     print("all oracle == reference checks passed (bitwise)")

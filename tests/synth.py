@@ -170,3 +170,48 @@ def depth_inputs(B, H, W, seed, n_alpha=2):
     gt_pose = torch.cat((0.02 * (torch.rand(B, n_alpha, 3, generator=gen) - 0.5),       # translation / pose_factor
                          0.002 * (torch.rand(B, n_alpha, 3, generator=gen) - 0.5)), dim=-1)
     return x.contiguous(), x_alpha.contiguous(), R, T, zfar, gt_pose.contiguous()
+
+
+# ---- MACARONS candidate scoring ---------------------------------------
+def look_at_RT(eye, at, up=(0.0, 1.0, 0.0)):
+    """pytorch3d `look_at_view_transform(eye=, at=)` convention restated: rows of X_view = X_world @ R + T,
+    +Z towards `at`, +X left, +Y up.  eye, at (n,3) -> R (n,3,3), T (n,3)."""
+    up = torch.tensor(up, dtype=eye.dtype).view(1, 3).expand_as(eye)
+    z = torch.nn.functional.normalize(at - eye, eps=1e-5)
+    x = torch.nn.functional.normalize(torch.cross(up, z, dim=1), eps=1e-5)
+    y = torch.nn.functional.normalize(torch.cross(z, x, dim=1), eps=1e-5)
+    R = torch.cat((x[:, None, :], y[:, None, :], z[:, None, :]), dim=1).transpose(1, 2)
+    T = -torch.bmm(R.transpose(1, 2), eye[:, :, None])[:, :, 0]
+    return R.contiguous(), T.contiguous()
+
+
+def ndc_bounds(image_height=256, image_width=456):
+    """(min_ndc_x, max_ndc_x, min_ndc_y, max_ndc_y) as `Camera.__init__` derives them (macarons_utils.py:1929-1938)."""
+    m = min(image_width, image_height)
+    max_x = image_width / m
+    min_x = image_width / m - ((image_width - 1) / (m - 1)) * 2
+    max_y = image_height / m
+    min_y = image_height / m - ((image_height - 1) / (m - 1)) * 2
+    f = lambda v: float(torch.tensor(v, dtype=torch.float32))
+    return f(min_x), f(max_x), f(min_y), f(max_y)
+
+
+def macarons_scene(N, C, seed, half_extent=(40.0, 15.0, 40.0)):
+    """A synthetic MACARONS scoring state: N proxy points uniform in the scene box with a blobby occupancy field
+    (a third of them below the 0.1 threshold), their view harmonics, C candidate cameras inside the box looking at
+    random targets, and the prediction camera.  -> dict of CPU tensors."""
+    gen = torch.Generator(device="cpu").manual_seed(int(seed))
+    ext = torch.tensor(half_extent)
+    X = (torch.rand(N, 3, generator=gen) * 2 - 1) * ext
+    centres = (torch.rand(6, 3, generator=gen) * 2 - 1) * ext * 0.7
+    d2 = ((X[:, None, :] - centres[None]) / (0.45 * ext)).pow(2).sum(-1)
+    occ = (torch.exp(-d2).sum(-1) * (0.6 + 0.4 * torch.rand(N, generator=gen))).clamp(0, 1).view(N, 1)
+    vh = 0.3 * torch.randn(N, 64, generator=gen)
+    eye = (torch.rand(C, 3, generator=gen) * 2 - 1) * ext * 0.9
+    at = (torch.rand(C, 3, generator=gen) * 2 - 1) * ext * 0.5
+    R, T = look_at_RT(eye, at)
+    pe = (torch.rand(1, 3, generator=gen) * 2 - 1) * ext * 0.5
+    pR, pT = look_at_RT(pe, torch.zeros(1, 3))
+    return {"X_world": X.contiguous(), "occ": occ.contiguous(), "vh": vh.contiguous(), "X_cam": eye.contiguous(),
+            "R": R, "T": T, "pred_R": pR, "pred_T": pT, "x_min": -ext, "x_max": ext,
+            "diag": torch.linalg.norm(2 * ext).item(), "u": torch.rand(C, 2048, 1, generator=gen)}
