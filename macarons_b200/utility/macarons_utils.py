@@ -67,29 +67,49 @@ def get_distance_factor_smooth(params, pts, X_cam, fov_camera, cell_resolution):
     return 1. / (1. + (dists / distance_th.to(pts.device)) ** 2)
 
 
+def _as_list(fov_cameras):
+    return list(fov_cameras) if isinstance(fov_cameras, (list, tuple)) else None
+
+
+def _camera_fovs(fov_cameras, C, device):
+    """(C,) field-of-view angles in degrees of a batched camera or a list of single cameras."""
+    cams = _as_list(fov_cameras)
+    fov = fov_cameras.fov if cams is None else torch.cat([torch.as_tensor(c.fov, dtype=torch.float32).reshape(-1)[:1] for c in cams])
+    return torch.as_tensor(fov, dtype=torch.float32, device=device).reshape(-1).expand(C)
+
+
 def _distance_factors(params, world_xyz, X_cam_world, fov_cameras, cell_resolution):
     """Batched: world_xyz (C, S, 3), X_cam_world (C, 3) -> (C, S), selecting the rule like the reference (:1685-1701)."""
-    out = []
-    for c in range(world_xyz.shape[0]):
-        if params.distance_factor_th is None:
-            f = get_distance_factor(params, world_xyz[c], X_cam_world[c:c + 1], fov_cameras[c], cell_resolution)
-        elif params.distance_factor_th == 'smooth':
-            f = get_distance_factor_smooth(params, world_xyz[c], X_cam_world[c:c + 1], fov_cameras[c], cell_resolution)
-        else:
-            f = get_distance_factor_threshold(world_xyz[c], X_cam_world[c:c + 1], distance_th=params.distance_factor_th)
-        out.append(f.view(1, -1))
-    return torch.cat(out, dim=0)
+    C = world_xyz.shape[0]
+    dists = torch.linalg.norm(world_xyz - X_cam_world.view(C, 1, 3), dim=-1)
+    if params.distance_factor_th is not None and params.distance_factor_th != 'smooth':
+        th = params.distance_factor_th
+        return torch.where(dists > th, th ** 2 / dists ** 2, torch.ones_like(dists))          # get_distance_factor_threshold
+    focal_length = (1. / torch.tan(np.pi / 180. * _camera_fovs(fov_cameras, C, world_xyz.device) / 2.)).view(C, 1)
+    pixel_size = 2. / min(params.image_height, params.image_width)
+    epsilon = np.sqrt(np.pi) / 2. * cell_resolution
+    distance_th = focal_length * epsilon / pixel_size
+    if params.distance_factor_th == 'smooth':
+        return 1. / (1. + (dists / distance_th) ** 2)                                          # get_distance_factor_smooth
+    far = epsilon ** 2 * (focal_length / pixel_size / dists) ** 2                              # get_distance_factor
+    return torch.where(dists > distance_th, far, torch.ones_like(dists))
 
 
 def _camera_rows(fov_cameras, device):
-    """(C, 36) rows [full projection 4x4 | world-to-view 4x4 | centre 3 | 0] of C single pytorch3d-style cameras."""
-    rows = []
-    for cam in fov_cameras:
-        proj = cam.get_full_projection_transform().get_matrix().reshape(-1)[:16]
-        view = cam.get_world_to_view_transform().get_matrix().reshape(-1)[:16]
-        centre = cam.get_camera_center().reshape(-1)[:3]
-        rows.append(torch.cat((proj, view, centre, centre.new_zeros(1))).view(1, 36))
-    return torch.cat(rows, dim=0).to(device=device, dtype=torch.float32).contiguous()
+    """(C, 36) rows [full projection 4x4 | world-to-view 4x4 | centre 3 | 0] of one batched pytorch3d-style camera
+    (C entries: three batched calls) or of a list of C single cameras (the reference's call pattern, C x 3 calls)."""
+    cams = _as_list(fov_cameras)
+    if cams is None:
+        proj = fov_cameras.get_full_projection_transform().get_matrix()
+        view = fov_cameras.get_world_to_view_transform().get_matrix()
+        centre = fov_cameras.get_camera_center()
+    else:
+        proj = torch.cat([c.get_full_projection_transform().get_matrix().reshape(1, 4, 4) for c in cams])
+        view = torch.cat([c.get_world_to_view_transform().get_matrix().reshape(1, 4, 4) for c in cams])
+        centre = torch.cat([c.get_camera_center().reshape(1, 3) for c in cams])
+    C = proj.shape[0]
+    rows = torch.cat((proj.reshape(C, 16), view.reshape(C, 16), centre.reshape(C, 3), centre.new_zeros(C, 1)), dim=1)
+    return rows.to(device=device, dtype=torch.float32).contiguous()
 
 
 def _scone_vis(macarons, params):
@@ -102,14 +122,16 @@ def predict_coverage_gains_for_cameras(params, macarons, proxy_scene, surface_sc
     """Coverage gains of C candidate cameras in one pass (see the module docstring).
 
     X_world (N,3), proxy_view_harmonics (N,64), occ_probs (N,1): the scene's proxy points; X_cams_world (C,3) and
-    `fov_cameras` (sequence of C cameras): the candidates; `samples` (C, seq_len) injects the uniforms of the proxy
+    `fov_cameras` (ONE batched camera of C entries -- preferred, 3 matrix calls in total -- or a sequence of C single
+    cameras): the candidates; `samples` (C, seq_len) injects the uniforms of the proxy
     sampling (default: torch.rand on the device, like the reference per call).
     -> dict with coverage_gain (C,1), visibility_gains (C,1,seq_len), proxy_points_world (C,seq_len,4),
        view_harmonics (C,seq_len,64), n_points_in_fov (C,) int32, n_unique (C,) int32, fov_proxy_volume (C,)."""
     if not params.use_occ_to_sample_proxy_points:
         raise NotImplementedError("the batched path implements occupancy-weighted sampling (the reference default)")
     dev = X_world.device
-    C = len(fov_cameras)
+    X_cams_world = X_cams_world.reshape(-1, 3).to(torch.float32)
+    C = X_cams_world.shape[0]
     S = int(params.seq_len)
     vis_model = _scone_vis(macarons, params)
     if not vis_model.use_sigmoid:
@@ -121,7 +143,6 @@ def predict_coverage_gains_for_cameras(params, macarons, proxy_scene, surface_sc
     if samples is None:
         samples = torch.rand(C, S, device=dev)
     ndc = [float(v) for v in (camera.min_ndc_x, camera.max_ndc_x, camera.min_ndc_y, camera.max_ndc_y)]
-    X_cams_world = X_cams_world.view(C, 3).to(torch.float32)
 
     # field of view + occupancy threshold + inverse-CDF sampling + unique, all candidates at once  (:1603-1628)
     res, res_h, inverse, counts, volume = ops.fov_sample_proxy(

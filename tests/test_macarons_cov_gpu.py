@@ -98,6 +98,14 @@ def test_batched_candidates_match_oracle_and_reference_golden(cuda_device, name)
                                                     prediction_camera=pred, samples=u.to(dev))
     cov = out["coverage_gain"].view(-1).cpu().numpy()
     ref = g["coverage"]
+    # the same candidates as ONE batched camera object (three matrix calls instead of 3 C)
+    from oracle import cameras as o_cams
+    batch_cam = o_cams.FoVPerspectiveCameras(R=s["R"], T=s["T"], zfar=1000., device=dev)
+    with torch.no_grad():
+        out_b = mu.predict_coverage_gains_for_cameras(params, macarons, proxy_scene, surface_scene, s["X_world"].to(dev),
+                                                      s["vh"].to(dev), s["occ"].to(dev), camera, batch_cam.get_camera_center(),
+                                                      batch_cam, prediction_camera=pred, samples=u.to(dev))
+    assert np.abs(out_b["coverage_gain"].view(-1).cpu().numpy() - cov).max() <= COV_RTOL * np.abs(ref).max()
     assert np.abs(cov - ref).max() <= COV_RTOL * np.abs(ref).max(), (cov, ref)
     assert cov[-1] == 0.0 and int(out["n_points_in_fov"][-1]) == 0           # empty field of view
     assert int(np.argmax(cov)) == int(np.argmax(ref))                        # the NBV among the candidates
