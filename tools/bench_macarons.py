@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--c", type=int, default=128)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--cpu-cands", type=int, default=2)
+    ap.add_argument("--no-loop", action="store_true", help="skip the per-candidate loop (profiling runs)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     S = 2048
@@ -71,7 +72,8 @@ def main():
                 if cov.shape[0] > 0 and cov > best:     # testers/scene.py:454
                     best, best_c = cov, c
             return best_c
-        res["per_candidate_loop_ms"] = timed(loop, max(1, args.iters // 2), warmup=1)
+        if not args.no_loop:
+            res["per_candidate_loop_ms"] = timed(loop, max(1, args.iters // 2), warmup=1)
 
         # stages of the batched pass
         rows = mu._camera_rows(cams, dev)
