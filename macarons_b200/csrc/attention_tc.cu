@@ -36,8 +36,6 @@ constexpr int kKB = 64;      // keys per block
 constexpr int kRow = 32;     // floats per packed q / k row (one SW128 span): [hi | lo | 0]
 constexpr float kSlack = 8.f;  // the running softmax maximum may lag the true one by this much (base-2 exponent)
 
-__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-
 // ---- 1. operand preparation ---------------------------------------------------------------------
 template <int DQK, int DV>
 __global__ void __launch_bounds__(256) attn_prep_kernel(const float *__restrict__ qkv, int ldq, float *__restrict__ qp,
@@ -295,7 +293,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                 float lo[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    v[i] = tf32_trunc(s[c * 32 + i]);
+                    v[i] = tf32_hi(s[c * 32 + i]);
                     lo[i] = s[c * 32 + i] - v[i];
                 }
                 tmem_st32(t_phi + lane_addr + c * 32, v);

@@ -13,8 +13,9 @@
 //     every product is evaluated as  x_hi w_hi + x_lo w_hi + x_hi w_lo  (x = x_hi + x_lo with both parts
 //     exactly representable in TF32; the dropped x_lo w_lo term is 2^-22 relative).  W is split once when
 //     the weights are packed; X is split in shared memory by 4 dedicated warps (element-wise, hence
-//     oblivious to the swizzle), fenced to the async proxy and handed to the MMA warp through a second
-//     mbarrier.
+//     oblivious to the swizzle; x_hi by clearing the low mantissa bits, x_lo = x - x_hi rounded with integer
+//     arithmetic: 4 full-rate instructions per element, tc_common.h), fenced to the async proxy and handed to
+//     the MMA warp through a second mbarrier.
 //   * persistent CTAs (one per SM) walk the tiles; two TMEM accumulators let the TMA / split / MMA warps work
 //     on tile t+1 while the 4 epilogue warps drain tile t.
 //   * epilogue: one output row per thread, 32 columns at a time: tcgen05.ld -> bias -> activation (ReLU /
@@ -276,8 +277,8 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     for (int i = 0; i < kATileBytes / 16 / 128; ++i) {
                         const float4 v = hi[t + i * 128];
                         float4 h, l;
-                        h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
-                        l.x = to_tf32(v.x - h.x), l.y = to_tf32(v.y - h.y), l.z = to_tf32(v.z - h.z), l.w = to_tf32(v.w - h.w);
+                        h.x = tf32_hi(v.x), h.y = tf32_hi(v.y), h.z = tf32_hi(v.z), h.w = tf32_hi(v.w);
+                        l.x = tf32_lo(v.x, h.x), l.y = tf32_lo(v.y, h.y), l.z = tf32_lo(v.z, h.z), l.w = tf32_lo(v.w, h.w);
                         hi[t + i * 128] = h;
                         lo[t + i * 128] = l;
                     }

@@ -151,6 +151,14 @@ __device__ __forceinline__ float to_tf32(float x)
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
+// Split of an fp32 value into two TF32 halves with full-rate integer / FADD instructions (cvt.rna.tf32.f32 is emulated
+// by ~5 instructions on sm_100a): hi = x with the 13 low mantissa bits cleared (NaN / inf preserved), lo = x - hi exactly
+// (|lo| < 2^-10 |x|), rounded to nearest TF32 by adding half an ulp to the bit pattern.  x = hi + lo to 2^-22 relative.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_lo(float x, float hi)
+{
+    return __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
+}
 #endif  // __CUDACC__
 
 }  // namespace mac
