@@ -122,6 +122,15 @@ int mac_covgain_push_f32(const float *pts, int pts_dim, const float *harmonics, 
 int mac_gather_wait_argmax(const float *scores, const unsigned int *flags, int world, unsigned int epoch,
                            int B, int C, long long *best, int *status, void *stream);
 
+/* One sharded scoring step = mac_covgain_push_f32 followed by mac_gather_wait_argmax on this rank's board
+ * (board->scores[board->rank], board->flags[board->rank]) in ONE host call: at 64 cameras per GPU the step is ~70 us
+ * of device time, so the host side (two ctypes calls, argument marshalling) must not cost more than that.
+ * ev_begin / ev_end: optional cudaEvent_t recorded on `stream` around the scoring kernel (per-kernel timing). */
+int mac_covgain_push_argmax_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams, int B, int P,
+                                int C, int cam_begin, int cam_end, int act, void *workspace, size_t workspace_bytes,
+                                const mac_peer_board_t *board, long long *best, int *status, void *ev_begin,
+                                void *ev_end, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused linear layer on tcgen05 tensor cores (building block of SconeOcc / SconeVis; replaces the
  * nn.Linear + LayerNorm + GELU + residual sequences of /root/reference/macarons/networks/Attention.py:96-98,

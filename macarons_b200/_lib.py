@@ -45,6 +45,11 @@ SYMBOLS["mac_covgain_push_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_f
                                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                   ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
                                                   ctypes.POINTER(PeerBoard), ctypes.c_void_p])
+SYMBOLS["mac_covgain_push_argmax_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p,
+                                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                                         ctypes.POINTER(PeerBoard), ctypes.c_void_p, ctypes.c_void_p,
+                                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p])
 SYMBOLS["mac_gather_wait_argmax"] = (ctypes.c_int, [_c_float_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint,
                                                     ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                     ctypes.c_void_p])

@@ -435,6 +435,10 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
         else break;
     }
     while (cpt > 32 && cpt / 2 >= n_local) cpt /= 2;
+    // MAC_COVGAIN_CPT / MAC_COVGAIN_TPT override the heuristics (tuning knobs for tools/bench_covgain.py)
+    static const int force_cpt = [] { const char *e = getenv("MAC_COVGAIN_CPT"); return e ? atoi(e) : 0; }();
+    static const int force_tpt = [] { const char *e = getenv("MAC_COVGAIN_TPT"); return e ? atoi(e) : 0; }();
+    if (force_cpt == 32 || force_cpt == 64 || force_cpt == 96 || force_cpt == 128) cpt = force_cpt;
     prm.cams_per_task = cpt;
     prm.n_cam_chunks = (n_local + cpt - 1) / cpt;
     // Several point tiles per task only when there are far more tasks than warp slots (fewer atomics).
@@ -442,6 +446,7 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
     long long tpt = base_tasks / (24 * slots);
     if (tpt < 1) tpt = 1;
     if (tpt > 64) tpt = 64;
+    if (force_tpt > 0) tpt = force_tpt;
     prm.tiles_per_task = static_cast<int>(tpt);
     prm.runs_per_cloud = (prm.tiles_per_cloud + prm.tiles_per_task - 1) / prm.tiles_per_task;
     const long long total = static_cast<long long>(B) * prm.runs_per_cloud * prm.n_cam_chunks;
@@ -531,4 +536,23 @@ extern "C" int mac_covgain_push_f32(const float *pts, int pts_dim, const float *
     }
     return mac::plan_and_launch(true, pts, pts_dim, harmonics, cams, nullptr, B, P, C, cam_begin, cam_end, act,
                                 workspace, workspace_bytes, stream, board);
+}
+
+extern "C" int mac_covgain_push_argmax_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams, int B,
+                                           int P, int C, int cam_begin, int cam_end, int act, void *workspace,
+                                           size_t workspace_bytes, const mac_peer_board_t *board, long long *best,
+                                           int *status, void *ev_begin, void *ev_end, void *stream)
+{
+    if (!board || !best || !status) {
+        mac::set_error("mac_covgain_push_argmax_f32 needs a peer board, best and status");
+        return MAC_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ev_begin) MAC_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_begin), st));
+    if (int rc = mac::plan_and_launch(true, pts, pts_dim, harmonics, cams, nullptr, B, P, C, cam_begin, cam_end, act, workspace,
+                                      workspace_bytes, stream, board))
+        return rc;
+    if (ev_end) MAC_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_end), st));
+    return mac_gather_wait_argmax(board->scores[board->rank], board->flags[board->rank], board->world, board->epoch, B, C,
+                                  best, status, stream);
 }

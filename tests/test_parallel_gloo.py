@@ -43,6 +43,13 @@ def _worker(rank, world, port, C, ret):
         scores, best = parallel.sharded_coverage_gain(_oracle_slice_scorer, pts, harm, cams)
         full = sh_cov.coverage_gain(pts, harm, cams)
         ok = torch.equal(scores, full) and torch.equal(best, full.argmax(-1))
+        # sharded upload: every rank copies 1/W of the rows, one all-gather completes the tensor (rows % W != 0 too)
+        for rows in (10, 7, 1):
+            host = torch.arange(rows * 3, dtype=torch.float32).view(rows, 3)
+            ok = ok and torch.equal(parallel.upload_rows_sharded(host, torch.device("cpu")), host)
+        buf = torch.empty((-(-7 // world) * world, 3))
+        ok = ok and torch.equal(parallel.upload_rows_sharded(host.expand(7, 3).contiguous(), torch.device("cpu"), buf=buf),
+                                host.expand(7, 3))
         gathered = [None] * world
         dist.all_gather_object(gathered, (ok, best.tolist()))
         if rank == 0:
