@@ -254,7 +254,8 @@ def run_ours(args, cfg):
     if not args.nccl_gather:
         try:
             board = parallel.PeerScoreBoard(B, C, dev)
-            exchange = "fused: scores pushed to every peer's board from the scoring kernel (NVLink P2P), 1 wait+argmax kernel"
+            exchange = ("fused: the finishing CTA of the scoring kernel pushes the scores to every peer's board (NVLink P2P), waits for "
+                        "the peers' flags and takes the argmax: 1 launch per step")
         except Exception as exc:  # symmetric memory unavailable: fall back to the NCCL collective
             exchange += " (peer board unavailable: %s)" % type(exc).__name__
 

@@ -122,9 +122,10 @@ int mac_covgain_push_f32(const float *pts, int pts_dim, const float *harmonics, 
 int mac_gather_wait_argmax(const float *scores, const unsigned int *flags, int world, unsigned int epoch,
                            int B, int C, long long *best, int *status, void *stream);
 
-/* One sharded scoring step = mac_covgain_push_f32 followed by mac_gather_wait_argmax on this rank's board
- * (board->scores[board->rank], board->flags[board->rank]) in ONE host call: at 64 cameras per GPU the step is ~70 us
- * of device time, so the host side (two ctypes calls, argument marshalling) must not cost more than that.
+/* One sharded scoring step in ONE launch: mac_covgain_push_f32 whose finishing CTA, after raising this rank's flags,
+ * also does the work of mac_gather_wait_argmax on this rank's own board (board->scores[board->rank],
+ * board->flags[board->rank]): it waits for the flags of all ranks and writes best / status.  At 64 cameras per GPU the
+ * step is ~70 us of device time, so neither a second launch nor two host calls with argument marshalling are affordable.
  * ev_begin / ev_end: optional cudaEvent_t recorded on `stream` around the scoring kernel (per-kernel timing). */
 int mac_covgain_push_argmax_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams, int B, int P,
                                 int C, int cam_begin, int cam_end, int act, void *workspace, size_t workspace_bytes,

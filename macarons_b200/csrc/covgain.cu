@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include "gather_dev.h"
 #include "mac_common.h"
 #include "sh_horner_gen.h"
 
@@ -69,6 +70,10 @@ struct CovgainParams {
     unsigned int push_epoch;
     float *push_dst[MAC_MAX_PEERS];
     unsigned int *push_flag[MAC_MAX_PEERS];
+    // fused wait + argmax (push_world > 0 and best != null): after raising its flags the finishing CTA waits for the
+    // flags of all ranks on the LOCAL board and writes the replicated NBV index: the whole sharded step is one launch
+    long long *best;
+    int *status;
 };
 
 struct Ray {
@@ -311,6 +316,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
                     st_release_sys(prm.push_flag[threadIdx.x] + prm.push_rank, prm.push_epoch);
             }
             if (threadIdx.x == 0) *prm.done = 0u;
+            if (prm.push_world > 0 && prm.best) {
+                __syncthreads();
+                wait_scores_and_argmax<WARPS * 32>(prm.push_dst[prm.push_rank], prm.push_flag[prm.push_rank], prm.push_world,
+                                                   prm.push_epoch, prm.B, prm.C, prm.best, prm.status);
+            }
         }
     }
 }
@@ -353,7 +363,7 @@ int make_harmonics_map(CUtensorMap *map, const float *harm, int B, int P)
 int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *harm, const float *cams, float *out,
                     int B, int P, int C, int cam_begin, int cam_end, int act, void *workspace,
                     size_t workspace_bytes, void *stream, const mac_peer_board_t *board = nullptr, int mean_count = 0,
-                    int finalize = 1)
+                    int finalize = 1, long long *best = nullptr, int *status = nullptr)
 {
     MAC_REQUIRE(pts && harm && cams && (out || board), "null tensor pointer");
     if (board) {
@@ -392,6 +402,8 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
             prm.push_dst[r] = board->scores[r];
             prm.push_flag[r] = board->flags[r];
         }
+        prm.best = best;
+        prm.status = status;
     }
     if (reduce) {
         const size_t need = mac_covgain_workspace_bytes(B, C);
@@ -549,10 +561,10 @@ extern "C" int mac_covgain_push_argmax_f32(const float *pts, int pts_dim, const 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (ev_begin) MAC_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_begin), st));
+    // the finishing CTA of the scoring kernel also waits for the peers and takes the argmax: one launch per step
     if (int rc = mac::plan_and_launch(true, pts, pts_dim, harmonics, cams, nullptr, B, P, C, cam_begin, cam_end, act, workspace,
-                                      workspace_bytes, stream, board))
+                                      workspace_bytes, stream, board, 0, 1, best, status))
         return rc;
     if (ev_end) MAC_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_end), st));
-    return mac_gather_wait_argmax(board->scores[board->rank], board->flags[board->rank], board->world, board->epoch, B, C,
-                                  best, status, stream);
+    return MAC_OK;
 }

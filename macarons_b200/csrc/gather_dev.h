@@ -1,0 +1,77 @@
+// Device side of the score exchange: wait until every rank's columns have landed in the local score board, then
+// take the replicated NBV argmax (reference testers/shapenet.py:172, testers/scene.py:454: first maximum wins).
+// Used by the stand-alone kernel of gather.cu and by the finishing CTA of the scoring kernel (covgain.cu).
+#pragma once
+#include "mac_common.h"
+
+namespace mac {
+
+// total order used for the argmax: NaN beats everything (torch.argmax semantics), then larger value, then lower index
+__device__ __forceinline__ bool score_better(float av, int ai, float bv, int bi)
+{
+    const bool an = av != av, bn = bv != bv;
+    if (an != bn) return an;
+    if (!an && av != bv) return av > bv;
+    return ai < bi;
+}
+
+// Called by all NT threads of ONE CTA.
+template <int NT>
+__device__ void wait_scores_and_argmax(const float *scores, const unsigned int *flags, int world, unsigned int epoch, int B,
+                                       int C, long long *best, int *status)
+{
+    __shared__ int timed_out;
+    __shared__ float s_val[NT];
+    __shared__ int s_idx[NT];
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
+    if (threadIdx.x < world) {
+        unsigned long long t0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        // flags carry epochs that only grow; compare as a signed distance so that wrap-around is harmless
+        while (static_cast<int>(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 2000000000ull) {  // 2 s: a peer died; do not hang the device
+                timed_out = 1;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    if (timed_out) {
+        if (threadIdx.x == 0) *status = 1;
+        return;
+    }
+    for (int b = 0; b < B; ++b) {
+        float v = 0.f;
+        int idx = 0x7fffffff;
+        for (int c = threadIdx.x; c < C; c += NT) {
+            const float x = __ldcg(scores + static_cast<size_t>(b) * C + c);  // written by peers: skip L1
+            if (idx == 0x7fffffff || score_better(x, c, v, idx)) {
+                v = x;
+                idx = c;
+            }
+        }
+        s_val[threadIdx.x] = v;
+        s_idx[threadIdx.x] = idx;
+        __syncthreads();
+        for (int off = NT / 2; off > 0; off >>= 1) {
+            if (threadIdx.x < off) {
+                const float ov = s_val[threadIdx.x + off];
+                const int oi = s_idx[threadIdx.x + off];
+                if (oi != 0x7fffffff &&
+                    (s_idx[threadIdx.x] == 0x7fffffff || score_better(ov, oi, s_val[threadIdx.x], s_idx[threadIdx.x]))) {
+                    s_val[threadIdx.x] = ov;
+                    s_idx[threadIdx.x] = oi;
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) best[b] = s_idx[0];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *status = 0;
+}
+
+}  // namespace mac
