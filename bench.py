@@ -31,8 +31,8 @@ WORKLOADS = {
 METRIC = "coverage_gain_evals_per_sec"
 UNIT = "evals/s"
 N_INPUT_SETS = 5          # distinct resident input sets rotated between steps (5 x 54.6 MB > 126 MB L2)
-FMA_CYCLES_PER_PAIR = 85.0  # FMA-pipe issue cycles per (point, camera) pair: 35 FFMA + 21 FFMA2 x 2 + 8 FADD/FMUL
-                            # (SASS of the sweep loop, profiles/r01_covgain.md); 1 per cycle per SM sub-partition
+FMA_CYCLES_PER_PAIR = 74.0  # FMA-pipe cycles per (point, camera) pair: 27 FFMA2 x 2 + 11 FFMA + 9 FADD/FMUL
+                            # (SASS of the sweep loop); 1 per cycle per SM sub-partition
 
 
 def load_peaks():

@@ -8,8 +8,9 @@
 //     TMA (two 32-row x 128-B boxes of a 3-D tensor map over (64, P, B), SWIZZLE_128B, mbarrier
 //     completion; rows past P are zero-filled by the hardware), pulled into registers with 16
 //     conflict-free LDS.128 (the swizzle un-does the 128-B row stride) and converted ONCE to 64 "Horner-ready"
-//     coefficients (sh_horner_gen.h): the SH sum becomes Re sum_m (A_m(ct) - i B_m(ct)) (uz + i ux)^m
-//     with u the unit ray, i.e. 49 + 26 FMAs per (point, camera) pair and no trigonometry.
+//     coefficients (sh_horner_gen.h): on the unit sphere the SH sum is P(ct, uz) + ux Q(ct, uz) with u the unit
+//     ray (deg P <= 7, deg Q <= 6: 64 monomial coefficients), i.e. 63 FMAs per (point, camera) pair and no
+//     trigonometry.
 //   * the warp then sweeps a chunk of cameras (broadcast LDS.128 from a per-warp table).  Per-pair
 //     values go through a padded per-warp transpose buffer so that the sum over the 32 points costs
 //     ~2 instructions per pair instead of a 10-instruction shuffle tree.
@@ -91,7 +92,7 @@ template <bool PACKED, int NG, int NG0, int NGP>
 __device__ __forceinline__ void load_coefficients(const float (&h)[64], float (&g)[NG], float (&g0)[NG0],
                                                   unsigned long long (&gp)[NGP], const float scale)
 {
-    if constexpr (PACKED) mac_sh_pretransform_packed(h, g0, gp, scale);
+    if constexpr (PACKED) mac_sh_pretransform_pq(h, g0, gp, scale);
     else mac_sh_pretransform(h, g, scale);
 }
 template <bool PACKED, int NG, int NG0, int NGP>
@@ -99,7 +100,7 @@ __device__ __forceinline__ void eval_two_rays(const float (&g)[NG], const float 
                                               const unsigned long long (&gp)[NGP], const Ray a, const Ray b, float &za,
                                               float &zb)
 {
-    if constexpr (PACKED) mac_sh_eval2_packed(g0, gp, a.ux, a.ct, a.uz, b.ux, b.ct, b.uz, za, zb);
+    if constexpr (PACKED) mac_sh_eval2_pq(g0, gp, a.ux, a.ct, a.uz, b.ux, b.ct, b.uz, za, zb);
     else mac_sh_eval2(g, a.ux, a.ct, a.uz, b.ux, b.ct, b.uz, za, zb);
 }
 
