@@ -214,6 +214,26 @@ def test_full_size_cfg5_properties(cuda_device):
     assert (full.cpu()[:, :2] - want).abs().max().item() <= COVERAGE_ATOL
 
 
+def test_full_size_cfg4_batched_clouds(cuda_device):
+    """BASELINE config 4 shape (32 clouds x 2048 proxy points x 256 cameras, 32 cameras per GPU at 8 GPUs): three of the
+    clouds against the fp32 oracle and the float64 closed form, the 8-way camera partition bitwise neutral, NBV per cloud."""
+    B, P, C = 32, 2048, 256
+    pts, harm, cams = synth.covgain_inputs(B, P, C, seed=4004)
+    d = [t.to(cuda_device) for t in (pts, harm, cams)]
+    full = ops.coverage_gain(*d)
+    assert full.shape == (B, C) and torch.isfinite(full).all()
+    for b in (0, 13, 31):
+        want = sh_cov.coverage_gain(pts[b:b + 1], harm[b:b + 1], cams[b:b + 1], cam_chunk=32)
+        assert (full[b:b + 1].cpu() - want).abs().max().item() <= COVERAGE_ATOL
+        truth = sh_cov.coverage_gain_f64(pts[b:b + 1].numpy(), harm[b:b + 1].numpy(), cams[b:b + 1, :16].numpy())
+        assert np.abs(full[b:b + 1, :16].cpu().numpy() - truth).max() <= 2e-6
+        assert int(full[b].argmax()) == int(want[0].argmax())
+    out = torch.zeros_like(full)
+    for r in range(8):
+        ops.coverage_gain(*d, cam_range=parallel.camera_partition(C, 8, r), out=out)
+    assert torch.equal(out, full)
+
+
 def test_fused_push_and_argmax_single_rank(cuda_device):
     """World size 1 of the fused gather: the kernel pushes into a local board, the wait kernel takes the argmax."""
     pts, harm, cams = synth.covgain_inputs(3, 900, 70, seed=31)

@@ -151,3 +151,35 @@ def test_single_camera_api(cuda_device):
         camera.fov_camera_0 = None
         mu.predict_coverage_gains_for_cameras(params, macarons, proxy_scene, surface_scene, *args[:3], None,
                                               cams[0].get_camera_center(), [cams[0]])
+
+
+def test_full_size_scene_properties(cuda_device):
+    """BASELINE config 3 shape (128 candidate poses over 100 k proxy points): the batched pass must agree with scoring the
+    candidates one at a time through the reference-signature function (same kernels, C = 1), gains are non-negative and
+    bounded by the proxy volume in the field of view, and an all-zero occupancy field scores zero everywhere."""
+    from macarons_b200.utility import macarons_utils as mu
+    from oracle import cameras as o_cams
+    dev = cuda_device
+    N, C, S = 100000, 128, 2048
+    s, params, cams, pred, camera, proxy_scene, surface_scene, nb, _ = macarons_case.build(N, C, 31, 17.0, S, device=dev)
+    macarons, _ = _model(dev)
+    batch_cam = o_cams.FoVPerspectiveCameras(R=s["R"], T=s["T"], zfar=1000., device=dev)
+    X_cams = batch_cam.get_camera_center()
+    u = torch.rand(C, S, generator=torch.Generator().manual_seed(5)).to(dev)
+    args = (s["X_world"].to(dev), s["vh"].to(dev), s["occ"].to(dev), camera)
+    with torch.no_grad():
+        out = mu.predict_coverage_gains_for_cameras(params, macarons, proxy_scene, surface_scene, *args, X_cams, batch_cam,
+                                                    prediction_camera=pred, samples=u)
+        cov = out["coverage_gain"].view(-1)
+        assert torch.isfinite(cov).all() and (cov >= 0).all()
+        assert (cov <= out["fov_proxy_volume"] + 1e-3).all()          # sigmoid gains and distance factors are <= 1
+        assert int((out["n_points_in_fov"] > 0).sum()) >= C // 2 and int(out["n_points_in_fov"][-1]) == 0
+        for c in (0, 37, 126):
+            one = mu.predict_coverage_gains_for_cameras(params, macarons, proxy_scene, surface_scene, *args, X_cams[c:c + 1],
+                                                        [cams[c]], prediction_camera=pred, samples=u[c:c + 1])
+            assert int(one["n_unique"][0]) == int(out["n_unique"][c])
+            assert abs(one["coverage_gain"].item() - cov[c].item()) <= 1e-4 * max(1.0, cov[c].item())
+        zero = mu.predict_coverage_gains_for_cameras(params, macarons, proxy_scene, surface_scene, args[0], args[1],
+                                                     torch.zeros_like(args[2]), camera, X_cams, batch_cam,
+                                                     prediction_camera=pred, samples=u)
+        assert float(zero["coverage_gain"].abs().max()) == 0.0
