@@ -95,7 +95,22 @@ struct LinearParams {
     int res_first;  // 1: out = act(acc + bias + res) (ResNet blocks); 0: out = act(acc + bias) + res (transformer residuals)
 };
 
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU(x) = x/2 (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, the accuracy class of
+// erff itself): erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z), z >= 0.  14 instructions with two MUFU
+// (rcp, ex2) instead of ~30 for erff: the GELU epilogues (ff1 layers, N = 256 / 512 per row) were issue-bound on it.
+__device__ __forceinline__ float gelu_exact(float x)
+{
+    const float h = 0.5f * x;
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = ex2_approx(z * z * -1.4426950408889634f);
+    const float erf_abs = fmaf(-p * t, e, 1.0f);          // erf(|x| / sqrt 2)
+    return fmaf(fabsf(h), erf_abs, h);                     // x/2 + |x|/2 erf(|x|/sqrt 2) = x/2 (1 + erf(x/sqrt 2))
+}
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float y)
@@ -185,7 +200,8 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128u : (2 * BN <= 256 ? 256u : 512u);   // power of two >= 2 BN
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -472,7 +488,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -532,6 +548,8 @@ int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo
     // (two per 256 columns re-read X from L2 but run two-deep epilogue staging and twice the CTAs).
     int bn;
     if (ln_out || pool) bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    else if (N > 128 && N <= 192 && !res) bn = 192;   // e.g. the fused q|k|v projection of the 128-wide transformers: one
+                                                      // tile per row block instead of a full and a half-empty 128-wide one
     else bn = N <= 64 ? 64 : 128;
     MAC_REQUIRE(!(ln_out || pool) || N <= bn, "row-wise epilogues need the tile to span N");
 
@@ -551,10 +569,12 @@ int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo
     if (split) {
         if (bn == 64) return launch<64, true>(mapA, mapBhi, mapBlo, p, stream);
         if (bn == 128) return launch<128, true>(mapA, mapBhi, mapBlo, p, stream);
+        if (bn == 192) return launch<192, true>(mapA, mapBhi, mapBlo, p, stream);
         return launch<256, true>(mapA, mapBhi, mapBlo, p, stream);
     }
     if (bn == 64) return launch<64, false>(mapA, mapBhi, mapBlo, p, stream);
     if (bn == 128) return launch<128, false>(mapA, mapBhi, mapBlo, p, stream);
+    if (bn == 192) return launch<192, false>(mapA, mapBhi, mapBlo, p, stream);
     return launch<256, false>(mapA, mapBhi, mapBlo, p, stream);
 }
 
