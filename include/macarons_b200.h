@@ -234,7 +234,7 @@ int mac_sconevis_forward_ragged_f32(const mac_sconevis_w_t *w, const float *pts,
  *   pc_scale[s] (B, n_scale_pts[s], 3)   the cloud kNN is taken in at scale s (full, /ds, /ds^2)
  *   x (B, Q, 3) queries, view_harmonics (B, Q, 64)  ->  out (B, Q, 1) = GELU(MLP(...)) occupancy values.
  * Queries are processed `chunk` at a time (results do not depend on it). */
-size_t mac_sconeocc_workspace_bytes(int B, int Sg, int chunk);
+size_t mac_sconeocc_workspace_bytes(int B, int Sg, int chunk, int Q);
 int mac_sconeocc_forward_f32(const mac_sconeocc_w_t *w, const float *pc_global, int Sg, const float *const *pc_scale,
                              const int *n_scale_pts, const float *x, const float *view_harmonics, float *out, int B,
                              int Q, int chunk, void *workspace, size_t workspace_bytes, void *stream);

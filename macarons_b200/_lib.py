@@ -69,7 +69,7 @@ SYMBOLS["mac_sconevis_forward_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_
 SYMBOLS["mac_sconevis_forward_ragged_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
                                                              ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                                              ctypes.c_void_p])
-SYMBOLS["mac_sconeocc_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
+SYMBOLS["mac_sconeocc_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int])
 SYMBOLS["mac_sconeocc_forward_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_void_p,
                                                       ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
                                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,

@@ -20,7 +20,19 @@ namespace mac {
 
 namespace {
 
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU with the A&S 7.1.26 erf (|error| <= 1.5e-7), see linear.cu
+__device__ __forceinline__ float gelu_exact(float x)
+{
+    const float h = 0.5f * x;
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = ex2_approx(z * z * -1.4426950408889634f);
+    return fmaf(fabsf(h), fmaf(-p * t, e, 1.0f), h);
+}
 
 // ------------------------------------------------------------------------------------------------
 // kNN: one thread per query, cloud tiled through shared memory, sorted top-16 kept in registers.
@@ -393,37 +405,49 @@ __global__ void __launch_bounds__(256) attn_dense_kernel(const float *__restrict
 
 // ------------------------------------------------------------------------------------------------
 // colpool: out_max[b, c] = max_s in[b, s, c]; out_mean[b, c] = mean_s in[b, s, c]   (either may be null)
-// block = 32 columns x 8 row lanes
+// block = 32 columns x 32 row lanes
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colpool_kernel(const float *__restrict__ in, int ld, int S_stride, int N,
-                                                      float *__restrict__ out_max, float *__restrict__ out_mean, int ldo,
-                                                      const int *__restrict__ lens)
+__global__ void __launch_bounds__(1024) colpool_kernel(const float *__restrict__ in, int ld, int S_stride, int N,
+                                                       float *__restrict__ out_max, float *__restrict__ out_mean, int ldo,
+                                                       const int *__restrict__ lens)
 {
-    __shared__ float smax[8][33], ssum[8][33];
+    constexpr int RL = 32;   // row lanes per column (the first version had 8 and one dependent load chain per lane: 73 us
+                             // for one 2048-token cloud)
+    __shared__ float smax[RL][33], ssum[RL][33];
     const int b = blockIdx.y;
     const int S = lens ? lens[b] : S_stride;   // ragged batches: only the first lens[b] rows of cloud b are tokens
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int ry = threadIdx.x >> 5;
-    float mx = -FLT_MAX, sm = 0.f;
+    float mx[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX}, sm[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < N) {
         const float *p = in + static_cast<size_t>(b) * S_stride * ld + c;
-        for (int s = ry; s < S; s += 8) {
+        int s = ry;
+        for (; s + 3 * RL < S; s += 4 * RL) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float v = p[static_cast<size_t>(s + u * RL) * ld];
+                mx[u] = fmaxf(mx[u], v);
+                sm[u] += v;
+            }
+        }
+        for (; s < S; s += RL) {
             const float v = p[static_cast<size_t>(s) * ld];
-            mx = fmaxf(mx, v);
-            sm += v;
+            mx[0] = fmaxf(mx[0], v);
+            sm[0] += v;
         }
     }
-    smax[ry][threadIdx.x & 31] = mx;
-    ssum[ry][threadIdx.x & 31] = sm;
+    smax[ry][threadIdx.x & 31] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    ssum[ry][threadIdx.x & 31] = (sm[0] + sm[1]) + (sm[2] + sm[3]);
     __syncthreads();
     if (ry == 0 && c < N) {
+        float m = smax[0][threadIdx.x], t = ssum[0][threadIdx.x];
 #pragma unroll
-        for (int r = 1; r < 8; ++r) {
-            mx = fmaxf(mx, smax[r][threadIdx.x]);
-            sm += ssum[r][threadIdx.x];
+        for (int r = 1; r < RL; ++r) {
+            m = fmaxf(m, smax[r][threadIdx.x]);
+            t += ssum[r][threadIdx.x];
         }
-        if (out_max) out_max[static_cast<size_t>(b) * ldo + c] = S > 0 ? mx : 0.f;
-        if (out_mean) out_mean[static_cast<size_t>(b) * ldo + c] = S > 0 ? sm / static_cast<float>(S) : 0.f;
+        if (out_max) out_max[static_cast<size_t>(b) * ldo + c] = S > 0 ? m : 0.f;
+        if (out_mean) out_mean[static_cast<size_t>(b) * ldo + c] = S > 0 ? t / static_cast<float>(S) : 0.f;
     }
 }
 
@@ -579,7 +603,7 @@ int colpool(const float *in, int ld, int B, int S, int N, float *out_max, float 
 {
     MAC_REQUIRE(in && (out_max || out_mean) && B > 0 && S > 0 && N > 0, "null tensor pointer");
     dim3 grid((N + 31) / 32, B);
-    colpool_kernel<<<grid, 256, 0, stream>>>(in, ld, S, N, out_max, out_mean, ldo, lens);
+    colpool_kernel<<<grid, 1024, 0, stream>>>(in, ld, S, N, out_max, out_mean, ldo, lens);
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return MAC_OK;

@@ -275,7 +275,7 @@ def sconeocc_forward(w, pc_global, pc_scales, x, view_harmonics, chunk=16384):
     counts = (ctypes.c_int * len(pc_scales))(*[p.shape[1] for p in pc_scales])
     lib = _lib.load()
     with torch.cuda.device(x.device):
-        ws = _net_workspace(x.device, lib.mac_sconeocc_workspace_bytes(B, Sg, chunk))
+        ws = _net_workspace(x.device, lib.mac_sconeocc_workspace_bytes(B, Sg, chunk, Q))
         _lib.check(lib.mac_sconeocc_forward_f32(ctypes.byref(w), pc_global.data_ptr(), Sg, ptrs, counts, x.data_ptr(),
                                                 view_harmonics.data_ptr(), out.data_ptr(), B, Q, chunk, ws.data_ptr(),
                                                 ws.numel(), _stream_ptr(x.device)))
