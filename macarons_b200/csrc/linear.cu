@@ -27,6 +27,7 @@
 //     pooled over groups of 16 consecutive rows (the 16-token neighbourhoods of SconeOcc).
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "tc_common.h"
 
@@ -551,6 +552,8 @@ int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo
     else if (N > 128 && N <= 192 && !res) bn = 192;   // e.g. the fused q|k|v projection of the 128-wide transformers: one
                                                       // tile per row block instead of a full and a half-empty 128-wide one
     else bn = N <= 64 ? 64 : 128;
+    static const int wide = [] { const char *e = getenv("MAC_LINEAR_WIDE"); return e ? atoi(e) : 0; }();   // tuning knob
+    if (wide && !(ln_out || pool) && N % 256 == 0) bn = 256;
     MAC_REQUIRE(!(ln_out || pool) || N <= bn, "row-wise epilogues need the tile to span N");
 
     CUtensorMap mapA, mapBhi, mapBlo;
