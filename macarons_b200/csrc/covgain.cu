@@ -14,10 +14,12 @@
 //   * the warp then sweeps a chunk of cameras (broadcast LDS.128 from a per-warp table).  Per-pair
 //     values go through a padded per-warp transpose buffer so that the sum over the 32 points costs
 //     ~2 instructions per pair instead of a 10-instruction shuffle tree.
-//   * per-task partial sums are accumulated as exact fixed-point int64 with one atomic per
-//     (task, camera); integer addition is associative, so the result is bitwise independent of
-//     scheduling, launch geometry and of how cameras are partitioned across GPUs.  The last CTA to
-//     finish converts the accumulators to the fp32 mean and re-zeroes the workspace.
+//   * the 32-point sum of every (tile, camera) is converted to exact fixed point and all further additions
+//     (per-warp accumulators in shared memory, one 64-bit atomic per camera when a warp changes camera chunk)
+//     are integer additions: associative, so the result is bitwise independent of scheduling, launch geometry
+//     and of how cameras are partitioned across GPUs.  Warps are persistent and pull (camera chunk, tile)
+//     tasks from a global counter.  The last CTA to finish converts the accumulators to the fp32 mean and
+//     re-zeroes the workspace.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -40,7 +42,7 @@ constexpr float kFixRelu = 16777216.0f;       // 2^24: sums of relu values (unbo
 struct __align__(1024) WarpSmem {
     float stage[2 * kBoxBytes / 4];  // TMA landing zone (coefficients 0-31 | 32-63); re-used as the 32x36 transpose buffer
     float4 cams[kCamChunkMax + 2];  // +2: the pipelined sweep normalises one pair ahead
-    float wacc[kCamChunkMax];
+    long long wacc[kCamChunkMax];   // per-camera sums of this warp, exact fixed point (2^-32 or 2^-24 units)
     uint64_t bar;
 };
 static_assert(sizeof(WarpSmem) % 1024 == 0, "SWIZZLE_128B boxes need 1024-B aligned shared memory");
@@ -54,6 +56,7 @@ struct CovgainParams {
     unsigned long long *acc;   // (B*C) fixed-point accumulators   [REDUCE only]
     unsigned int *flags;       // (B*C) non-finite markers         [REDUCE only]
     unsigned int *done;        // CTA completion ticket            [REDUCE only]
+    unsigned int *next_task;   // dynamic task counter (tasks beyond the first one of every warp)
     int pts_dim;
     int B, P, C;
     int cam_begin, cam_end;
@@ -118,8 +121,12 @@ __device__ __forceinline__ float activation_finish(const float e)
 }
 
 // Sum over the 32 points of a tile for the 32 cameras of one batch: lane j adds up row j of the transpose
-// buffer (8 conflict-free LDS.128) and accumulates into the per-warp, per-camera partial sum.
-__device__ __forceinline__ void reduce_batch(const float *red, float *wacc, const int cb, const int lane)
+// buffer (8 conflict-free LDS.128), converts the 32-point sum to fixed point and adds it to the per-warp,
+// per-camera integer accumulator.  The float sum covers exactly one tile in a fixed order and every later addition
+// is an integer addition, so the result does not depend on which warp processes which tile, on the launch geometry
+// or on the camera partition.  Returns a non-zero mask if the sum is not finite (the camera's score becomes NaN).
+template <bool SIGMOID>
+__device__ __forceinline__ unsigned reduce_batch(const float *red, long long *wacc, const int cb, const int lane)
 {
     __syncwarp();
     const float4 *r4 = reinterpret_cast<const float4 *>(&red[lane * kRedStride]);
@@ -129,8 +136,10 @@ __device__ __forceinline__ void reduce_batch(const float *red, float *wacc, cons
         const float4 v = r4[q];
         s += (v.x + v.y) + (v.z + v.w);
     }
-    wacc[cb + lane] += s;  // lane j owns camera cb + j
+    const bool ok = fabsf(s) < 1.0e12f;
+    if (ok) wacc[cb + lane] += __float2ll_rn(s * (SIGMOID ? kFixSigmoid : kFixRelu));  // lane j owns camera cb + j
     __syncwarp();
+    return ok ? 0u : (1u << (cb >> 5));
 }
 
 // WARPS x MINB = resident warps per SM (register budget 65536 / (32 * WARPS * MINB)); PACKED selects the
@@ -150,29 +159,50 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
     }
     __syncwarp();
 
-    const int task = blockIdx.x * WARPS + warp;
-    if (task < prm.total_tasks) {
-        // task -> (cloud, run of point tiles, camera chunk); camera chunk fastest so that the warps of
-        // one CTA share their coefficient rows through L1/L2.
-        const int cc = task % prm.n_cam_chunks;
-        const int rest = task / prm.n_cam_chunks;
+    // Persistent warps: the first task of a warp is static, further ones come from a global counter.  Tasks are ordered
+    // (camera chunk, cloud, run of tiles), so consecutive tasks of a warp almost always share the camera chunk: the camera
+    // table is staged and the per-camera accumulators are flushed (one 64-bit atomic per camera) only when it changes.
+    int task = blockIdx.x * WARPS + warp;
+    int key = -1, b = 0, cam0 = 0, ncam = 0, ncam32 = 0;
+    unsigned bad = 0;
+    uint32_t parity = 0;
+    auto flush = [&]() {
+        if (!REDUCE || key < 0) return;
+        __syncwarp();
+        for (int j = lane; j < ncam; j += 32) {
+            const size_t idx = static_cast<size_t>(b) * prm.C + cam0 + j;
+            const long long q = ws.wacc[j];
+            if (q != 0) atomicAdd(prm.acc + idx, static_cast<unsigned long long>(q));
+            if (bad & (1u << (j >> 5))) atomicOr(prm.flags + idx, 1u);  // NaN / inf / overflow -> result is NaN
+        }
+        bad = 0;
+    };
+    const int tasks_per_chunk = prm.B * prm.runs_per_cloud;
+    while (task < prm.total_tasks) {
+        const int cc = task / tasks_per_chunk;
+        const int rest = task - cc * tasks_per_chunk;
         const int run = rest % prm.runs_per_cloud;
-        const int b = rest / prm.runs_per_cloud;
-        const int cam0 = prm.cam_begin + cc * prm.cams_per_task;
-        const int ncam = min(prm.cams_per_task, prm.cam_end - cam0);
-        const int ncam32 = (ncam + 31) & ~31;
-
-        for (int j = lane; j < ncam32 + 2; j += 32) {
-            float4 c = make_float4(0.f, 0.f, 1048576.f, 0.f);  // padding camera: finite, result discarded
-            if (j < ncam) {
-                const float *src = prm.cams + (static_cast<size_t>(b) * prm.C + cam0 + j) * 3;
-                c = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), 0.f);
+        const int tb = rest / prm.runs_per_cloud;
+        if (tb * prm.n_cam_chunks + cc != key) {
+            flush();
+            key = tb * prm.n_cam_chunks + cc;
+            b = tb;
+            cam0 = prm.cam_begin + cc * prm.cams_per_task;
+            ncam = min(prm.cams_per_task, prm.cam_end - cam0);
+            ncam32 = (ncam + 31) & ~31;
+            __syncwarp();
+            for (int j = lane; j < ncam32 + 2; j += 32) {
+                float4 c = make_float4(0.f, 0.f, 1048576.f, 0.f);  // padding camera: finite, result discarded
+                if (j < ncam) {
+                    const float *src = prm.cams + (static_cast<size_t>(b) * prm.C + cam0 + j) * 3;
+                    c = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), 0.f);
+                }
+                ws.cams[j] = c;
+                if (j < ncam32) ws.wacc[j] = 0;
             }
-            ws.cams[j] = c;
-            if (j < ncam32) ws.wacc[j] = 0.f;
+            __syncwarp();
         }
 
-        uint32_t parity = 0;
         const int tile_end = min(prm.tiles_per_cloud, (run + 1) * prm.tiles_per_task);
         for (int tile = run * prm.tiles_per_task; tile < tile_end; ++tile) {
             const int p = tile * 32 + lane;
@@ -253,7 +283,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
                 eB = activation_start<SIGMOID>(zB);
                 rA = qA;
                 rB = qB;
-                if (REDUCE && (jj & 15) == 0 && jj > 0) reduce_batch(red, ws.wacc, c & ~31, lane);
+                if (REDUCE && (jj & 15) == 0 && jj > 0) bad |= reduce_batch<SIGMOID>(red, ws.wacc, c & ~31, lane);
             }
             {
                 const float vA = activation_finish<SIGMOID>(eA), vB = activation_finish<SIGMOID>(eB);
@@ -263,7 +293,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
                         red[(c & 31) * kRedStride + lane] = vA;
                         red[((c & 31) + 1) * kRedStride + lane] = vB;
                     }
-                    reduce_batch(red, ws.wacc, c & ~31, lane);
+                    bad |= reduce_batch<SIGMOID>(red, ws.wacc, c & ~31, lane);
                 } else if (valid) {
                     float *o = prm.out + (static_cast<size_t>(b) * prm.C + cam0 + c) * prm.P + p;
                     if (c < ncam) o[0] = vA;
@@ -272,19 +302,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
             }
         }
 
+        // next task of this warp: dynamic for the reducing kernel (the workspace holds the counter), strided otherwise
         if (REDUCE) {
-            for (int j = lane; j < ncam; j += 32) {
-                const float s = ws.wacc[j];
-                const size_t idx = static_cast<size_t>(b) * prm.C + cam0 + j;
-                if (fabsf(s) < 1.0e12f) {
-                    const long long q = __float2ll_rn(s * (SIGMOID ? kFixSigmoid : kFixRelu));
-                    atomicAdd(prm.acc + idx, static_cast<unsigned long long>(q));
-                } else {
-                    atomicOr(prm.flags + idx, 1u);  // NaN / inf / overflow -> result is NaN
-                }
-            }
+            int nt = 0;
+            if (lane == 0) nt = static_cast<int>(atomicAdd(prm.next_task, 1u)) + static_cast<int>(gridDim.x) * WARPS;
+            task = __shfl_sync(0xffffffffu, nt, 0);
+        } else {
+            task += static_cast<int>(gridDim.x) * WARPS;
         }
     }
+    flush();
 
     if (REDUCE) {
         // ---- last CTA: fixed-point accumulators -> fp32 mean; leave the workspace zeroed ----
@@ -296,7 +323,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
         }
         __syncthreads();
         if (is_last && !prm.finalize) {
-            if (threadIdx.x == 0) *prm.done = 0u;   // partial sums stay in the workspace for the next point slice
+            if (threadIdx.x == 0) *prm.done = 0u, *prm.next_task = 0u;   // partial sums stay in the workspace for the next point slice
         } else if (is_last) {
             __threadfence();
             const int nloc = prm.cam_end - prm.cam_begin;
@@ -316,7 +343,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
                 if (threadIdx.x < prm.push_world)  // ... before the arrival flag of this rank is
                     st_release_sys(prm.push_flag[threadIdx.x] + prm.push_rank, prm.push_epoch);
             }
-            if (threadIdx.x == 0) *prm.done = 0u;
+            if (threadIdx.x == 0) *prm.done = 0u, *prm.next_task = 0u;
             if (prm.push_world > 0 && prm.best) {
                 __syncthreads();
                 wait_scores_and_argmax<WARPS * 32>(prm.push_dst[prm.push_rank], prm.push_flag[prm.push_rank], prm.push_world,
@@ -419,6 +446,7 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
         prm.flags = reinterpret_cast<unsigned int *>(w);
         w += align_up(static_cast<size_t>(B) * C * sizeof(unsigned int), 16);
         prm.done = reinterpret_cast<unsigned int *>(w);
+        prm.next_task = prm.done + 1;
     }
 
     CUtensorMap harm_map;
@@ -454,9 +482,10 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
     if (force_cpt == 32 || force_cpt == 64 || force_cpt == 96 || force_cpt == 128) cpt = force_cpt;
     prm.cams_per_task = cpt;
     prm.n_cam_chunks = (n_local + cpt - 1) / cpt;
-    // Several point tiles per task only when there are far more tasks than warp slots (fewer atomics).
+    // One point tile per task: the warps are persistent and pull tasks dynamically, so small tasks only cost one
+    // counter atomic each and keep the tail short (several tiles per task only for enormous launches).
     const long long base_tasks = static_cast<long long>(B) * prm.tiles_per_cloud * prm.n_cam_chunks;
-    long long tpt = base_tasks / (24 * slots);
+    long long tpt = base_tasks / (256 * slots);
     if (tpt < 1) tpt = 1;
     if (tpt > 64) tpt = 64;
     if (force_tpt > 0) tpt = force_tpt;
@@ -466,7 +495,9 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
     MAC_REQUIRE(total < (1ll << 31) - 64, "problem too large for one launch (%lld tasks)", total);
     prm.total_tasks = static_cast<int>(total);
 
-    const dim3 grid(static_cast<unsigned>(total > 0 ? (total + warps_per_cta - 1) / warps_per_cta : 1));
+    long long n_ctas = total > 0 ? (total + warps_per_cta - 1) / warps_per_cta : 1;
+    if (n_ctas > slots / warps_per_cta) n_ctas = slots / warps_per_cta;   // persistent: one resident wave
+    const dim3 grid(static_cast<unsigned>(n_ctas));
     const size_t smem = sizeof(WarpSmem) * warps_per_cta;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
