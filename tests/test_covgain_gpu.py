@@ -214,6 +214,27 @@ def test_full_size_cfg5_properties(cuda_device):
     assert (full.cpu()[:, :2] - want).abs().max().item() <= COVERAGE_ATOL
 
 
+def test_non_finite_inputs_give_nan_scores(cuda_device):
+    """A NaN / inf coefficient row or point makes every score of its cloud NaN (the reference's mean over the points
+    propagates it), a NaN camera only its own score; the other clouds and the next call are unaffected."""
+    pts, harm, cams = synth.covgain_inputs(3, 500, 40, seed=77)
+    clean = ops.coverage_gain(pts.to(cuda_device), harm.to(cuda_device), cams.to(cuda_device))
+    h2 = harm.clone()
+    h2[1, 123, 7] = float("nan")
+    p2 = pts.clone()
+    p2[2, 499, 1] = float("inf")
+    got = ops.coverage_gain(p2.to(cuda_device), h2.to(cuda_device), cams.to(cuda_device))
+    assert torch.equal(got[0], clean[0]) and torch.isnan(got[1]).all() and torch.isnan(got[2]).all()
+    c2 = cams.clone()
+    c2[0, 5, 2] = float("nan")
+    got = ops.coverage_gain(pts.to(cuda_device), harm.to(cuda_device), c2.to(cuda_device))
+    assert torch.isnan(got[0, 5]) and torch.equal(got[1:], clean[1:])
+    keep = torch.ones(40, dtype=torch.bool)
+    keep[5] = False
+    assert torch.equal(got[0, keep], clean[0, keep])
+    assert torch.equal(ops.coverage_gain(pts.to(cuda_device), harm.to(cuda_device), cams.to(cuda_device)), clean)
+
+
 def test_full_size_cfg4_batched_clouds(cuda_device):
     """BASELINE config 4 shape (32 clouds x 2048 proxy points x 256 cameras, 32 cameras per GPU at 8 GPUs): three of the
     clouds against the fp32 oracle and the float64 closed form, the 8-way camera partition bitwise neutral, NBV per cloud."""
