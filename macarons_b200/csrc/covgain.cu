@@ -472,7 +472,7 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
     int cpt = kCamChunkMax;
     while (cpt > 32) {
         const long long tasks = static_cast<long long>(B) * prm.tiles_per_cloud * ((n_local + cpt - 1) / cpt);
-        if (cpt / 2 >= n_local || tasks < 6 * slots) cpt /= 2;
+        if (cpt / 2 >= n_local || tasks < 2 * slots) cpt /= 2;   // dynamic scheduling balances ~2.5 tasks per warp well
         else break;
     }
     while (cpt > 32 && cpt / 2 >= n_local) cpt /= 2;
