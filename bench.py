@@ -306,7 +306,7 @@ def run_ours(args, cfg):
         elapsed_ms, kernel_ms = t.tolist()
 
     # ---- end to end through the public API: pinned host inputs -> device, score, gather, argmax -> host ----
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 30))
     h2d = sum(t.numel() * 4 for t in pinned[0]) + cams_pin.numel() * 4
     d2h = B * C * 4 + B * 8
 
@@ -342,10 +342,14 @@ def run_ours(args, cfg):
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
+    e2e_each = []
     for i in range(e2e_steps):
+        t_i = time.perf_counter()
         s_host, b_host = e2e_step(i)
+        e2e_each.append(1e3 * (time.perf_counter() - t_i))
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
+    e2e_median_ms = statistics.median(e2e_each)   # reported next to the mean: single steps occasionally take +0.4 ms (host jitter)
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -391,6 +395,7 @@ def run_ours(args, cfg):
             "clocks": clocks,
             "e2e": {"value": B * C * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "ms_per_step_median": e2e_median_ms,
                     "api": ("mac_covgain_host (C ABI, pinned HOST buffers in, host scores out; 8 H2D slices overlapped with the "
                             "kernel) + argmax on the host") if world == 1 else
                            "pinned host tensors -> each rank uploads 1/N of the point rows + NCCL all-gather over NVLink "

@@ -28,3 +28,17 @@ print("kernel (device resident)  %.3f ms" % wall(lambda: ops.coverage_gain(dp, d
 pn, hn, cn = pp.numpy(), hp.numpy(), cams.numpy()
 print("mac_covgain_host pinned   %.3f ms" % wall(lambda: ops.coverage_gain_host(pn, hn, cn, device=0)))
 print("mac_covgain_host pageable %.3f ms" % wall(lambda: ops.coverage_gain_host(pts.numpy(), harm.numpy(), cn, device=0), 5))
+
+# two pinned input sets used alternately (what bench.py does)
+pts2, harm2, _ = synth.covgain_inputs(1, 200704, 1, seed=2)
+pp2, hp2 = pts2.pin_memory(), harm2.pin_memory()
+sets = [(pn, hn), (pp2.numpy(), hp2.numpy())]
+state = {"i": 0}
+def alt():
+    p, h = sets[state["i"] & 1]
+    state["i"] += 1
+    s = torch.from_numpy(ops.coverage_gain_host(p, h, cn, device=0))
+    return s, torch.argmax(s, dim=-1)
+print("alternating 2 pinned sets %.3f ms" % wall(alt))
+big = [torch.empty(1, 200704, 64, device=dev) for _ in range(5)]   # bench.py keeps 5 resident input sets
+print("with 5 resident sets      %.3f ms" % wall(alt))
