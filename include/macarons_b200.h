@@ -156,6 +156,14 @@ int mac_covgain_push_argmax_f32(const float *pts, int pts_dim, const float *harm
 int mac_linear_f32(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias,
                    float *out, int ldo, int M, int N, int K, int act, const float *res, int ldr, float *ln_out,
                    int ldl, const float *ln_g, const float *ln_b, float ln_eps, int pool, void *stream);
+/* mac_linear_f32 with the LayerNorm of the INPUT rows applied on load -- lnin_stats (M, 2) = (mean, rstd) per row,
+ * lnin_g / lnin_b (K <= 512), split weights required -- and / or the (mean, rstd) of every OUTPUT row written to
+ * stats_out (M, 2) with ln_eps (N <= 256): consecutive layers of /root/reference/macarons/networks/Attention.py:281-298
+ * (norm1 -> attention -> residual -> norm2 -> feed-forward) pass 8 bytes per row instead of a normalised copy. */
+int mac_linear_lnio_f32(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias, float *out,
+                        int ldo, int M, int N, int K, int act, const float *res, int ldr, const float *lnin_stats,
+                        const float *lnin_g, const float *lnin_b, float *stats_out, float ln_eps, void *stream);
+
 
 /* ---------------------------------------------------------------------------------------------
  * k nearest neighbours (k = 16)  --  replaces get_knn_points, /root/reference/macarons/utility/utils.py:1497-1509

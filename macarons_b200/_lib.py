@@ -61,6 +61,12 @@ SYMBOLS["mac_linear_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p
                                             _c_float_p, _c_float_p, ctypes.c_float, ctypes.c_int, ctypes.c_void_p])
 
 
+SYMBOLS["mac_linear_lnio_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_int, _c_float_p,
+                                                 _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p,
+                                                 _c_float_p, ctypes.c_float, ctypes.c_void_p])
+
+
 SYMBOLS["mac_knn16_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_void_p])
 SYMBOLS["mac_sconevis_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int])

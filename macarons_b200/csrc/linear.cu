@@ -94,6 +94,10 @@ struct LinearParams {
     int act;
     int pool;       // 0, or 16: max | mean over groups of 16 rows -> out (M/16, 2N)
     int res_first;  // 1: out = act(acc + bias + res) (ResNet blocks); 0: out = act(acc + bias) + res (transformer residuals)
+    // LayerNorm applied to X on load (by the split warps): x' = (x - mean[row]) * rstd[row] * g[col] + b[col]
+    const float *lnin_stats;   // (M, 2) = (mean, rstd) per row, or null
+    const float *lnin_g, *lnin_b;   // (K)
+    float *stats_out;          // (M, 2): (mean, rstd) of every output row (for the LayerNorm-on-load of the next layer)
 };
 
 // GELU(x) = x/2 (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, the accuracy class of
@@ -135,7 +139,9 @@ struct Cfg {
     static constexpr int kEpiBufs = (BN <= 128) ? 2 : 1;
     static constexpr int kWSlots = 2;
     static constexpr int kLoSlots = SPLIT ? 2 : 0;
-    static constexpr int kVecBytes = 3 * BN * 4 + 2 * 128 * 4;  // bias | gamma | beta of the tile's columns, LayerNorm partials
+    static constexpr int kLnInMaxK = 512;
+    static constexpr int kVecBytes = 3 * BN * 4 + 2 * 128 * 4 +   // bias | gamma | beta of the tile's columns, LayerNorm partials
+                                     (SPLIT ? 2 * kLnInMaxK * 4 : 0);   // gamma | beta (K) of the LayerNorm applied on load
     static constexpr int kThreads = kBaseThreads + 128 * ((BN <= 128) ? 2 : 1);
     static constexpr int kBudget = 226 * 1024 - 1024 - 512 - kVecBytes - kEpiBufs * kEpiBufBytes - kWSlots * kWSlotBytes - kLoSlots * kATileBytes;
     static constexpr int kRawSlots = (kBudget / kATileBytes) < kMaxStages ? (kBudget / kATileBytes) : kMaxStages;
@@ -281,8 +287,31 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         // ===== X split: x -> (tf32(x), tf32(x - tf32(x))), element-wise in shared memory =====
         if (SPLIT) {
             const int t = threadIdx.x - 128;  // 0..127
+            // LayerNorm on load: thread t always owns the same 4 logical columns of a k-chunk (16-byte piece t & 7 of a
+            // 128-byte row, un-swizzled with the row's low bits, which are those of t >> 3) and rows (t >> 3) + 16 i.
+            const bool lnin = p.lnin_stats != nullptr;
+            float *kvec = svec + 3 * BN + 2 * 128;   // [2][kLnInMaxK]: gamma | beta over K
+            const int col4 = (((t & 7) ^ ((t >> 3) & 7)) << 2);
+            if (lnin) {
+                for (int c = t; c < C::kLnInMaxK; c += 128) {
+                    kvec[c] = c < p.K ? p.lnin_g[c] : 0.f;
+                    kvec[C::kLnInMaxK + c] = c < p.K ? p.lnin_b[c] : 0.f;
+                }
+                named_bar_sync(8, 128);   // the 4 split warps only (ids 1-3 belong to the epilogue groups)
+            }
             int kt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                float mean[8], rstd[8];
+                if (lnin) {
+                    const int m0 = (tile / p.n_tiles_n) * kBM;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = m0 + (t >> 3) + 16 * i;
+                        float2 st = make_float2(0.f, 0.f);
+                        if (row < p.M) st = __ldg(reinterpret_cast<const float2 *>(p.lnin_stats) + row);
+                        mean[i] = st.x, rstd[i] = st.y;
+                    }
+                }
                 for (int kc = 0; kc < nk; ++kc, ++kt) {
                     const int sx = kt % C::kRawSlots, s2 = kt & 1;
                     const uint32_t phx = (kt / C::kRawSlots) & 1, ph2 = (kt >> 1) & 1;
@@ -290,9 +319,20 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     mbar_wait(&empty_lo[s2], ph2 ^ 1);
                     float4 *hi = reinterpret_cast<float4 *>(a_hi(sx));
                     float4 *lo = reinterpret_cast<float4 *>(a_lo(s2));
+                    float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lnin) {
+                        g4 = *reinterpret_cast<const float4 *>(kvec + kc * kBK + col4);
+                        b4 = *reinterpret_cast<const float4 *>(kvec + C::kLnInMaxK + kc * kBK + col4);
+                    }
 #pragma unroll
                     for (int i = 0; i < kATileBytes / 16 / 128; ++i) {
-                        const float4 v = hi[t + i * 128];
+                        float4 v = hi[t + i * 128];
+                        if (lnin) {
+                            v.x = fmaf((v.x - mean[i]) * rstd[i], g4.x, b4.x);
+                            v.y = fmaf((v.y - mean[i]) * rstd[i], g4.y, b4.y);
+                            v.z = fmaf((v.z - mean[i]) * rstd[i], g4.z, b4.z);
+                            v.w = fmaf((v.w - mean[i]) * rstd[i], g4.w, b4.w);
+                        }
                         float4 h, l;
                         h.x = tf32_hi(v.x), h.y = tf32_hi(v.y), h.z = tf32_hi(v.z), h.w = tf32_hi(v.w);
                         l.x = tf32_lo(v.x, h.x), l.y = tf32_lo(v.y, h.y), l.z = tf32_lo(v.z, h.z), l.w = tf32_lo(v.w, h.w);
@@ -431,13 +471,13 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         sum += (y4.x + y4.y) + (y4.z + y4.w);
                         *reinterpret_cast<float4 *>(mine + j) = y4;
                     }
-                    if (p.ln_out) tmem_st32(taddr + c * 32, v);  // keep y for the LayerNorm passes
+                    if (p.ln_out || p.stats_out) tmem_st32(taddr + c * 32, v);  // keep y for the LayerNorm passes
                     named_bar_sync(gbar, 128);                   // the 128 x 32 chunk of y is staged
                     if (p.out) store_chunk(c, p.out, p.ldo);
                     named_bar_sync(gbar, 128);                   // staging buffer drained
                     if (has_res && c + G < nch) fetch_res(c + G);
                 }
-                if (p.ln_out) {
+                if (p.ln_out || p.stats_out) {
                     // LayerNorm over the N columns of this row (the tile spans all of N): mean, then centred variance;
                     // the groups hold disjoint column chunks and combine their partial sums through shared memory
                     if (G > 1) {
@@ -462,7 +502,9 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         var = red[rl] + red[128 + rl];
                     }
                     const float rstd = 1.0f / sqrtf(var / static_cast<float>(p.N) + p.ln_eps);
-                    for (int c = g; c < nch; c += G) {
+                    if (p.stats_out && g == 0 && row_ok)   // the next layer normalises on load: 8 bytes instead of a row
+                        *reinterpret_cast<float2 *>(p.stats_out + 2 * static_cast<size_t>(row)) = make_float2(mean, rstd);
+                    for (int c = g; p.ln_out && c < nch; c += G) {
                         tmem_ld32(taddr + c * 32, v);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -530,9 +572,15 @@ int launch(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap
 
 int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias, float *out,
                    int ldo, int M, int N, int K, int act, const float *res, int ldr, float *ln_out, int ldl,
-                   const float *ln_g, const float *ln_b, float ln_eps, int pool, cudaStream_t stream, int res_first)
+                   const float *ln_g, const float *ln_b, float ln_eps, int pool, cudaStream_t stream, int res_first,
+                   const float *lnin_stats, const float *lnin_g, const float *lnin_b, float *stats_out)
 {
     MAC_REQUIRE(X && W_hi && (out || ln_out), "null tensor pointer");
+    MAC_REQUIRE(!lnin_stats || (W_lo && lnin_g && lnin_b && K <= 512 && K % 4 == 0 &&
+                                (reinterpret_cast<uintptr_t>(lnin_stats) & 7u) == 0),
+                "LayerNorm on load needs split weights, gamma / beta and K <= 512");
+    MAC_REQUIRE(!stats_out || (N <= 256 && !pool && (reinterpret_cast<uintptr_t>(stats_out) & 7u) == 0),
+                "row statistics need N <= 256 and no pooling");
     MAC_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive (got %d, %d, %d)", M, N, K);
     MAC_REQUIRE(act >= MAC_LIN_NONE && act <= MAC_LIN_SIGMOID, "bad activation %d", act);
     MAC_REQUIRE(pool == 0 || pool == 16, "pool must be 0 or 16");
@@ -548,13 +596,13 @@ int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo
     // 256-wide tiles only where a row-wise epilogue (LayerNorm) must see all of N; otherwise 128-wide tiles
     // (two per 256 columns re-read X from L2 but run two-deep epilogue staging and twice the CTAs).
     int bn;
-    if (ln_out || pool) bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-    else if (N > 128 && N <= 192 && !res) bn = 192;   // e.g. the fused q|k|v projection of the 128-wide transformers: one
+    if (ln_out || pool || stats_out) bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    else if (N > 128 && N <= 192 && !res && !stats_out) bn = 192;   // e.g. the fused q|k|v projection of the 128-wide transformers: one
                                                       // tile per row block instead of a full and a half-empty 128-wide one
     else bn = N <= 64 ? 64 : 128;
     static const int wide = [] { const char *e = getenv("MAC_LINEAR_WIDE"); return e ? atoi(e) : 0; }();   // tuning knob
-    if (wide && !(ln_out || pool) && N % 256 == 0) bn = 256;
-    MAC_REQUIRE(!(ln_out || pool) || N <= bn, "row-wise epilogues need the tile to span N");
+    if (wide && !(ln_out || pool || stats_out) && N % 256 == 0) bn = 256;
+    MAC_REQUIRE(!(ln_out || pool || stats_out) || N <= bn, "row-wise epilogues need the tile to span N");
 
     CUtensorMap mapA, mapBhi, mapBlo;
     if (int rc = make_tensor_map_2d(&mapA, X, M, K, ldx, kBM)) return rc;
@@ -568,6 +616,8 @@ int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo
     p.res = res, p.ldr = ldr;
     p.ln_out = ln_out, p.ldl = ldl, p.ln_g = ln_g, p.ln_b = ln_b, p.ln_eps = ln_eps;
     p.act = act, p.pool = pool, p.res_first = res_first;
+    p.lnin_stats = lnin_stats, p.lnin_g = lnin_g, p.lnin_b = lnin_b, p.stats_out = stats_out;
+    if (stats_out && !ln_out) p.ln_eps = ln_eps;
 
     if (split) {
         if (bn == 64) return launch<64, true>(mapA, mapBhi, mapBlo, p, stream);
@@ -590,4 +640,16 @@ extern "C" int mac_linear_f32(const float *X, int ldx, const float *W_hi, const 
 {
     return mac::linear_forward(X, ldx, W_hi, W_lo, ldw, bias, out, ldo, M, N, K, act, res, ldr, ln_out, ldl, ln_g, ln_b,
                                ln_eps, pool, static_cast<cudaStream_t>(stream));
+}
+
+// mac_linear_f32 with the LayerNorm of the INPUT rows applied on load (lnin_stats (M, 2) = (mean, rstd) per row,
+// lnin_g / lnin_b (K)) and / or the (mean, rstd) of every OUTPUT row written to stats_out (M, 2) with ln_eps: a chain of
+// layers then passes 8 bytes per row instead of a normalised copy of the activations.
+extern "C" int mac_linear_lnio_f32(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias,
+                                   float *out, int ldo, int M, int N, int K, int act, const float *res, int ldr,
+                                   const float *lnin_stats, const float *lnin_g, const float *lnin_b, float *stats_out,
+                                   float ln_eps, void *stream)
+{
+    return mac::linear_forward(X, ldx, W_hi, W_lo, ldw, bias, out, ldo, M, N, K, act, res, ldr, nullptr, 0, nullptr, nullptr,
+                               ln_eps, 0, static_cast<cudaStream_t>(stream), 0, lnin_stats, lnin_g, lnin_b, stats_out);
 }

@@ -167,5 +167,7 @@ namespace mac {
 // linear.cu: see mac_linear_f32 in include/macarons_b200.h
 int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias, float *out,
                    int ldo, int M, int N, int K, int act, const float *res, int ldr, float *ln_out, int ldl,
-                   const float *ln_g, const float *ln_b, float ln_eps, int pool, cudaStream_t stream, int res_first = 0);
+                   const float *ln_g, const float *ln_b, float ln_eps, int pool, cudaStream_t stream, int res_first = 0,
+                   const float *lnin_stats = nullptr, const float *lnin_g = nullptr, const float *lnin_b = nullptr,
+                   float *stats_out = nullptr);
 }  // namespace mac

@@ -192,6 +192,24 @@ def linear(x, packed, act=ACT_NONE, residual=None, out=None, ln=None, pool=0, K=
     return (out, ln_out) if ln is not None else out
 
 
+def linear_lnio(x, packed, act=ACT_NONE, residual=None, ln_in=None, stats_out=False, eps=1e-5):
+    """mac_linear_lnio_f32: `ln_in=(stats (M,2), gamma (K), beta (K))` normalises the rows of x on load;
+    `stats_out=True` also returns the (mean, rstd) (M,2) of the output rows."""
+    _require_cuda_f32("x", x)
+    M, K, N = x.shape[0], packed.K, packed.N
+    dev = x.device
+    out = torch.empty((M, (N + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :N]
+    stats = torch.empty((M, 2), dtype=torch.float32, device=dev) if stats_out else None
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.mac_linear_lnio_f32(
+            x.data_ptr(), x.stride(0), packed.hi.data_ptr(), _ptr(packed.lo), packed.ldw, _ptr(packed.bias), out.data_ptr(),
+            out.stride(0), M, N, K, int(act), _ptr(residual), 0 if residual is None else residual.stride(0),
+            0 if ln_in is None else ln_in[0].data_ptr(), 0 if ln_in is None else ln_in[1].data_ptr(),
+            0 if ln_in is None else ln_in[2].data_ptr(), _ptr(stats), float(eps), _stream_ptr(dev)))
+    return (out, stats) if stats_out else out
+
+
 # ---- kNN and the fused network forwards (csrc/pointnet.cu, csrc/scone_nets.cu) --------------------
 _net_workspaces = {}
 

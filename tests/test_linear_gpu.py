@@ -105,3 +105,29 @@ def test_output_into_column_slice(cuda_device):
     ops.linear(xbuf.to(cuda_device), pk, out=wide[:, 256:384])
     assert (wide[:, 256:384].cpu().double() - ref).abs().max().item() <= 4e-6 * _scale(ref) * 8
     assert torch.all(wide[:, :256] == -7.0) and torch.all(wide[:, 384:] == -7.0)
+
+
+@pytest.mark.parametrize("M,N,K", [(515, 128, 128), (300, 256, 256), (2048, 192, 128), (130, 64, 512)])
+def test_layernorm_on_load_and_row_statistics(M, N, K, cuda_device):
+    """Two chained layers that pass (mean, rstd) instead of a normalised copy == LayerNorm + Linear in float64."""
+    xbuf, w1, b1 = _case(M, K, K, seed=M + N)
+    _, w2, b2 = _case(M, N, K, seed=M + N + 1)
+    gen = torch.Generator().manual_seed(9)
+    g, beta = 1 + 0.1 * torch.randn(K, generator=gen), 0.1 * torch.randn(K, generator=gen)
+    res = torch.randn(M, K, generator=gen)
+    y1 = res.double() + xbuf.double() @ w1.double().t() + b1.double()
+    ln = F.layer_norm(y1, (K,), g.double(), beta.double(), 1e-5)
+    ref = F.gelu(ln @ w2.double().t() + b2.double())
+    pk1 = packing.PackedLinear(w1.to(cuda_device), b1.to(cuda_device))
+    pk2 = packing.PackedLinear(w2.to(cuda_device), b2.to(cuda_device))
+    if K <= 256:
+        got1, stats = ops.linear_lnio(xbuf.to(cuda_device), pk1, residual=res.to(cuda_device), stats_out=True)
+        assert (got1.cpu().double() - y1).abs().max().item() <= 4e-6 * _scale(y1) * (K ** 0.5)
+        mean, rstd = y1.mean(-1), 1.0 / torch.sqrt(y1.var(-1, unbiased=False) + 1e-5)
+        assert (stats[:, 0].cpu().double() - mean).abs().max().item() <= 1e-5 * _scale(y1)
+        assert ((stats[:, 1].cpu().double() - rstd) / rstd).abs().max().item() <= 1e-5
+    else:   # row statistics need N <= 256: take them from the float64 reference
+        got1 = y1.float().to(cuda_device)
+        stats = torch.stack((y1.mean(-1), 1.0 / torch.sqrt(y1.var(-1, unbiased=False) + 1e-5)), dim=-1).float().to(cuda_device)
+    got = ops.linear_lnio(got1, pk2, act=ops.ACT_GELU, ln_in=(stats, g.to(cuda_device), beta.to(cuda_device)))
+    assert (got.cpu().double() - ref).abs().max().item() <= 2e-5 * max(1.0, _scale(ref)) * (K ** 0.5) / 8
