@@ -26,17 +26,24 @@ struct Bump {  // carve the caller's workspace
     }
 };
 
+// `lnin`: LayerNorm of the rows of X applied on load (statistics from the producing layer, gamma / beta of the consumer's
+// norm); `stats_out`: (mean, rstd) of the output rows for the next layer's on-load LayerNorm.
+struct LnIn {
+    const float *stats = nullptr, *g = nullptr, *b = nullptr;
+};
 int lin(const float *X, int ldx, const mac_linear_w_t &w, const float *bias, float *out, int ldo, long long M, int act,
-        const float *res, int ldr, float *ln_out, int ldl, const float *g, const float *b, int pool, cudaStream_t st)
+        const float *res, int ldr, float *ln_out, int ldl, const float *g, const float *b, int pool, cudaStream_t st,
+        LnIn lnin = LnIn(), float *stats_out = nullptr)
 {
     return linear_forward(X, ldx, w.hi, w.lo, w.ldw, bias, out, ldo, static_cast<int>(M), w.N, w.K, act, res, ldr, ln_out, ldl,
-                          g, b, kLnEps, pool, st);
+                          g, b, kLnEps, pool, st, 0, lnin.stats, lnin.g, lnin.b, stats_out);
 }
 
 // Buffers of one encoder stack over T tokens of width D.
 struct EncBufs {
     float *x, *x2, *ln, *qkv, *att, *ff;
     float *attn_scratch;  // tensor-core attention operands (dense attention only)
+    float *stats;         // (T, 2) row statistics (mean, rstd) of the residual stream: LayerNorm is applied on load
     int ldqkv;
 };
 
@@ -49,7 +56,7 @@ bool use_tc_attention(int S)
     }();
     return !force_cuda_cores && S >= 64;
 }
-size_t enc_floats_per_token(int D, int qkv_n) { return 3 * static_cast<size_t>(D) + qkv_n + D + 2 * D; }
+size_t enc_floats_per_token(int D, int qkv_n) { return 3 * static_cast<size_t>(D) + qkv_n + D + 2 * D + 2; }
 
 EncBufs carve_enc(Bump &ws, long long T, int D, int qkv_n, size_t attn_scratch_floats = 0)
 {
@@ -57,18 +64,26 @@ EncBufs carve_enc(Bump &ws, long long T, int D, int qkv_n, size_t attn_scratch_f
     e.x = ws.f(T * D), e.x2 = ws.f(T * D), e.ln = ws.f(T * D);
     e.qkv = ws.f(T * qkv_n), e.att = ws.f(T * D), e.ff = ws.f(T * 2 * D);
     e.attn_scratch = attn_scratch_floats ? ws.f(attn_scratch_floats) : nullptr;
+    e.stats = ws.f(T * 2);
     e.ldqkv = qkv_n;
     return e;
 }
 
-// On entry e.x = residual stream, e.ln = norm1 of encoder 0 applied to it.  On exit e.ln = final LayerNorm(x).
-// seq16: attention over groups of 16 tokens; otherwise over B clouds of S tokens.
-int encoder_stack(const mac_encoder_w_t *enc, int n_enc, const float *fin_g, const float *fin_b, EncBufs &e, long long T,
-                  int D, int dqk, int dv, bool seq16, int B, int S, cudaStream_t st, const int *lens = nullptr)
+// On entry e.x = residual stream and either e.ln = norm1 of encoder 0 applied to it (first_is_materialised) or e.stats =
+// its row statistics.  Inside the stack no normalised copy is written: every layer that ends a residual branch emits the
+// (mean, rstd) of its rows and the consumer applies its own LayerNorm (gamma, beta) while splitting X for the tensor
+// cores.  On exit e.x = residual stream, e.stats = its statistics: the caller's next layer normalises with (fin_g, fin_b).
+// seq16: attention over groups of 16 tokens; otherwise over B clouds of S tokens (lens: ragged batches).
+int encoder_stack(const mac_encoder_w_t *enc, int n_enc, EncBufs &e, long long T, int D, int dqk, int dv, bool seq16, int B, int S,
+                  cudaStream_t st, const int *lens = nullptr, bool first_is_materialised = false)
 {
     for (int i = 0; i < n_enc; ++i) {
         const mac_encoder_w_t &w = enc[i];
-        if (int rc = lin(e.ln, D, w.qkv, w.qkv.bias, e.qkv, e.ldqkv, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+        const bool mat = first_is_materialised && i == 0;
+        LnIn n1;
+        if (!mat) n1.stats = e.stats, n1.g = w.ln1_g, n1.b = w.ln1_b;
+        if (int rc = lin(mat ? e.ln : e.x, D, w.qkv, w.qkv.bias, e.qkv, e.ldqkv, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr,
+                         nullptr, 0, st, n1))
             return rc;
         if (seq16) {
             if (int rc = attn16(e.qkv, e.ldqkv, e.att, D, T / 16, dqk, dv, st)) return rc;
@@ -79,14 +94,18 @@ int encoder_stack(const mac_encoder_w_t *enc, int n_enc, const float *fin_g, con
                 if (int rc = attn_dense(e.qkv, e.ldqkv, e.att, D, B, S, dqk, dv, st, lens)) return rc;
             }
         }
-        // x2 = x + out(att);  ln = norm2(x2)
-        if (int rc = lin(e.att, D, w.out, w.out.bias, e.x2, D, T, MAC_LIN_NONE, e.x, D, e.ln, D, w.ln2_g, w.ln2_b, 0, st)) return rc;
-        if (int rc = lin(e.ln, D, w.ff1, w.ff1.bias, e.ff, 2 * D, T, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+        // x2 = x + out(att), statistics of x2 for norm2
+        if (int rc = lin(e.att, D, w.out, w.out.bias, e.x2, D, T, MAC_LIN_NONE, e.x, D, nullptr, 0, nullptr, nullptr, 0, st, LnIn(),
+                         e.stats))
             return rc;
-        // x = x2 + ff2(ff);  ln = next norm1 (or the final norm)
-        const float *ng = (i + 1 < n_enc) ? enc[i + 1].ln1_g : fin_g;
-        const float *nb = (i + 1 < n_enc) ? enc[i + 1].ln1_b : fin_b;
-        if (int rc = lin(e.ff, 2 * D, w.ff2, w.ff2.bias, e.x, D, T, MAC_LIN_NONE, e.x2, D, e.ln, D, ng, nb, 0, st)) return rc;
+        LnIn n2;
+        n2.stats = e.stats, n2.g = w.ln2_g, n2.b = w.ln2_b;
+        if (int rc = lin(e.x2, D, w.ff1, w.ff1.bias, e.ff, 2 * D, T, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st, n2))
+            return rc;
+        // x = x2 + ff2(ff), statistics of x for the next norm1 (or the final norm)
+        if (int rc = lin(e.ff, 2 * D, w.ff2, w.ff2.bias, e.x, D, T, MAC_LIN_NONE, e.x2, D, nullptr, 0, nullptr, nullptr, 0, st, LnIn(),
+                         e.stats))
+            return rc;
     }
     return MAC_OK;
 }
@@ -115,7 +134,7 @@ extern "C" size_t mac_sconevis_workspace_bytes(int B, int S)
     size_t n = 0;
     n += align256(T * 128 * 4);                       // h
     n += align256(static_cast<size_t>(B) * 128 * 4);  // gmax
-    n += 6 * align256(T * 512 * 4);                   // encoder buffers (upper bound: D = 256, qkv 384, ff 512)
+    n += 6 * align256(T * 512 * 4) + align256(T * 2 * 4);   // encoder buffers (upper bound: D = 256, qkv 384, ff 512), row stats
     n += align256(T * 256 * 4) + align256(T * 128 * 4);
     n += align256(attn_dense_tc_scratch_floats(B, S, 64) * 4);
     return n + 4096;
@@ -151,9 +170,11 @@ int sconevis_forward(const mac_sconevis_w_t *w, const float *pts, const float *v
     if (int rc = colpool(e.x, D, B, S, F, gmax, nullptr, 128, st, lens)) return rc;
     if (int rc = vis_embed_finish(e.x, D, gmax, 128, pts, 4, F, 4, S, T, w->enc[0].ln1_g, w->enc[0].ln1_b, kLnEps, e.ln, D, st))
         return rc;
-    if (int rc = encoder_stack(w->enc, w->n_enc, w->ln_g, w->ln_b, e, T, D, w->dqk, w->dv, false, B, S, st, lens)) return rc;
-    // head: fc1 + GELU | view harmonics -> fc2 + GELU -> fc3
-    if (int rc = lin(e.ln, D, w->fc1, w->fc1.bias, hb, 256, T, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st)) return rc;
+    if (int rc = encoder_stack(w->enc, w->n_enc, e, T, D, w->dqk, w->dv, false, B, S, st, lens, true)) return rc;
+    // head: final norm (on load) -> fc1 + GELU | view harmonics -> fc2 + GELU -> fc3
+    LnIn fin;
+    fin.stats = e.stats, fin.g = w->ln_g, fin.b = w->ln_b;
+    if (int rc = lin(e.x, D, w->fc1, w->fc1.bias, hb, 256, T, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st, fin)) return rc;
     MAC_CUDA(cudaMemcpy2DAsync(hb + 192, 256 * sizeof(float), vh, 64 * sizeof(float), 64 * sizeof(float), T,
                                cudaMemcpyDeviceToDevice, st));
     if (int rc = lin(hb, 256, w->fc2, w->fc2.bias, h2, 128, T, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st)) return rc;
@@ -193,7 +214,8 @@ size_t sconeocc_workspace(int B, int Sg, int chunk, int Q)
     const size_t Tm = Tg > Tl ? Tg : Tl;
     size_t n = 0;
     n += align256(Tm * 128 * 4);                                  // h
-    n += 3 * align256(Tm * 128 * 4) + align256(Tm * 192 * 4) + align256(Tm * 128 * 4) + align256(Tm * 256 * 4);  // encoder
+    n += 3 * align256(Tm * 128 * 4) + align256(Tm * 192 * 4) + align256(Tm * 128 * 4) + align256(Tm * 256 * 4) +
+         align256(Tm * 2 * 4);  // encoder, row statistics
     n += align256(Tg * 256 * 4);                                  // global linear0 output
     n += align256(attn_dense_tc_scratch_floats(B, Sg, 32) * 4);   // tensor-core attention operands (global transformer)
     n += 2 * align256(static_cast<size_t>(B) * 512 * 4);          // global feature, per-cloud bias
@@ -251,10 +273,13 @@ extern "C" int mac_sconeocc_forward_f32(const mac_sconeocc_w_t *w, const float *
     {
         const mac_pct_w_t &g = w->global_pct;
         if (int rc = embed_first(pc_global, 3, 3, nullptr, nullptr, nullptr, 0, 0, g.emb1_w, g.emb1_b, g.inner, 1, h, 128, Tg, st)) return rc;
-        if (int rc = lin(h, 128, g.emb2, g.emb2.bias, e.x, D, Tg, MAC_LIN_NONE, nullptr, 0, e.ln, D, g.enc[0].ln1_g, g.enc[0].ln1_b, 0, st))
+        if (int rc = lin(h, 128, g.emb2, g.emb2.bias, e.x, D, Tg, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st, LnIn(),
+                         e.stats))
             return rc;
-        if (int rc = encoder_stack(g.enc, g.n_enc, g.ln_g, g.ln_b, e, Tg, D, g.dqk, g.dv, false, B, Sg, st)) return rc;
-        if (int rc = lin(e.ln, D, g.linear0, g.linear0.bias, g0, 256, Tg, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+        if (int rc = encoder_stack(g.enc, g.n_enc, e, Tg, D, g.dqk, g.dv, false, B, Sg, st)) return rc;
+        LnIn fin;
+        fin.stats = e.stats, fin.g = g.ln_g, fin.b = g.ln_b;
+        if (int rc = lin(e.x, D, g.linear0, g.linear0.bias, g0, 256, Tg, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st, fin))
             return rc;
         if (int rc = colpool(g0, 256, B, Sg, 256, gfeat, gfeat + 256, 512, st)) return rc;
         // the global feature is the same for every query of a cloud: fold it into the bias of linear1
@@ -283,12 +308,14 @@ extern "C" int mac_sconeocc_forward_f32(const mac_sconeocc_w_t *w, const float *
                 if (int rc = embed_first(nullptr, 0, 3, pcs, xq, idx_all[s] + static_cast<size_t>(q0) * 16, nq, N, l.emb1_w, l.emb1_b,
                                          l.inner, 1, h, 128, T, st))
                     return rc;
-                if (int rc = lin(h, 128, l.emb2, l.emb2.bias, e.x, D, T, MAC_LIN_NONE, nullptr, 0, e.ln, D, l.enc[0].ln1_g,
-                                 l.enc[0].ln1_b, 0, st))
+                if (int rc = lin(h, 128, l.emb2, l.emb2.bias, e.x, D, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st,
+                                 LnIn(), e.stats))
                     return rc;
-                if (int rc = encoder_stack(l.enc, l.n_enc, l.ln_g, l.ln_b, e, T, D, l.dqk, l.dv, true, 0, 0, st)) return rc;
-                if (int rc = lin(e.ln, D, l.linear0, l.linear0.bias, feat + s * 256, kFeat, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0,
-                                 nullptr, nullptr, 16, st))
+                if (int rc = encoder_stack(l.enc, l.n_enc, e, T, D, l.dqk, l.dv, true, 0, 0, st)) return rc;
+                LnIn fin;
+                fin.stats = e.stats, fin.g = l.ln_g, fin.b = l.ln_b;
+                if (int rc = lin(e.x, D, l.linear0, l.linear0.bias, feat + s * 256, kFeat, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0,
+                                 nullptr, nullptr, 16, st, fin))
                     return rc;
             }
             if (int rc = embed_first(xq, 3, 3, nullptr, nullptr, nullptr, 0, 0, w->xemb1_w, w->xemb1_b, w->xemb1_n, 0, xe1, 128, nq, st))
