@@ -81,16 +81,21 @@ HOST_HARNESS = r"""
 #include <cstdio>
 #define __device__
 #define __forceinline__ inline
+#define MAC_HOST_EMULATION
 #include "sh_horner_gen.h"
 int main() {
-    float h[64], g[64]; double d[3];
+    float h[64], g[64], g0[8]; unsigned long long gp[28]; double d[3];
     int n; if (scanf("%d", &n) != 1) return 1;
     for (int i = 0; i < n; ++i) {
         for (int k = 0; k < 64; ++k) if (scanf("%f", &h[k]) != 1) return 1;
         if (scanf("%lf %lf %lf", &d[0], &d[1], &d[2]) != 3) return 1;
         mac_sh_pretransform(h, g, 1.0f);
+        mac_sh_pretransform_pq(h, g0, gp, 1.0f);
         double r = std::sqrt(d[0]*d[0] + d[1]*d[1] + d[2]*d[2]);
-        printf("%.9g\n", mac_sh_eval(g, (float)(d[0]/r), (float)(d[1]/r), (float)(d[2]/r)));
+        const float ux = (float)(d[0]/r), ct = (float)(d[1]/r), uz = (float)(d[2]/r);
+        float z0, z1;   // the evaluator of the kernel: two rays at once (here the ray and its mirror image in x)
+        mac_sh_eval2_pq(g0, gp, ux, ct, uz, -ux, ct, uz, z0, z1);
+        printf("%.9g %.9g %.9g\n", mac_sh_eval(g, ux, ct, uz), z0, z1);
     }
     return 0;
 }
@@ -98,7 +103,8 @@ int main() {
 
 
 def test_generated_change_of_basis_on_host(tmp_path):
-    """sum_k H_k Y_k(u) == Re sum_m (A_m(ct) - i B_m(ct)) (uz + i ux)^m with the generated constants."""
+    """sum_k H_k Y_k(u) == Re sum_m (A_m(ct) - i B_m(ct)) (uz + i ux)^m == P(ct, uz) + ux Q(ct, uz) with the generated
+    constants (coefficients ~ N(0, 1): twice the scale of the accuracy figures quoted in DESIGN.md)."""
     src = tmp_path / "harness.cpp"
     src.write_text(HOST_HARNESS)
     exe = tmp_path / "harness"
@@ -111,9 +117,15 @@ def test_generated_change_of_basis_on_host(tmp_path):
     D[8:12, [0, 2]] = 1e-4 * D[8:12][:, [0, 2]]   # nearly straight up/down
     lines = ["%d" % n] + [" ".join("%.9g" % v for v in H[i]) + " %.17g %.17g %.17g" % tuple(D[i]) for i in range(n)]
     out = subprocess.run([str(exe)], input="\n".join(lines), capture_output=True, text=True, check=True).stdout
-    got = np.array([float(x) for x in out.split()])
+    got = np.array([float(x) for x in out.split()]).reshape(n, 3)
     want = np.sum(sh_cov.sh_basis_closed_form_f64(D) * H.astype(np.float64), axis=-1)
-    assert np.abs(got - want).max() < 3e-5, np.abs(got - want).max()
+    assert np.abs(got[:, 0] - want).max() < 3e-5, np.abs(got[:, 0] - want).max()
+    # the P(ct, uz) + ux Q(ct, uz) form the kernel evaluates (63 FMAs per ray), and its second ray (x mirrored)
+    assert np.abs(got[:, 1] - want).max() < 8e-5, np.abs(got[:, 1] - want).max()
+    Dm = D * np.array([-1.0, 1.0, 1.0])
+    want_m = np.sum(sh_cov.sh_basis_closed_form_f64(Dm) * H.astype(np.float64), axis=-1)
+    assert np.abs(got[:, 2] - want_m).max() < 8e-5, np.abs(got[:, 2] - want_m).max()
+    assert np.abs(got[:, 1] - want).mean() < 5e-6
 
 
 def test_generated_header_is_current():
