@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) attn16_kernel(const float *__restrict__ q
             float l = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                sc[j] = exp2f(sc[j] - m);
+                sc[j] = ex2_approx(sc[j] - m);   // arguments <= 0: the flush-to-zero of tiny weights is harmless
                 l += sc[j];
             }
             const float inv = 1.0f / l;
