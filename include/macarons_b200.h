@@ -301,6 +301,20 @@ int mac_fov_sample_proxy_f32(const float *X, const float *preds, const float *vi
                              void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Depth-side helpers, methods of `Camera` in /root/reference/macarons/utility/macarons_utils.py:
+ *   mac_unproject_depth_f32  project_depth_in_3D :2339-2360: depth (B, H, W) metric depth -> out (B, H*W, 3) world points;
+ *       cams (B, 18) = [inverse full projection 4x4, row-vector convention | f1 | f2] with f1 = K[2][2], f2 = K[3][2] of
+ *       the pytorch3d projection matrix (unproject_points, scaled_depth_input = False); the NDC pixel tables are those
+ *       of Camera.__init__ :1929-1938.
+ *   mac_signed_distance_f32  get_signed_distance_to_depth_maps :2451-2500: pts (P, 3), depth_maps (n, H, W), mask (n, H, W)
+ *       bytes, cams (n, 32) = [full projection 4x4 | world-to-view 4x4] -> out (n, P) = view z - bilinear sample of the
+ *       depth map (border padding, align_corners = False; masked pixels read as `fill` = 1.1 zfar).
+ * ------------------------------------------------------------------------------------------- */
+int mac_unproject_depth_f32(const float *depth, const float *cams, float *out, int B, int H, int W, void *stream);
+int mac_signed_distance_f32(const float *pts, const float *depth_maps, const unsigned char *mask, const float *cams, float *out,
+                            int n_depth, int P, int H, int W, float fill, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * ManyDepth.forward (row a14), /root/reference/macarons/networks/ManyDepth.py:719-758 -> DepthDecoder.forward
  * :474-531 -> CostVolumeBuilder.forward :207-305, inference mode (BatchNorm folded into the convolutions at packing
  * time, ground-truth relative poses already composed into per-frame cameras by the caller, ManyDepth.py:740-750).

@@ -100,6 +100,10 @@ SYMBOLS["mac_fov_sample_proxy_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, _c
                                                       _c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])
 
 
+SYMBOLS["mac_unproject_depth_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.c_void_p])
+SYMBOLS["mac_signed_distance_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p, _c_float_p, _c_float_p, ctypes.c_int,
+                                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p])
 SYMBOLS["mac_manydepth_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                             ctypes.c_int])
 SYMBOLS["mac_manydepth_forward_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p,

@@ -72,7 +72,9 @@ class SconeOcc(nn.Module):
         self.linear2 = nn.Linear(512, 256)
         self.linear3 = nn.Linear(256, output_dim)
         self.non_linear1, self.non_linear2, self.non_linear3 = _activation(gelu), _activation(gelu), _activation(gelu)
-        self.queries_per_pass = 16384   # internal chunking of the fused forward (results do not depend on it)
+        # internal chunking of the fused forward (results do not depend on it): 65536 queries = 1 M neighbourhood tokens
+        # per launch, ~4.6 GB of workspace; measured 77.1 ms per 64^3 grid vs 79.3 ms at 16384 (fewer launch ramps / tails)
+        self.queries_per_pass = 65536
 
     def draw_subsamples(self, full_seq_len):
         """The random sub-samples of one forward call, drawn like the reference does (CPU generator, same

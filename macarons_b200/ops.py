@@ -271,7 +271,7 @@ def sconevis_forward(w, pts, view_harmonics, lens=None):
     return out
 
 
-def sconeocc_forward(w, pc_global, pc_scales, x, view_harmonics, chunk=16384):
+def sconeocc_forward(w, pc_global, pc_scales, x, view_harmonics, chunk=65536):
     """Packed weights (netpack.SconeOccW); pc_global (B,Sg,3); pc_scales: list of 3 (B,N_s,3) clouds;
     x (B,Q,3); view_harmonics (B,Q,64) -> (B,Q,1)."""
     import ctypes
@@ -410,6 +410,39 @@ def fov_sample_proxy(X_world, preds, view_harmonics, cams, ndc_bounds, fov_range
                                                 inverse.data_ptr(), counts.data_ptr(), volume.data_ptr(), ws.data_ptr(),
                                                 ws.numel(), _stream_ptr(dev)))
     return res, res_h, inverse, counts, volume
+
+
+def unproject_depth(depth, cams, H, W):
+    """depth (B, H*W) metric depth, cams (B, 18) [inverse full projection | f1 | f2] -> world points (B, H*W, 3)."""
+    _require_cuda_f32("depth", depth)
+    _require_cuda_f32("cams", cams)
+    B = depth.shape[0]
+    if depth.numel() != B * H * W or tuple(cams.shape) != (B, 18):
+        raise ValueError("expected depth with B*H*W elements and cams (B, 18)")
+    depth, cams = depth.contiguous(), cams.contiguous()
+    out = torch.empty((B, H * W, 3), dtype=torch.float32, device=depth.device)
+    with torch.cuda.device(depth.device):
+        _lib.check(_lib.load().mac_unproject_depth_f32(depth.data_ptr(), cams.data_ptr(), out.data_ptr(), B, int(H), int(W),
+                                                       _stream_ptr(depth.device)))
+    return out
+
+
+def signed_distance(pts, depth_maps, mask, cams, H, W, fill):
+    """pts (P,3), depth_maps (n,H,W), mask (n,H,W) bool, cams (n,32) [full projection | world-to-view] -> (n, P)."""
+    for name, t in (("pts", pts), ("depth_maps", depth_maps), ("cams", cams)):
+        _require_cuda_f32(name, t)
+    n, P = depth_maps.shape[0], pts.shape[0]
+    if tuple(pts.shape) != (P, 3) or depth_maps.numel() != n * H * W or mask.numel() != n * H * W or tuple(cams.shape) != (n, 32):
+        raise ValueError("expected pts (P,3), depth_maps / mask (n,H,W), cams (n,32)")
+    pts, depth_maps, cams = pts.contiguous(), depth_maps.contiguous(), cams.contiguous()
+    mask = mask.to(device=pts.device, dtype=torch.uint8).contiguous()
+    out = torch.empty((n, P), dtype=torch.float32, device=pts.device)
+    if P == 0:
+        return out
+    with torch.cuda.device(pts.device):
+        _lib.check(_lib.load().mac_signed_distance_f32(pts.data_ptr(), depth_maps.data_ptr(), mask.data_ptr(), cams.data_ptr(),
+                                                       out.data_ptr(), n, P, int(H), int(W), float(fill), _stream_ptr(pts.device)))
+    return out
 
 
 def manydepth_forward(w, x, x_alpha, cam):

@@ -198,3 +198,60 @@ def predict_coverage_gain_for_single_camera(params, macarons, proxy_scene, surfa
     dummy_harm = macarons(mode='visibility', proxy_points=dummy_pts, view_harmonics=dummy_vh)
     gains = model.compute_visibility_gains(pts=dummy_pts, harmonics=dummy_harm, X_cam=X_cam_world.view(1, -1, 3))
     return dummy_pts, dummy_vh, gains, (torch.mean(gains, dim=-1) * 0.).view(-1, 1)
+
+
+# ---- depth-side helpers (reference: methods of `Camera`, macarons_utils.py:2339-2500) -----------------------------------
+# They take the reference's Camera object (or anything with image_height, image_width, zfar, gathering_factor, fov_camera)
+# as first argument, so a maintainer binds them back as methods: `Camera.project_depth_in_3D = project_depth_in_3D`, ...
+def _unproject_rows(fov_cameras, device):
+    """(B, 18) rows [inverse full projection 4x4 | f1 | f2] for mac_unproject_depth_f32 (pytorch3d unproject_points)."""
+    inv = fov_cameras.get_full_projection_transform().inverse().get_matrix()
+    K = fov_cameras.get_projection_transform().get_matrix()
+    B = inv.shape[0]
+    rows = torch.cat((inv.reshape(B, 16), K[:, 2, 2].reshape(B, 1), K[:, 3, 2].reshape(B, 1)), dim=1)
+    return rows.to(device=device, dtype=torch.float32).contiguous()
+
+
+def project_depth_in_3D(camera, depth, fov_cameras=None):
+    """depth (batch_size, height, width, 1) -> world points (batch_size, height*width, 3)   [reference :2339-2360]"""
+    if fov_cameras is None:
+        fov_cameras = camera.fov_camera
+    B = depth.shape[0]
+    return ops.unproject_depth(depth.reshape(B, -1), _unproject_rows(fov_cameras, depth.device), camera.image_height,
+                               camera.image_width)
+
+
+def compute_partial_point_cloud(camera, depth, mask, images=None, fov_cameras=None, gathering_factor=None, fov_range=None):
+    """Partial point cloud seen by one camera: masked pixels un-projected, a random fraction kept  [reference :2362-2398].
+    depth, mask (1, height, width, 1); the permutation is drawn like the reference (torch.randperm, CPU generator)."""
+    points_mask = mask.view(1, -1) if fov_range is None else mask.view(1, -1) * (depth < fov_range).view(1, -1)
+    world_points = project_depth_in_3D(camera, depth, fov_cameras=fov_cameras)[points_mask]
+    if gathering_factor is None:
+        gathering_factor = camera.gathering_factor
+    n_points = int(len(world_points) * gathering_factor)
+    points_indices = torch.randperm(len(world_points))[:n_points].to(world_points.device)
+    world_points = world_points[points_indices]
+    if images is None:
+        return world_points
+    return world_points, (0. + images.view(1, -1, 3))[points_mask][points_indices]
+
+
+def get_signed_distance_to_depth_maps(camera, pts, depth_maps, mask, fov_camera=None):
+    """pts (n_points, 3), depth_maps / mask (n_depth, height, width, 1) -> (n_depth, n_points, 1): positive behind the
+    surface seen in the depth map, negative in front of it  [reference :2451-2500]."""
+    n_depths = depth_maps.shape[0]
+    if fov_camera is None:
+        fov_camera = camera.fov_camera
+        if n_depths > 1:
+            raise NameError("Too many depth maps provided for current camera; depth_maps should have shape (1, ...)"
+                            "If you want to simultaneously process depth maps for multiple cameras, "
+                            "please provide the corresponding fov_camera argument.")
+    elif n_depths != fov_camera.R.shape[0]:
+        raise NameError("Number of cameras should be the same as number of depths.")
+    H, W = camera.image_height, camera.image_width
+    full = fov_camera.get_full_projection_transform().get_matrix()
+    view = fov_camera.get_world_to_view_transform().get_matrix()
+    rows = torch.cat((full.reshape(n_depths, 16), view.reshape(n_depths, 16)), dim=1).to(device=pts.device, dtype=torch.float32)
+    out = ops.signed_distance(pts, depth_maps.reshape(n_depths, H, W), mask.reshape(n_depths, H, W), rows, H, W,
+                              1.1 * float(camera.zfar))
+    return out.view(n_depths, -1, 1)

@@ -34,6 +34,7 @@ from macarons.utility import utils as ref_utils  # noqa: E402
 from macarons.networks import ManyDepth as ref_md  # noqa: E402
 from oracle import cameras as o_cams  # noqa: E402
 from oracle import depth as o_depth  # noqa: E402
+from oracle import depth_io as o_dio  # noqa: E402
 from oracle import macarons_cov as o_mcov  # noqa: E402
 from oracle import sampling as o_sampling  # noqa: E402
 from oracle import scone_nets as o_nets  # noqa: E402
@@ -248,6 +249,41 @@ def macarons_cov_goldens():
              visibility_sum=torch.cat(vis_sum), n_returned=np.asarray(nuniq))
 
 
+
+def depth_io_goldens():
+    """`Camera.project_depth_in_3D`, `compute_partial_point_cloud` and `get_signed_distance_to_depth_maps` of the reference
+    (utility/macarons_utils.py:2339-2500), called unbound on a stand-in for `self` (the Camera constructor needs a renderer)."""
+    import types
+    from macarons.utility import macarons_utils as ref_mu
+    H, W, seed = 48, 80, 801
+    s = synth.depth_io_inputs(H, W, seed)
+    cam = o_cams.FoVPerspectiveCameras(R=s["R"], T=s["T"], zfar=100.)
+    cam1 = o_cams.FoVPerspectiveCameras(R=s["R"][:1], T=s["T"][:1], zfar=100.)
+    nx, ny = o_dio.ndc_tables(H, W)
+    fake = types.SimpleNamespace(image_height=H, image_width=W, ndc_x_tab=nx, ndc_y_tab=ny, fov_camera=cam1, zfar=100.,
+                                 gathering_factor=0.05)
+    fake.project_depth_in_3D = types.MethodType(ref_mu.Camera.project_depth_in_3D, fake)
+    fake.get_points_zbuf = types.MethodType(ref_mu.Camera.get_points_zbuf, fake)
+    world = ref_mu.Camera.project_depth_in_3D(fake, s["depth"], fov_cameras=cam)
+    must_equal(world, o_dio.project_depth_in_3D(s["depth"], cam, H, W), "depth unprojection")
+    state = torch.get_rng_state()
+    torch.manual_seed(seed)
+    pc, col = ref_mu.Camera.compute_partial_point_cloud(fake, s["depth"][:1], s["mask"][:1], images=s["images"][:1],
+                                                        fov_cameras=cam1, fov_range=9.0)
+    torch.manual_seed(seed)
+    n_sel = int((s["mask"][:1].view(1, -1) * (s["depth"][:1] < 9.0).view(1, -1)).sum())
+    perm = torch.randperm(n_sel)
+    torch.set_rng_state(state)
+    pc2, col2 = o_dio.compute_partial_point_cloud(s["depth"][:1], s["mask"][:1], cam1, H, W, 0.05, images=s["images"][:1],
+                                                  fov_range=9.0, perm=perm)
+    must_equal(pc, pc2, "partial point cloud")
+    must_equal(col, col2, "partial point cloud colours")
+    sd = ref_mu.Camera.get_signed_distance_to_depth_maps(fake, s["pts"], s["depth"], s["mask"], fov_camera=cam)
+    must_equal(sd, o_dio.signed_distance_to_depth_maps(s["pts"], s["depth"], s["mask"], cam, H, W, 100.), "signed distances")
+    save("depth_io_48x80", H=H, W=W, seed=seed, input_digest=digest(s["depth"], s["pts"], s["R"], s["T"]),
+         world_points=world[:, ::7], partial_pc=pc, perm=perm, signed_distance=sd)
+
+
 # (name, B, H, W, seed, stored row stride)
 DEPTH_CASES = [("depth_64x96", 1, 64, 96, 601, 1), ("depth_96x160_b2", 2, 96, 160, 602, 2)]
 
@@ -285,6 +321,9 @@ if __name__ == "__main__":
     if "--depth-only" in sys.argv:
         depth_goldens()
         raise SystemExit(0)
+    if "--depth-io-only" in sys.argv:
+        depth_io_goldens()
+        raise SystemExit(0)
     if "--macarons-only" in sys.argv:
         macarons_cov_goldens()
         raise SystemExit(0)
@@ -296,5 +335,6 @@ if __name__ == "__main__":
     sampling_goldens()
     nets_goldens()
     macarons_cov_goldens()
+    depth_io_goldens()
     depth_goldens()
     print("all oracle == reference checks passed (bitwise)")

@@ -215,3 +215,15 @@ def macarons_scene(N, C, seed, half_extent=(40.0, 15.0, 40.0)):
     return {"X_world": X.contiguous(), "occ": occ.contiguous(), "vh": vh.contiguous(), "X_cam": eye.contiguous(),
             "R": R, "T": T, "pred_R": pR, "pred_T": pT, "x_min": -ext, "x_max": ext,
             "diag": torch.linalg.norm(2 * ext).item(), "u": torch.rand(C, 2048, 1, generator=gen)}
+
+
+def depth_io_inputs(H, W, seed, n=2):
+    """n depth maps with masks and colours, cameras looking at the origin, and 3-D probe points around it."""
+    gen = torch.Generator(device="cpu").manual_seed(int(seed))
+    eye = torch.tensor([[3., 2., -8.], [1., -1., -6.], [-4., 1., 5.]])[:n]
+    R, T = look_at_RT(eye, torch.zeros(n, 3))
+    depth = 2 + 10 * torch.rand(n, H, W, 1, generator=gen)
+    mask = torch.rand(n, H, W, 1, generator=gen) > 0.3
+    images = torch.rand(n, H, W, 3, generator=gen)
+    pts = (torch.rand(700, 3, generator=gen) - 0.5) * 8
+    return {"R": R, "T": T, "depth": depth, "mask": mask, "images": images, "pts": pts}

@@ -37,7 +37,7 @@ def main():
     ap.add_argument("--n", type=int, default=4096)
     ap.add_argument("--s", type=int, default=2048)
     ap.add_argument("--clouds", type=int, default=1)
-    ap.add_argument("--chunk", type=int, default=16384)
+    ap.add_argument("--chunk", type=int, default=65536)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--skip-occ", action="store_true")
     ap.add_argument("--depth", action="store_true")
