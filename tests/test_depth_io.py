@@ -81,8 +81,8 @@ def test_depth_io_kernels_match_oracle(cuda_device):
 
 @pytest.mark.gpu
 def test_depth_io_full_resolution_properties(cuda_device):
-    """256 x 456 (the MACARONS image size): un-projected pixels lie at their depth in front of the camera and have zero
-    signed distance to their own depth map (up to the bilinear interpolation between neighbouring pixels)."""
+    """256 x 456 (the MACARONS image size): un-projected pixels lie at their depth in front of the camera; world points and
+    signed distances agree with the oracle at full resolution; the partial cloud keeps the reference's fraction of pixels."""
     from macarons_b200.utility import macarons_utils as mu
     dev = cuda_device
     H, W = 256, 456
@@ -94,9 +94,21 @@ def test_depth_io_full_resolution_properties(cuda_device):
     camera = types.SimpleNamespace(image_height=H, image_width=W, zfar=100., gathering_factor=0.05, fov_camera=cam)
     world = mu.project_depth_in_3D(camera, depth)
     view_z = cam.get_world_to_view_transform().transform_points(world)[..., 2]
-    assert (view_z - depth.view(1, -1)).abs().max().item() <= 1e-3
+    # fp32 through the inverse of a znear = 1 / zfar = 100 projection (as the reference does it): 1e-6 relative on the
+    # matrix moves a point at depth 8 by ~5e-4 (measured on the CPU oracle), hence the 5e-3 / 1e-2 bounds on depths of 4-8
+    z_err = (view_z - depth.view(1, -1)).abs().max().item()
+    assert z_err <= 5e-3, z_err
     mask = torch.ones(1, H, W, 1, dtype=torch.bool, device=dev)
-    sd = mu.get_signed_distance_to_depth_maps(camera, world[0], depth, mask)
-    assert sd.shape == (1, H * W, 1) and sd.abs().max().item() <= 2e-3
+    # signed distance of the un-projected pixels to their own depth map, against the oracle on identical inputs (it is not
+    # zero: the reference's NDC tables step by 2 / (min(H, W) - 1) while grid_sample uses align_corners = False, so a pixel
+    # re-projects up to ~half a pixel away from its own centre; the oracle reproduces that, max 0.29 on this depth map)
+    cam_cpu = o_cams.FoVPerspectiveCameras(R=R, T=T, zfar=100.)
+    world_cpu = o_dio.project_depth_in_3D(depth.cpu(), cam_cpu, H, W)
+    want = o_dio.signed_distance_to_depth_maps(world_cpu[0], depth.cpu(), mask.cpu(), cam_cpu, H, W, 100.)
+    sd = mu.get_signed_distance_to_depth_maps(camera, world_cpu[0].to(dev), depth, mask)
+    assert sd.shape == (1, H * W, 1)
+    sd_err = (sd.cpu() - want).abs().max().item()
+    assert sd_err <= 5e-3, sd_err
+    assert (world.cpu() - world_cpu).abs().max().item() <= 5e-3
     pc = mu.compute_partial_point_cloud(camera, depth, mask)
     assert pc.shape == (int(H * W * 0.05), 3)
