@@ -461,7 +461,7 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
         return e ? atoi(e) : 0;
     }();
     // 8 warps x 2 CTAs/SM (128 registers) measured fastest; 12 x 1 (168 regs) and 16 x 1 were 9-11 % slower
-    // (profiles/r01_covgain.md).
+    // (DESIGN.md section 4.3).
     const int warps_per_cta = 8;
     const int ctas_per_sm = 2;
     const long long slots = static_cast<long long>(sm_count(device)) * ctas_per_sm * warps_per_cta;  // resident warps
