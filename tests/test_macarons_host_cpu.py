@@ -1,0 +1,99 @@
+"""CPU tests of the host-side logic around the MACARONS scoring kernels (macarons_b200/utility/macarons_utils.py): the
+distance factors (reference utility/macarons_utils.py:1741-1788) against the oracle restatement, the camera rows handed to
+the kernels, and the argument / error behaviour that needs no GPU."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from macarons_b200.utility import macarons_utils as mu
+from oracle import cameras as o_cams
+from oracle import macarons_cov as o_mcov
+
+
+def _params(th):
+    return types.SimpleNamespace(distance_factor_th=th, image_height=256, image_width=456, sensor_range=70.,
+                                 min_occ_for_proxy_points=0.1, seq_len=64, use_occ_to_sample_proxy_points=True, jz=False,
+                                 ddp=False, k_for_knn=16, n_harmonics=64)
+
+
+@pytest.mark.parametrize("th", [17.0, "smooth", None])
+def test_distance_factors_match_oracle(th):
+    gen = torch.Generator().manual_seed(3)
+    pts = (torch.rand(500, 3, generator=gen) - 0.5) * 120
+    X_cam = torch.tensor([[3., -2., 5.]])
+    R, T = synth.look_at_RT(X_cam, torch.zeros(1, 3))
+    cam = o_cams.FoVPerspectiveCameras(R=R, T=T, zfar=1000.)
+    params = _params(th)
+    if th is None:
+        got = mu.get_distance_factor(params, pts, X_cam, cam, 0.5)
+        want = o_mcov.distance_factor(pts, X_cam, cam.fov, 256, 456, 0.5)
+    elif th == "smooth":
+        got = mu.get_distance_factor_smooth(params, pts, X_cam, cam, 0.5)
+        want = o_mcov.distance_factor_smooth(pts, X_cam, cam.fov, 256, 456, 0.5)
+    else:
+        got = mu.get_distance_factor_threshold(pts, X_cam, distance_th=th)
+        want = o_mcov.distance_factor_threshold(pts, X_cam, distance_th=th)
+    assert got.shape == want.shape == (500, 1)
+    assert torch.allclose(got, want, rtol=1e-6, atol=0)
+    # the batched form used by predict_coverage_gains_for_cameras: C cameras at once == one camera at a time
+    eye = torch.tensor([[3., -2., 5.], [-10., 4., 1.], [0.5, 0.5, 30.]])
+    R3, T3 = synth.look_at_RT(eye, torch.zeros(3, 3))
+    batch = o_cams.FoVPerspectiveCameras(R=R3, T=T3, zfar=1000.)
+    world = pts[:64][None].expand(3, -1, -1).contiguous()
+    f = mu._distance_factors(params, world, eye, batch, 0.5)
+    singles = [o_cams.FoVPerspectiveCameras(R=R3[c:c + 1], T=T3[c:c + 1], zfar=1000.) for c in range(3)]
+    f_list = mu._distance_factors(params, world, eye, singles, 0.5)
+    assert f.shape == (3, 64) and torch.equal(f, f_list)
+    for c in range(3):
+        if th is None:
+            w = o_mcov.distance_factor(world[c], eye[c:c + 1], singles[c].fov, 256, 456, 0.5)
+        elif th == "smooth":
+            w = o_mcov.distance_factor_smooth(world[c], eye[c:c + 1], singles[c].fov, 256, 456, 0.5)
+        else:
+            w = o_mcov.distance_factor_threshold(world[c], eye[c:c + 1], distance_th=th)
+        assert torch.allclose(f[c], w.view(-1), rtol=1e-6, atol=0)
+
+
+def test_camera_rows_batched_equals_list():
+    s = synth.macarons_scene(100, 5, 3)
+    batch = o_cams.FoVPerspectiveCameras(R=s["R"], T=s["T"], zfar=1000.)
+    singles = [o_cams.FoVPerspectiveCameras(R=s["R"][c:c + 1], T=s["T"][c:c + 1], zfar=1000.) for c in range(5)]
+    rows_b, rows_l = mu._camera_rows(batch, "cpu"), mu._camera_rows(singles, "cpu")
+    assert rows_b.shape == (5, 36) and torch.allclose(rows_b, rows_l, rtol=1e-6, atol=1e-6)
+    # [full projection | world-to-view | centre | 0]: the centre is where the world-to-view transform maps to the origin
+    centre = rows_b[:, 32:35]
+    assert np.abs((centre - s["X_cam"]).numpy()).max() <= 1e-4
+    view = rows_b[:, 16:32].view(5, 4, 4)
+    origin = torch.cat((centre, torch.ones(5, 1)), dim=1)[:, None, :] @ view
+    assert origin[:, 0, :3].abs().max().item() <= 1e-4
+    inv = mu._unproject_rows(batch, "cpu")
+    assert inv.shape == (5, 18)
+    full = rows_b[:, :16].view(5, 4, 4)
+    eye4 = full @ inv[:, :16].view(5, 4, 4)
+    assert (eye4 - torch.eye(4)).abs().max().item() <= 1e-3
+
+
+def test_argument_errors_without_gpu():
+    params = _params(17.0)
+    vis = types.SimpleNamespace(use_sigmoid=False)
+    macarons = types.SimpleNamespace(visibility=vis)
+    s = synth.macarons_scene(50, 2, 4)
+    cams = o_cams.FoVPerspectiveCameras(R=s["R"], T=s["T"], zfar=1000.)
+    args = (s["X_world"], s["vh"], s["occ"])
+    with pytest.raises(NameError):       # ReLU visibility model, as Macarons.compute_visibility_gains (reference :176)
+        mu.predict_coverage_gains_for_cameras(params, macarons, None, None, *args, None, s["X_cam"], cams, prediction_camera=cams)
+    vis.use_sigmoid = True
+    with pytest.raises(NameError):       # neither camera nor prediction camera (reference :1639-1641)
+        mu.predict_coverage_gains_for_cameras(params, macarons, None, None, *args, None, s["X_cam"], cams)
+    params.use_occ_to_sample_proxy_points = False
+    with pytest.raises(NotImplementedError):
+        mu.predict_coverage_gains_for_cameras(params, macarons, None, None, *args, None, s["X_cam"], cams, prediction_camera=cams)
+    camera = types.SimpleNamespace(image_height=4, image_width=4, zfar=10., fov_camera=cams)
+    with pytest.raises(NameError):       # several depth maps for the camera's single pose (reference :2466-2470)
+        mu.get_signed_distance_to_depth_maps(camera, s["X_world"], torch.zeros(2, 4, 4, 1), torch.ones(2, 4, 4, 1, dtype=torch.bool))
+    with pytest.raises(NameError):       # number of cameras != number of depth maps (reference :2472-2473)
+        mu.get_signed_distance_to_depth_maps(camera, s["X_world"], torch.zeros(3, 4, 4, 1), torch.ones(3, 4, 4, 1, dtype=torch.bool),
+                                             fov_camera=cams)
