@@ -152,6 +152,8 @@ class PeerScoreBoard:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         key = (pts.data_ptr(), harmonics.data_ptr(), X_cam.data_ptr(), tuple(pts.shape), tuple(X_cam.shape), stream)
         plan = self._plans.get(key)
+        if plan is not None and not (pts.is_contiguous() and harmonics.is_contiguous() and X_cam.is_contiguous()):
+            plan = None   # same address and shape as a validated input set, but a different layout: validate again
         if plan is None:
             p_c, h_c, x_c, B, P, D, C = ops._prep(pts, harmonics, X_cam)
             if (B, C) != (self.B, self.C):
