@@ -138,3 +138,64 @@ def test_oracle_equals_live_reference_when_present():
     vis = RefVis()
     assert torch.equal(vis.compute_coverage_gain(pts, harm, cams), sh_cov.coverage_gain(pts, harm, cams))
     assert torch.equal(vis.compute_visibilities(pts, harm, cams), sh_cov.visibility_gains(pts, harm, cams))
+
+
+def test_macarons_and_depth_io_oracles_equal_live_reference_when_present():
+    """Bitwise pin of oracle/macarons_cov.py and oracle/depth_io.py against the reference's own functions (its Camera
+    methods called unbound on a stand-in for `self`, its Macarons / SconeVis classes), where /root/reference exists."""
+    import os
+    import sys
+    import types
+    import warnings
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not present on this machine")
+    ref_shim.install()
+    warnings.filterwarnings("ignore", message="Default grid_sample")
+    from macarons.networks.Macarons import Macarons as RefMacarons
+    from macarons.networks.SconeVis import SconeVis as RefVis
+    from macarons.utility import macarons_utils as ref_mu
+    from oracle import cameras as o_cams
+    from oracle import depth_io as o_dio
+    from oracle import macarons_cov as o_mcov
+
+    vis = RefVis()
+    sd = synth.seeded_state_dict(vis.state_dict(), 5)
+    vis.load_state_dict(sd)
+    vis.eval()
+    H, W, S = 256, 456, 128
+    nb = synth.ndc_bounds(H, W)
+    s = synth.macarons_scene(3000, 2, 911)
+    params = types.SimpleNamespace(sensor_range=70., min_occ_for_proxy_points=0.1, seq_len=S, use_occ_to_sample_proxy_points=True,
+                                   jz=False, ddp=False, distance_factor_th=17., image_height=H, image_width=W, k_for_knn=16,
+                                   n_harmonics=64)
+    fake = types.SimpleNamespace(min_ndc_x=nb[0], max_ndc_x=nb[1], min_ndc_y=nb[2], max_ndc_y=nb[3], device="cpu")
+    fake.get_points_in_fov = types.MethodType(ref_mu.Camera.get_points_in_fov, fake)
+    pred = o_cams.FoVPerspectiveCameras(R=s["pred_R"], T=s["pred_T"], zfar=1000.)
+    cam = o_cams.FoVPerspectiveCameras(R=s["R"][:1], T=s["T"][:1], zfar=1000.)
+    X_cam = cam.get_camera_center()
+    state = torch.get_rng_state()
+    torch.manual_seed(12)
+    u = torch.rand(S, 1)
+    torch.manual_seed(12)
+    with torch.no_grad():
+        ref = ref_mu.predict_coverage_gain_for_single_camera(
+            params, RefMacarons(None, None, vis), types.SimpleNamespace(x_min=s["x_min"], x_max=s["x_max"]),
+            types.SimpleNamespace(cell_resolution=0.5), s["X_world"].clone(), s["vh"].clone(), s["occ"].clone(), fake, X_cam, cam,
+            prediction_camera=pred)
+        torch.set_rng_state(state)
+        got = o_mcov.predict_coverage_gain_for_single_camera(sd, s["X_world"], s["vh"], s["occ"], X_cam, cam, pred, nb, s["diag"],
+                                                             seq_len=S, u=u)
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
+
+    d = synth.depth_io_inputs(24, 40, 912)
+    cams = o_cams.FoVPerspectiveCameras(R=d["R"], T=d["T"], zfar=100.)
+    nx, ny = o_dio.ndc_tables(24, 40)
+    fake = types.SimpleNamespace(image_height=24, image_width=40, ndc_x_tab=nx, ndc_y_tab=ny, fov_camera=cams, zfar=100.)
+    fake.get_points_zbuf = types.MethodType(ref_mu.Camera.get_points_zbuf, fake)
+    assert torch.equal(ref_mu.Camera.project_depth_in_3D(fake, d["depth"], fov_cameras=cams),
+                       o_dio.project_depth_in_3D(d["depth"], cams, 24, 40))
+    assert torch.equal(ref_mu.Camera.get_signed_distance_to_depth_maps(fake, d["pts"], d["depth"], d["mask"], fov_camera=cams),
+                       o_dio.signed_distance_to_depth_maps(d["pts"], d["depth"], d["mask"], cams, 24, 40, 100.))
