@@ -1,0 +1,67 @@
+"""CPU: macarons_b200.dropin.install() on the live reference tree (skipped where /root/reference is absent): after it, the
+names the reference's testers / trainers bind resolve to the sm_100a implementation, everything else stays the reference's.
+Runs in a subprocess: install() patches the reference modules of the process it is called in."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+SCRIPT = r'''
+import os, sys
+ROOT, GOLDEN = sys.argv[1], sys.argv[2]
+sys.path.insert(0, ROOT)
+sys.path.insert(0, GOLDEN)
+import ref_shim
+if not ref_shim.reference_available():
+    raise SystemExit(77)
+ref_shim.install()
+import macarons.utility.macarons_utils as ref_mu       # imports scone_utils, the networks, ... (binds their names)
+import macarons.utility.scone_utils as ref_su
+original_loader = ref_mu.load_params
+from macarons_b200 import dropin
+import macarons_b200.networks.Macarons as our_mac
+import macarons_b200.networks.SconeOcc as our_occ
+import macarons_b200.networks.SconeVis as our_vis
+import macarons_b200.utility.macarons_utils as our_mu
+import macarons_b200.utility.scone_utils as our_su
+report = dropin.install()
+import macarons.networks.Macarons as ref_mac_mod
+import macarons.networks.SconeVis as ref_vis_mod
+# the classes, in the module that defines them AND in every module that imported them by name
+assert ref_vis_mod.SconeVis is our_vis.SconeVis and ref_mu.SconeVis is our_vis.SconeVis and ref_su.SconeVis is our_vis.SconeVis
+assert ref_mu.SconeOcc is our_occ.SconeOcc and ref_mac_mod.Macarons is our_mac.Macarons and ref_mu.Macarons is our_mac.Macarons
+# hot functions: scone_utils' own and the copies `from .scone_utils import (...)` left in macarons_utils
+for name in ("compute_view_state", "compute_view_harmonics", "move_view_state_to_view_space", "sample_proxy_points"):
+    assert getattr(ref_su, name) is getattr(our_su, name), name
+    assert getattr(ref_mu, name) is getattr(our_su, name), name
+assert ref_su.compute_occupancy_probability is our_su.compute_occupancy_probability
+assert ref_mu.compute_occupancy_probability is our_mu.compute_occupancy_probability      # the MACARONS twin keeps its own signature
+assert ref_mu.predict_coverage_gain_for_single_camera is our_mu.predict_coverage_gain_for_single_camera
+assert ref_mu.predict_coverage_gains_for_cameras is our_mu.predict_coverage_gains_for_cameras
+assert ref_mu.Camera.project_depth_in_3D is our_mu.project_depth_in_3D
+assert ref_mu.Camera.get_signed_distance_to_depth_maps is our_mu.get_signed_distance_to_depth_maps
+assert set(report["camera_methods"]) == {"project_depth_in_3D", "compute_partial_point_cloud", "get_signed_distance_to_depth_maps"}
+# the control plane is untouched: loaders, optimiser wrappers, the factory functions (which now build OUR classes)
+assert ref_mu.load_params is original_loader
+assert ref_mac_mod.MacaronsWrapper.__module__ == "macarons.networks.Macarons"
+assert ref_mac_mod.create_macarons_model.__module__ == "macarons.networks.Macarons"
+assert ref_mac_mod.create_macarons_model.__globals__["Macarons"] is our_mac.Macarons
+assert ref_mac_mod.create_macarons_model.__globals__["SconeVis"] is our_vis.SconeVis
+assert len(report["replaced"]) >= 30
+# state_dict compatibility of what the reference's factories would now build
+vis = ref_su.SconeVis()
+assert "encoders.2.mhsa.w_q.weight" in vis.state_dict() and type(vis) is our_vis.SconeVis
+print("dropin ok", len(report["replaced"]))
+'''
+
+
+def test_dropin_patches_every_namespace_of_the_reference():
+    res = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, os.path.join(ROOT, "tests", "golden")], capture_output=True,
+                         text=True, timeout=600)
+    if res.returncode == 77:
+        pytest.skip("reference tree not present on this machine")
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "dropin ok" in res.stdout
