@@ -54,6 +54,14 @@ assert len(report["replaced"]) >= 30
 # state_dict compatibility of what the reference's factories would now build
 vis = ref_su.SconeVis()
 assert "encoders.2.mhsa.w_q.weight" in vis.state_dict() and type(vis) is our_vis.SconeVis
+# the reference's own weight initialisers (scone_utils.py:260-289, 399-428) walk OUR module trees
+import torch
+occ = ref_su.SconeOcc()
+before = occ.state_dict()["linear1.weight"].clone()
+ref_su.initialize_scone_occ_weights(occ)
+ref_su.initialize_scone_vis_weights(vis)
+assert not torch.equal(before, occ.state_dict()["linear1.weight"])
+assert sum(v.numel() for v in vis.state_dict().values()) == 1392888
 print("dropin ok", len(report["replaced"]))
 '''
 
