@@ -133,3 +133,16 @@ def test_generated_header_is_current():
     before = open(path).read()
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_sh_tables.py")], stdout=subprocess.DEVNULL)
     assert open(path).read() == before
+
+
+def test_c_caller_sees_error_codes(tmp_path):
+    """include/macarons_b200.h is a plain C header (compiled here as C99 by gcc) and the entry points validate their
+    arguments and report errors through return codes + mac_last_error() before touching the device."""
+    from macarons_b200 import _lib
+    exe = tmp_path / "abi_harness"
+    libdir = os.path.dirname(_lib.lib_path())
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi_harness.c"), "-L", libdir, "-lmacarons_b200",
+                           "-Wl,-rpath," + libdir, "-o", str(exe)])
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0 and "abi harness ok" in res.stdout, res.stdout + res.stderr
