@@ -55,15 +55,29 @@ def build(force=False, verbose=False):
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; cannot build %s" % LIBNAME)
     os.makedirs(LIBDIR, exist_ok=True)
-    objs = []
     logs = []
-    for src in sources():
+    # one object per source, compiled in parallel; an object is rebuilt when its source, any header of csrc/, the
+    # public header or this script is newer than it
+    headers = [d for d in _deps() if not d.endswith(".cu")]
+    h_time = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(h_time, os.path.getmtime(src)):
+            return obj, "", 0
         cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
-        logs.append("$ " + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-        if res.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + logs[-1])
+        return obj, "$ " + " ".join(cmd) + "\n" + res.stdout + res.stderr, res.returncode
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, sources()))
+    objs = []
+    for obj, log, rc in results:
+        if log:
+            logs.append(log)
+        if rc != 0:
+            raise RuntimeError("nvcc failed:\n" + log)
         objs.append(obj)
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)

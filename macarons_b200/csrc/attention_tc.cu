@@ -346,11 +346,8 @@ int run(const float *qkv, int ldq, float *out, int ldo, int B, int S, float *scr
     if (int rc = make_tensor_map_2d(&mK, kp, rows_qk, kRow, kRow, kKB)) return rc;
     if (int rc = make_tensor_map_2d(&mVh, vt_hi, B * kH * DV, S, Sp, DV)) return rc;
     if (int rc = make_tensor_map_2d(&mVl, vt_lo, B * kH * DV, S, Sp, DV)) return rc;
-    static bool configured = false;
-    if (!configured) {
-        MAC_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DQK, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (int rc = ensure_dynamic_smem(once, attn_tc_kernel<DQK, DV>, C::kSmem)) return rc;
     AttnParams p{out, ldo, S, (S + kQT - 1) / kQT, lens};
     attn_tc_kernel<DQK, DV><<<B * kH * p.n_qt, 192, C::kSmem, stream>>>(mQ, mK, mVh, mVl, p);
     MAC_CUDA(cudaGetLastError());

@@ -503,12 +503,9 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
 
 #define MAC_LAUNCH_V(SIG, RED, PACKED, WARPS, MINB)                                                              \
     do {                                                                                                          \
-        static bool attr_done = false;                                                                            \
-        if (!attr_done) {                                                                                         \
-            MAC_CUDA(cudaFuncSetAttribute(covgain_kernel<SIG, RED, PACKED, WARPS, MINB>,                          \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-            attr_done = true;                                                                                     \
-        }                                                                                                         \
+        static DeviceOnce once;                                                                                   \
+        if (int rc = ensure_dynamic_smem(once, covgain_kernel<SIG, RED, PACKED, WARPS, MINB>, static_cast<int>(smem))) \
+            return rc;                                                                                            \
         covgain_kernel<SIG, RED, PACKED, WARPS, MINB><<<grid, WARPS * 32, smem, st>>>(prm, harm_map);             \
     } while (0)
 #define MAC_LAUNCH(SIG, RED)                                       \

@@ -71,7 +71,7 @@ __device__ void wait_scores_and_argmax(const float *scores, const unsigned int *
         if (threadIdx.x == 0) best[b] = s_idx[0];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *status = 0;
+    // *status is sticky: a timeout of an earlier step stays visible until the host clears it (PeerScoreBoard.check)
 }
 
 }  // namespace mac

@@ -540,11 +540,8 @@ int launch_act(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtenso
                cudaStream_t stream)
 {
     using C = Cfg<BN, SPLIT>;
-    static bool configured = false;
-    if (!configured) {
-        MAC_CUDA(cudaFuncSetAttribute(linear_kernel<BN, SPLIT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (int rc = ensure_dynamic_smem(once, linear_kernel<BN, SPLIT, ACT>, C::kSmemBytes)) return rc;
     p.n_tiles_m = (p.M + kBM - 1) / kBM;
     p.n_tiles_n = (p.N + BN - 1) / BN;
     int device = 0;

@@ -75,6 +75,12 @@ extern "C" int mac_covgain_host(const float *pts, int pts_dim, const float *harm
     MAC_REQUIRE(B > 0 && P > 0 && C > 0 && pts_dim >= 3, "bad shape B=%d P=%d C=%d pts_dim=%d", B, P, C, pts_dim);
     MAC_REQUIRE(0 <= cam_begin && cam_begin <= cam_end && cam_end <= C, "bad camera range [%d, %d) for C=%d",
                 cam_begin, cam_end, C);
+    // the call works on `device` and leaves the caller's current device as it found it
+    struct DeviceGuard {
+        int prev = -1;
+        ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    } guard;
+    MAC_CUDA(cudaGetDevice(&guard.prev));
     MAC_CUDA(cudaSetDevice(device));
     HostCache &c = g_cache;
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };

@@ -1,6 +1,7 @@
 // Shared host-side plumbing of the C ABI: thread-local error text, CUDA error mapping, launch counter.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -34,6 +35,25 @@ int covgain_accumulate(const float *pts, int pts_dim, const float *harmonics, co
             return MAC_ERR_CUDA;                                                             \
         }                                                                                    \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: every launcher keeps one
+// DeviceOnce per kernel instantiation and configures the kernel the first time it is launched on each device.
+// Two threads racing on the first call both set the same value, which is harmless.
+struct DeviceOnce {
+    std::atomic<unsigned char> done[64];
+};
+template <class Kernel>
+inline int ensure_dynamic_smem(DeviceOnce &once, Kernel kernel, int bytes)
+{
+    int device = 0;
+    MAC_CUDA(cudaGetDevice(&device));
+    const bool tracked = device >= 0 && device < 64;
+    if (!tracked || !once.done[device].load(std::memory_order_acquire)) {
+        MAC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (tracked) once.done[device].store(1, std::memory_order_release);
+    }
+    return MAC_OK;
+}
 
 // ---- small PTX wrappers shared by the kernels (sm_100a) ---------------------------------------
 #ifdef __CUDACC__

@@ -563,11 +563,8 @@ int attn16(const float *qkv, int ldq, float *out, int ldo, long long n_seq, int 
     MAC_REQUIRE(ldq % 4 == 0 && ldo % 4 == 0, "attention rows must be 16-byte aligned");
     constexpr int LD = 2 * 4 * 8 + 4 * 32 + 4;
     const size_t smem = 8 * 16 * LD * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        MAC_CUDA(cudaFuncSetAttribute(attn16_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (int rc = ensure_dynamic_smem(once, attn16_kernel<8, 32>, static_cast<int>(smem))) return rc;
     const long long want = (n_seq + 7) / 8;
     const int grid = static_cast<int>(want < 148 * 2 ? want : 148 * 2);
     attn16_kernel<8, 32><<<grid, 256, smem, stream>>>(qkv, ldq, out, ldo, n_seq);
@@ -582,11 +579,8 @@ int attn_dense(const float *qkv, int ldq, float *out, int ldo, int B, int S, int
     MAC_REQUIRE(qkv && out && B > 0 && S > 0, "null tensor pointer");
     MAC_REQUIRE(ldq % 4 == 0 && ldo % 4 == 0, "attention rows must be 16-byte aligned");
     dim3 grid((S + 63) / 64, 4, B);
-    static bool configured = false;
-    if (!configured) {
-        MAC_CUDA(cudaFuncSetAttribute(attn_dense_kernel<16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32 * (16 + 64) * 4));
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (int rc = ensure_dynamic_smem(once, attn_dense_kernel<16, 64>, 4 * 32 * (16 + 64) * 4)) return rc;
     if (dqk == 8 && dv == 32) attn_dense_kernel<8, 32><<<grid, 256, 4 * 32 * (8 + 32) * 4, stream>>>(qkv, ldq, out, ldo, S, lens);
     else if (dqk == 16 && dv == 64) attn_dense_kernel<16, 64><<<grid, 256, 4 * 32 * (16 + 64) * 4, stream>>>(qkv, ldq, out, ldo, S, lens);
     else {

@@ -172,11 +172,8 @@ extern "C" int mac_view_harmonics_f32(const float *state, const float *base, con
     MAC_REQUIRE(n_bins > 0 && n_bins <= kMaxBins, "view state supports at most %d bins", kMaxBins);
     const long long n_pts = static_cast<long long>(B) * P;
     const size_t smem = (static_cast<size_t>(n_bins) * 64 + 32 * (n_bins + 1) + n_bins) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        MAC_CUDA(cudaFuncSetAttribute(view_harmonics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (int rc = ensure_dynamic_smem(once, view_harmonics_kernel, 64 * 1024)) return rc;
     const long long want = (n_pts + 31) / 32;
     const int grid = static_cast<int>(want < 148 * 4 ? want : 148 * 4);
     view_harmonics_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(

@@ -3,8 +3,9 @@
 
 Packing = TF32 hi/lo split of every Linear weight (packing.split_tf32), K padded to a multiple of 4 floats,
 w_q / w_k / w_v stacked into one (qk+qk+v, d) matrix, and Embedding.linear2 of the PCTransformers extended with
-identity rows so that the GEMM also concatenates the raw input (Attention.py:125).  A pack is cached on the
-module and rebuilt when any parameter's storage or version counter changes (load_state_dict, .to(), training).
+identity rows so that the GEMM also concatenates the raw input (Attention.py:125).  A pack is cached per
+module (outside the module, see _PACKS) and rebuilt when any parameter's storage or version counter changes
+(load_state_dict, .to(), optimizer steps); `invalidate_pack` covers writes through `.data`.
 """
 import ctypes
 
@@ -102,16 +103,48 @@ class _Packer:
         self.linear(pct.linear0.weight, pct.linear0.bias, dst.linear0)
 
 
+# Packs live OUTSIDE the modules (a WeakKeyDictionary keyed by the module): they hold ctypes structures with raw
+# pointers, which must never be seen by copy.deepcopy / torch.save(model) (the reference pickles whole models,
+# ManyDepth.py:546, :690).
+import os
+import weakref
+
+_PACKS = weakref.WeakKeyDictionary()
+# The fingerprint (storage address, version counter, device of every parameter / buffer) catches load_state_dict,
+# .to(), optimizer steps and every other in-place op on the parameters.  Writes through `.data` (p.data.copy_(),
+# an EMA written as p.data.mul_()) keep both the address and the version counter: call `invalidate_pack(module)`
+# after such a write, or set `verify_content = True` (env MAC_NETPACK_VERIFY=1) to add a float64 checksum of every
+# tensor to the fingerprint (one extra reduction and a host synchronisation per forward).
+verify_content = os.environ.get("MAC_NETPACK_VERIFY", "0") == "1"
+
+
+def _tensors(module):
+    return list(module.parameters()) + list(module.buffers())
+
+
 def _fingerprint(module):
-    return tuple((p.data_ptr(), p._version, p.device.index) for p in module.parameters())
+    ts = _tensors(module)
+    fp = tuple((t.data_ptr(), t._version, t.device.index) for t in ts)
+    if verify_content and ts:
+        with torch.no_grad():
+            sums = torch.stack([t.detach().double().sum() + 3.0 * t.detach().double().square().sum() for t in ts])
+        fp += (tuple(sums.tolist()),)
+    return fp
+
+
+def invalidate_pack(module):
+    """Drop the packed weights of `module` (and of its sub-modules): the next forward re-packs.  Needed only after
+    writes that bypass autograd's version counter (`param.data.<op>_()`)."""
+    for m in module.modules():
+        _PACKS.pop(m, None)
 
 
 def _cached(module, build):
     fp = _fingerprint(module)
-    cache = module.__dict__.get("_mac_pack")
+    cache = _PACKS.get(module)
     if cache is None or cache[0] != fp:
         cache = (fp,) + build()
-        module.__dict__["_mac_pack"] = cache
+        _PACKS[module] = cache
     return cache[1]
 
 
@@ -248,12 +281,4 @@ def pack_manydepth(model):
         w.n_depth, w.d_min, w.d_max = int(cvb.n_depth), float(cvb.d_min), float(cvb.d_max)
         return w, pk
 
-    def fingerprint():
-        return tuple((t.data_ptr(), t._version, t.device.index) for t in list(model.parameters()) + list(model.buffers()))
-
-    cache = model.__dict__.get("_mac_pack")
-    fp = fingerprint()
-    if cache is None or cache[0] != fp:
-        cache = (fp,) + build()
-        model.__dict__["_mac_pack"] = cache
-    return cache[1]
+    return _cached(model, build)

@@ -138,6 +138,7 @@ class ManyDepth(nn.Module):
                             "Consequently, Model must take ground truth poses as an input.")
         if self.training:
             raise NotImplementedError("the fused depth forward folds BatchNorm with its running statistics: call .eval()")
+        ops.refuse_grad("ManyDepth.forward", x, x_alpha, module=self)
         B, n_a = x.shape[0], x_alpha.shape[1]
         pose = gt_pose
         R_alpha, T_alpha = rotations.relative_cameras(R, T, pose, self.pose_factor)

@@ -97,6 +97,9 @@ class SconeOcc(nn.Module):
         """pc (B,N,3), x (B,Q,3), view_harmonics (B,Q,64) -> (B,Q,1)   [reference SconeOcc.py:250-347]"""
         if mask is not None:
             raise NotImplementedError("attention masks are never used on the NBV path (SURVEY.md A.4)")
+        if self.training and self.dropout is not None:
+            raise NotImplementedError("the fused SconeOcc forward has no dropout: call .eval() (dropout=%r)" % self.dropout)
+        ops.refuse_grad("SconeOcc.forward", pc, x, view_harmonics, module=self)
         global_idx, scale_idx = self.draw_subsamples(pc.shape[1])
         clouds = [pc]
         for idx in scale_idx:

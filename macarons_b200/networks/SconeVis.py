@@ -22,7 +22,7 @@ class SconeVis(nn.Module):
             # the reference hard-codes 64 in its projection (SconeVis.py:241); so does the kernel
             raise ValueError("SconeVis on sm_100a supports n_harmonics=64, max_harmonic_rank=8")
         self.pts_dim, self.seq_len, self.pts_embedding_dim = pts_dim, seq_len, pts_embedding_dim
-        self.n_heads, self.n_code = n_heads, n_code
+        self.n_heads, self.n_code, self.dropout = n_heads, n_code, dropout
         self.n_harmonics, self.max_harmonic_rank = n_harmonics, max_harmonic_rank
         self.use_view_state, self.use_global_feature = use_view_state, use_global_feature
         self.view_state_mode, self.alt, self.use_sigmoid = view_state_mode, alt, use_sigmoid
@@ -56,6 +56,9 @@ class SconeVis(nn.Module):
             raise NotImplementedError("attention masks are never used on the NBV path (SURVEY.md A.4)")
         if view_harmonics is None:
             raise NameError("view_harmonics is required (use_view_state=True, view_state_mode='end')")
+        if self.training and self.dropout is not None:
+            raise NotImplementedError("the fused SconeVis forward has no dropout: call .eval() (dropout=%r)" % self.dropout)
+        ops.refuse_grad("SconeVis.forward", pts, view_harmonics, module=self)
         return ops.sconevis_forward(netpack.pack_sconevis(self), pts, view_harmonics)
 
     # ---- a3/a4: SH integration over candidate cameras: CUDA kernel --------------------------------

@@ -21,6 +21,26 @@ def _require_cuda_f32(name, t):
         raise TypeError("%s must be float32 (got %s)" % (name, t.dtype))
 
 
+def wants_grad(*tensors, module=None):
+    """True if autograd is recording and any of the tensors (or parameters of `module`) requires a gradient."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        return True
+    return module is not None and any(p.requires_grad for p in module.parameters())
+
+
+def refuse_grad(what, *tensors, module=None):
+    """The fused forwards are inference kernels: they return tensors without a grad_fn.  Rather than silently
+    training nothing, refuse when a gradient would be expected (reference trainers call these under autograd:
+    trainers/pretrain_scone_vis.py:162-225, pretrain_scone_occ.py:158, train_macarons.py:423-444)."""
+    if wants_grad(*tensors, module=module):
+        raise NotImplementedError(
+            "%s is an inference kernel without a backward pass: call it under torch.no_grad() (or freeze the module with "
+            "requires_grad_(False) and pass inputs that do not require grad).  Differentiable on this path: "
+            "compute_coverage_gain / compute_visibilities / compute_visibility_gains w.r.t. the harmonics." % what)
+
+
 def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 

@@ -152,8 +152,9 @@ class PeerScoreBoard:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         key = (pts.data_ptr(), harmonics.data_ptr(), X_cam.data_ptr(), tuple(pts.shape), tuple(X_cam.shape), stream)
         plan = self._plans.get(key)
-        if plan is not None and not (pts.is_contiguous() and harmonics.is_contiguous() and X_cam.is_contiguous()):
-            plan = None   # same address and shape as a validated input set, but a different layout: validate again
+        if plan is not None and not (pts.is_contiguous() and harmonics.is_contiguous() and X_cam.is_contiguous()
+                                     and pts.dtype == harmonics.dtype == X_cam.dtype == torch.float32):
+            plan = None   # same address and shape as a validated input set, but a different layout / dtype: validate again
         if plan is None:
             p_c, h_c, x_c, B, P, D, C = ops._prep(pts, harmonics, X_cam)
             if (B, C) != (self.B, self.C):
@@ -163,11 +164,11 @@ class PeerScoreBoard:
                 raise ValueError("PeerScoreBoard.step needs contiguous inputs")
             c0, c1 = camera_partition(self.C, self.world, self.rank)
             ws = ops._workspace(self.device, B, C)
-            plan = (P, D, c0, c1, ws, (pts, harmonics, X_cam))     # keeps the tensors of this input set alive
-            if len(self._plans) > 64:
+            plan = (P, D, c0, c1, ws)     # validated metadata only: the caller's tensors are alive for the call
+            if len(self._plans) >= 8:
                 self._plans.clear()
             self._plans[key] = plan
-        P, D, c0, c1, ws, _ = plan
+        P, D, c0, c1, ws = plan
         board = self._c_boards[parity]
         board.epoch = self.epoch & 0xFFFFFFFF
         ev0 = ev1 = None
@@ -182,6 +183,8 @@ class PeerScoreBoard:
         return self._views[parity], self.best
 
     def check(self):
-        """Synchronises; raises if a wait timed out (a peer never arrived)."""
+        """Synchronises; raises if a wait timed out (a peer never arrived) in any step since the last check: the
+        device-side status is sticky and is cleared here."""
         if int(self.status.item()) != 0:
+            self.status.zero_()
             raise RuntimeError("PeerScoreBoard: timed out waiting for a peer's scores")
