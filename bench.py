@@ -111,21 +111,53 @@ def make_inputs(cfg, n_sets):
     return sets, cams
 
 
+def make_config(args, cfg):
+    """The `config` object of the JSON line: identical, key for key, for the GPU arm and for `--impl reference` (the
+    driver compares the two); what is specific to one arm lives outside it (`exchange`, `cpu_baseline.sample`)."""
+    world = max(1, int(args.gpus))
+    return {"workload": args.workload + ": " + cfg["desc"], "B": cfg["B"], "P": cfg["P"], "C": cfg["C"],
+            "parallelism": "GPU arm: camera axis sharded x%d (points replicated), one exchange of the per-camera scores; "
+                           "CPU arm: rank 0 only, all host threads" % world,
+            "cameras_per_gpu": -(-cfg["C"] // world),
+            "l2": "GPU arm: inputs rotate over %d distinct resident sets (%.0f MB > 126 MB L2); CPU arm: one input set"
+                  % (N_INPUT_SETS, N_INPUT_SETS * cfg["B"] * cfg["P"] * 272 / 1e6)}
+
+
+def host_threads():
+    """All host cores this process may run on, regardless of OMP_NUM_THREADS (torchrun sets it
+    to 1 in every rank)."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def run_reference(args, cfg):
     """CPU arm: the oracle port of the reference arithmetic (the reference is pure Python and is not on the
-    GPU box), all host threads torch gives us, on a bounded camera sample of the same workload per step."""
+    GPU box), all host threads, on a bounded camera sample of the same workload per step: the sample is calibrated
+    so that the whole `--steps K --warmup W` run takes about two minutes (all C cameras when that fits)."""
     import torch
     from oracle import sh_cov
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = host_threads()
     (pts, harm), = make_inputs(cfg, 1)[0][:1]
     cams = make_inputs(cfg, 0)[1]
-    n_cam = max(1, min(cfg["C"], (2_000_000 // (cfg["B"] * cfg["P"])) or 1))   # ~2 M pairs per step
     chunk = max(1, 900_000 // (cfg["B"] * cfg["P"]))                            # <= ~230 MB basis temporary
+    n_cal = max(1, min(cfg["C"], (1_000_000 // (cfg["B"] * cfg["P"])) or 1))
+    sh_cov.coverage_gain(pts, harm, cams[:, :n_cal].contiguous(), cam_chunk=chunk)          # page in / thread pool
+    t0 = time.perf_counter()
+    sh_cov.coverage_gain(pts, harm, cams[:, :n_cal].contiguous(), cam_chunk=chunk)
+    per_cam = (time.perf_counter() - t0) / n_cal
+    n_warm = max(1, args.warmup // 3)
+    budget_s = float(os.environ.get("MAC_BENCH_REFERENCE_BUDGET_S", "120"))
+    n_cam = int(max(1, min(cfg["C"], budget_s / (args.steps + n_warm) / max(per_cam, 1e-9))))
     sample = cams[:, :n_cam].contiguous()
-    for _ in range(max(1, args.warmup // 3)):
+    for _ in range(n_warm):
         sh_cov.coverage_gain(pts, harm, sample, cam_chunk=chunk)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -135,10 +167,11 @@ def run_reference(args, cfg):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + cfg["desc"], "B": cfg["B"], "P": cfg["P"], "C": cfg["C"]},
+            "config": make_config(args, cfg),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d of %d cameras x all %d points per step (oracle/sh_cov.py, torch CPU fp32)"
-                                       % (n_cam, cfg["C"], cfg["P"])},
+                             "sample": "%d of %d cameras x all %d points per step (oracle/sh_cov.py = the reference's torch "
+                                       "CPU fp32 arithmetic, bit-pinned to it; evals/s is per camera, so the sample size "
+                                       "does not bias it)" % (n_cam, cfg["C"], cfg["P"])},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -147,6 +180,7 @@ def run_reference(args, cfg):
 def cpu_baseline(cfg, budget_s=15.0):
     import torch
     from oracle import sh_cov
+    host_threads()
     (pts, harm), = make_inputs(cfg, 1)[0][:1]
     cams = make_inputs(cfg, 0)[1]
     chunk = max(1, 900_000 // (cfg["B"] * cfg["P"]))
@@ -213,6 +247,69 @@ def path_stages(dev):
         d = [t.to(dev) for t in synth.depth_inputs(1, 256, 456, 7)]
         out["manydepth_forward_256x456_ms"] = timed(lambda: depth(d[0], d[1], d[2], d[3], d[4], dev, gt_pose=d[5]))
     out["note"] = "fp32-accurate (3xTF32) tcgen05 linear layers; reference on 8 CPU threads: SconeVis 140 ms, SconeOcc 64^3 ~77 s (SURVEY section 6)"
+    return out
+
+
+def online_loop(args, cfg, dev, vis, board, world, rank, n_steps=50, seq_len=2048):
+    """50-step online NBV loop at the cfg5 shape (macarons_b200.nbv.scone_online_loop); device time by CUDA events,
+    max over ranks; the chosen camera sequence must be identical on every rank and (rank 0) to a single-GPU rerun."""
+    import torch
+    import torch.distributed as dist
+    import synth
+    from macarons_b200 import nbv
+    from macarons_b200.utility import scone_utils
+    B, P, C = cfg["B"], cfg["P"], cfg["C"]
+    pts_h, _, _ = synth.covgain_inputs(1, P, 1, seed=5100)         # xyz ~ U[-0.5, 0.5]^3, occupancy ~ U[0.1, 1]
+    pts = pts_h.to(dev)
+    cams = synth.fibonacci_cameras(C)[None].contiguous().to(dev)
+    X_view = synth.sphere_cameras(1, 1.5, torch.Generator().manual_seed(51)).to(dev)
+    vis.load_state_dict(synth.seeded_state_dict(vis.state_dict(), 5))
+    base, h_polar, h_azim = scone_utils.get_all_harmonics_under_degree(8, 7, 14, dev)
+    shard = world > 1
+
+    def score(p, h, c):
+        if board is not None:
+            return board.step(p, h, c, use_sigmoid=vis.use_sigmoid)
+        s = vis.compute_coverage_gain(p, h, c)
+        return s, s.argmax(-1)
+
+    def run():
+        return nbv.scone_online_loop(vis, pts, cams, X_view, base, h_polar, h_azim, n_steps, score_step=score,
+                                     seq_len=seq_len, shard_clouds=shard)
+
+    nbv.scone_online_loop(vis, pts, cams, X_view, base, h_polar, h_azim, 2, score_step=score, seq_len=seq_len,
+                          shard_clouds=shard)                      # warm-up (workspaces, packs)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    chosen, _ = run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    chosen = chosen.clone()
+    same = True
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        ref = chosen.clone()
+        dist.broadcast(ref, 0)
+        ok = torch.tensor([int(torch.equal(ref, chosen))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        same = bool(ok.item())
+    out = {"steps": n_steps, "ms_per_step": ms / n_steps, "evals_per_s": C * n_steps / (ms * 1e-3),
+           "clouds": P // seq_len, "tokens_per_cloud": seq_len, "chosen_first8": chosen[:8].tolist(),
+           "distinct_cameras_chosen": int(chosen.unique().numel()),
+           "stages": "fused view state+harmonics (1 launch) -> SconeVis.forward on %d clouds%s -> scoring kernel with fused "
+                     "exchange + argmax -> device-side append of the chosen camera; no host synchronisation inside the loop"
+                     % (P // seq_len, " sharded over the ranks + NCCL all-gather of the harmonics" if shard else "")}
+    if world > 1:
+        out["same_sequence_on_all_ranks"] = same
+        if rank == 0:   # single-GPU rerun of the same loop on rank 0: the sharded loop must reproduce it bit for bit
+            solo, _ = nbv.scone_online_loop(vis, pts, cams, X_view, base, h_polar, h_azim, n_steps, seq_len=seq_len)
+            out["same_sequence_as_single_gpu"] = bool(torch.equal(solo, chosen))
     return out
 
 
@@ -322,8 +419,8 @@ def run_ours(args, cfg):
         # N > 1: every rank uploads 1/N of the point rows from pinned host memory and one NCCL all-gather over NVLink
         # completes the (replicated) point set on every GPU: each input byte crosses PCIe once, not N times
         p_h, h_h = pinned[i % 2]
-        pts = parallel.upload_rows_sharded(p_h[0], dev, buf=e2e_bufs[0])[None]
-        harm = parallel.upload_rows_sharded(h_h[0], dev, buf=e2e_bufs[1])[None]
+        pts = parallel.upload_rows_sharded(p_h.view(B * P, -1), dev, buf=e2e_bufs[0]).view(B, P, -1)
+        harm = parallel.upload_rows_sharded(h_h.view(B * P, 64), dev, buf=e2e_bufs[1]).view(B, P, 64)
         cam_d = cams_pin.to(dev, non_blocking=True)
         if board is not None:
             s, b = board.step(pts, harm, cam_d, use_sigmoid=vis.use_sigmoid)
@@ -333,9 +430,7 @@ def run_ours(args, cfg):
 
     e2e_bufs = [None, None]
     if world > 1:
-        if B != 1:
-            raise SystemExit("bench.py e2e at N > 1 is written for one cloud (B = 1)")
-        n_rows = -(-P // world) * world
+        n_rows = -(-(B * P) // world) * world
         e2e_bufs = [torch.empty((n_rows, host_sets[0][0].shape[-1]), device=dev), torch.empty((n_rows, 64), device=dev)]
 
     for i in range(2):
@@ -355,19 +450,54 @@ def run_ours(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = t.item()
 
-    # ---- parity of what was timed: last step's argmax vs the float64 closed form on a camera subset ----
+    # ---- parity of what was timed: the LAST timed step's scores for all C cameras against (i) the float64 closed
+    # form of the reference integrand (C + OpenMP restatement, oracle/c/sh_cov_f64.c: seconds for 102.8 M pairs),
+    # (ii) the reference's fp32 torch arithmetic (oracle/sh_cov.py) on a camera sample around the maximum, and
+    # (iii) at N > 1 the same kernel run by rank 0 alone over all C cameras (bitwise) ----
     check = None
+    single = None
+    if world > 1:
+        pts_d, harm_d = dev_sets[(args.warmup + args.steps - 1) % N_INPUT_SETS]
+        single = ops.coverage_gain(pts_d, harm_d, cams, use_sigmoid=vis.use_sigmoid) if rank == 0 else None
+        torch.cuda.synchronize()
     if rank == 0:
         import numpy as np
         from oracle import sh_cov
+        host_threads()
         pts_h, harm_h = host_sets[(args.warmup + args.steps - 1) % N_INPUT_SETS]
         got = scores.cpu().numpy()
         if board is not None:
             board.check()
-        top = np.argsort(-got[0])[:4].tolist()
-        truth = sh_cov.coverage_gain_f64(pts_h.numpy(), harm_h.numpy(), cams_h.numpy()[:, top])
-        check = {"nbv_index": int(best[0]), "max_abs_err_vs_f64_top4": float(np.abs(got[:, top] - truth).max()),
-                 "top1_is_argmax_of_truth": bool(np.argmax(truth[0]) == 0)}
+        t0 = time.perf_counter()
+        truth = sh_cov.coverage_gain_f64_c(pts_h.numpy(), harm_h.numpy(), cams_h.numpy(), use_sigmoid=vis.use_sigmoid)
+        t_truth = time.perf_counter() - t0
+        order = np.argsort(-truth, axis=-1)
+        check = {"nbv_index": [int(v) for v in best.reshape(-1).tolist()],
+                 "cameras_checked_vs_f64": int(B * C),
+                 "max_abs_err_vs_f64": float(np.abs(got - truth).max()),
+                 "argmax_equals_f64_argmax": bool((got.argmax(-1) == truth.argmax(-1)).all()),
+                 "f64_top1_minus_top2": float(np.min(np.take_along_axis(truth, order[:, :1], -1)
+                                                     - np.take_along_axis(truth, order[:, 1:2], -1))),
+                 "f64_check_seconds": t_truth}
+        if B * P <= 250_000:   # fp32 reference arithmetic on the 4 best cameras of cloud 0 (a few seconds on the host)
+            top = order[0, :4].tolist()
+            ref32 = sh_cov.coverage_gain(pts_h[:1], harm_h[:1], cams_h[:1, top].contiguous(), use_sigmoid=vis.use_sigmoid,
+                                         cam_chunk=max(1, 900_000 // P)).numpy()
+            check["max_abs_err_vs_reference_fp32_top4"] = float(np.abs(got[:1, top] - ref32).max())
+            check["reference_fp32_err_vs_f64_top4"] = float(np.abs(ref32 - truth[:1, top]).max())
+        if single is not None:
+            check["bitwise_equal_to_single_gpu"] = bool(torch.equal(single.cpu(), scores.cpu()))
+            check["argmax_equal_to_single_gpu"] = bool(torch.equal(single.argmax(-1).cpu(), best.reshape(-1).cpu()))
+
+    # ---- BASELINE.json configs[4] as the online loop SURVEY.md section 8d defines (cfg5 only): 50 NBV steps, each = view
+    # harmonics of all points for the cameras visited so far -> SconeVis.forward on 98 clouds of 2048 tokens -> score all
+    # C cameras (sharded) -> argmax -> the chosen camera joins the visited set.  Reported next to `value`.
+    loop = None
+    if args.workload == "cfg5" and not args.no_loop:
+        try:
+            loop = online_loop(args, cfg, dev, vis, board, world, rank)
+        except Exception as exc:  # informational: never lose the headline line
+            loop = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     if rank == 0:
         peaks, peak_src = load_peaks()
@@ -386,12 +516,8 @@ def run_ours(args, cfg):
             "metric": METRIC, "value": B * C * args.steps / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + cfg["desc"], "B": B, "P": P, "C": C,
-                       "parallelism": "camera axis sharded x%d (points replicated), 1 all-gather of scores" % world,
-                       "exchange": exchange,
-                       "cameras_per_gpu": n_local,
-                       "l2": "inputs rotate over %d distinct resident sets (%.0f MB > 126 MB L2)"
-                             % (N_INPUT_SETS, N_INPUT_SETS * B * P * 272 / 1e6)},
+            "config": make_config(args, cfg),
+            "exchange": exchange,
             "clocks": clocks,
             "e2e": {"value": B * C * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
@@ -413,6 +539,8 @@ def run_ours(args, cfg):
                                        "sm_mhz": sm_mhz}},
             "parity": check,
         }
+        if loop is not None:
+            line["loop"] = loop
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg)
         if world == 1 and not args.no_stages:
@@ -437,6 +565,7 @@ def main():
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the informational timings of the other path stages")
+    ap.add_argument("--no-loop", action="store_true", help="skip the 50-step online NBV loop figure (cfg5)")
     ap.add_argument("--nccl-gather", action="store_true", help="use the NCCL all_gather instead of the fused peer push")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup

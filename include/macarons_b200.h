@@ -261,12 +261,18 @@ int mac_sconeocc_forward_f32(const mac_sconeocc_w_t *w, const float *pc_global, 
  *       -> out (B, P, 64) = sum_j state_j * base_kj * sin(polar_j) * polar_step * azim_step.
  *   mac_gather_bins_f32     the bin permutation of move_view_state_to_view_space, scone_utils.py:928:
  *       out[b, p, j] = in[b, p, index[j]].
+ *   mac_viewstate_harm_f32  compute_view_state followed by compute_view_harmonics (the pair of calls at
+ *       /root/reference/macarons/testers/shapenet.py:126-131, utility/macarons_utils.py:2818-2877) in one pass:
+ *       pts (B, P, pts_dim), views (V, 3), base (64, n_bins), h_polar (n_bins) -> out (B, P, 64); the histogram
+ *       never reaches HBM; results are bitwise those of the two separate calls.
  * ------------------------------------------------------------------------------------------- */
 int mac_view_state_f32(const float *pts, int pts_dim, const float *views, float *state, int B, int P, int V, int n_elev,
                        int n_azim, void *stream);
 int mac_view_harmonics_f32(const float *state, const float *base, const float *h_polar, float *out, int B, int P,
                            int n_elev, int n_azim, void *stream);
 int mac_gather_bins_f32(const float *in, const int *index, float *out, int B, int P, int n_bins, void *stream);
+int mac_viewstate_harm_f32(const float *pts, int pts_dim, const float *views, const float *base, const float *h_polar,
+                           float *out, int B, int P, int V, int n_elev, int n_azim, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * sample_proxy_points (row a13), /root/reference/macarons/utility/scone_utils.py:1030-1076, with the uniforms

@@ -88,6 +88,9 @@ SYMBOLS["mac_view_harmonics_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, _c_f
                                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p])
 SYMBOLS["mac_gather_bins_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_int,
                                                  ctypes.c_int, ctypes.c_void_p])
+SYMBOLS["mac_viewstate_harm_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_void_p])
 SYMBOLS["mac_sample_proxy_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_int])
 SYMBOLS["mac_sample_proxy_points_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
                                                          ctypes.c_int, ctypes.c_float, _c_float_p, _c_float_p,

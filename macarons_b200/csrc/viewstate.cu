@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(256) view_state_kernel(const ViewStateParams p
 }
 
 // out[pt, k] = sum_j state[pt, j] * base[k, j] * sin(polar_j) * polar_step * azim_step
-// block: 32 points; W (n_bins x 64) rebuilt in shared memory per block (cheap: 6272 entries)
+// block: 32 points; W (n_bins x 64) rebuilt in shared memory per block (cheap: 6272 entries).  The state is a {0,1}
+// histogram with at most V non-zero bins: bins whose state is exactly 0 contribute an exact 0 and are skipped (the
+// branch is uniform: the 64 threads of a group share the point), the others keep the reference's multiply order.
 __global__ void __launch_bounds__(256) view_harmonics_kernel(const float *__restrict__ state, const float *__restrict__ base,
                                                              const float *__restrict__ h_polar, float *__restrict__ out,
                                                              long long n_pts, int n_bins, float polar_step, float azim_step)
@@ -116,7 +118,64 @@ __global__ void __launch_bounds__(256) view_harmonics_kernel(const float *__rest
         for (int q = g; q < n; q += 4) {
             const float *s = st + q * (n_bins + 1);
             float acc = 0.f;
-            for (int j = 0; j < n_bins; ++j) acc += (((s[j] * W[j * 64 + k]) * sinp[j]) * polar_step) * azim_step;
+            for (int j = 0; j < n_bins; ++j) {
+                const float sj = s[j];
+                if (sj != 0.f) acc += (((sj * W[j * 64 + k]) * sinp[j]) * polar_step) * azim_step;
+            }
+            out[(p0 + q) * 64 + k] = acc;
+        }
+    }
+}
+
+// Fused view state -> view harmonics (compute_view_state followed by compute_view_harmonics, scone_utils.py:799-860 and
+// :934-960) without the (B, P, n_bins) histogram in HBM: per point, the bins of the V visited cameras are OR-ed into a
+// 128-bit mask in shared memory (one thread per (point, view) pair), then every set bin j adds the table row
+// T[j][k] = ((1 * base[k][j]) * sin(polar_j)) * polar_step * azim_step  -- bit for bit the term the two-kernel path adds for a
+// state of 1.0, in the same ascending-bin order, so both paths give identical results.
+// Traffic: 4*pts_dim B read + 256 B written per point (vs + 2 * 4 * n_bins B for the materialised histogram).
+constexpr int kFusedPts = 64;  // points per block iteration
+__global__ void __launch_bounds__(256) viewstate_harm_kernel(const ViewStateParams p, const float *__restrict__ base,
+                                                             const float *__restrict__ h_polar, float *__restrict__ out,
+                                                             float polar_step, float azim_step)
+{
+    extern __shared__ float sm[];
+    const int n_bins = p.n_elev * p.n_azim;
+    float *T = sm;                                                        // [n_bins][64]
+    float *sviews = T + n_bins * 64;                                      // [V][3]
+    float *spts = sviews + 3 * p.V;                                       // [kFusedPts][3]
+    unsigned *mask = reinterpret_cast<unsigned *>(spts + 3 * kFusedPts);  // [kFusedPts][4]
+    for (int i = threadIdx.x; i < n_bins * 64; i += blockDim.x) {
+        const int j = i >> 6, k = i & 63;
+        T[i] = (((1.0f * base[k * n_bins + j]) * sinf(h_polar[j])) * polar_step) * azim_step;
+    }
+    for (int i = threadIdx.x; i < p.V * 3; i += blockDim.x) sviews[i] = p.views[i];
+    const int k = threadIdx.x & 63, g = threadIdx.x >> 6;
+    for (long long p0 = blockIdx.x * static_cast<long long>(kFusedPts); p0 < p.n_pts;
+         p0 += gridDim.x * static_cast<long long>(kFusedPts)) {
+        __syncthreads();   // previous iteration's masks consumed (and, first time, T / sviews written)
+        const int n = static_cast<int>(p.n_pts - p0 < kFusedPts ? p.n_pts - p0 : kFusedPts);
+        for (int i = threadIdx.x; i < n * 3; i += blockDim.x) spts[i] = p.pts[(p0 + i / 3) * p.pts_dim + i % 3];
+        for (int i = threadIdx.x; i < kFusedPts * 4; i += blockDim.x) mask[i] = 0u;
+        __syncthreads();
+        // view-major items: consecutive threads take consecutive points of the same view (conflict-free spts reads)
+        for (int i = threadIdx.x; i < n * p.V; i += blockDim.x) {
+            const int v = i / n, q = i - v * n;
+            const int b = view_bin(p, sviews[3 * v] - spts[3 * q], sviews[3 * v + 1] - spts[3 * q + 1],
+                                   sviews[3 * v + 2] - spts[3 * q + 2]);
+            atomicOr(&mask[q * 4 + (b >> 5)], 1u << (b & 31));
+        }
+        __syncthreads();
+        for (int q = g; q < n; q += 4) {
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                unsigned m = mask[q * 4 + w];
+                while (m) {   // ascending bins; uniform across the 64 threads of the group
+                    const int j = w * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    acc += T[j * 64 + k];
+                }
+            }
             out[(p0 + q) * 64 + k] = acc;
         }
     }
@@ -190,6 +249,42 @@ extern "C" int mac_gather_bins_f32(const float *in, const int *index, float *out
     const long long want = (total + 255) / 256;
     const int grid = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
     gather_bins_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, index, out, total, n_bins);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+extern "C" int mac_viewstate_harm_f32(const float *pts, int pts_dim, const float *views, const float *base,
+                                      const float *h_polar, float *out, int B, int P, int V, int n_elev, int n_azim,
+                                      void *stream)
+{
+    MAC_REQUIRE(pts && views && base && h_polar && out, "null tensor pointer");
+    MAC_REQUIRE(B > 0 && P > 0 && V >= 0 && pts_dim >= 3, "bad shape B=%d P=%d V=%d pts_dim=%d", B, P, V, pts_dim);
+    MAC_REQUIRE(n_elev > 0 && n_azim > 0 && n_elev * n_azim <= kMaxBins, "view state supports at most %d bins", kMaxBins);
+    MAC_REQUIRE(V <= 4096, "at most 4096 visited cameras per call (got %d)", V);
+    ViewStateParams p{};
+    p.pts = pts, p.views = views, p.state = nullptr;
+    p.n_pts = static_cast<long long>(B) * P;
+    p.pts_dim = pts_dim, p.V = V, p.n_elev = n_elev, p.n_azim = n_azim;
+    const double es = M_PI / (n_elev + 1), as = 2.0 * M_PI / n_azim;
+    p.elev_step = static_cast<float>(es), p.azim_step = static_cast<float>(as);
+    p.half_elev_step = static_cast<float>(es / 2.0), p.half_azim_step = static_cast<float>(as / 2.0);
+    p.elev_lo = -((n_elev + 1) / 2);
+    p.azim_hi = n_azim / 2;
+    p.azim_wrap = -((n_azim + 1) / 2);
+    p.elev_shift = n_elev / 2;
+    const int n_bins = n_elev * n_azim;
+    const size_t smem = (static_cast<size_t>(n_bins) * 64 + 3 * static_cast<size_t>(V) + 3 * kFusedPts) * sizeof(float) +
+                        kFusedPts * 4 * sizeof(unsigned);
+    static DeviceOnce once;
+    if (int rc = ensure_dynamic_smem(once, viewstate_harm_kernel, 96 * 1024)) return rc;
+    const long long want = (p.n_pts + kFusedPts - 1) / kFusedPts;
+    int device = 0;
+    MAC_CUDA(cudaGetDevice(&device));
+    const long long resident = static_cast<long long>(sm_count(device)) * 4;   // 4 CTAs / SM (<= 32 KB of table each)
+    const int grid = static_cast<int>(want < resident ? want : resident);
+    viewstate_harm_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        p, base, h_polar, out, static_cast<float>(M_PI / (n_elev + 1)), static_cast<float>(2.0 * M_PI / n_azim));
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return MAC_OK;

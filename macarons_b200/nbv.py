@@ -37,3 +37,69 @@ def scone_nbv_step(scone_occ, scone_vis, pc, X, X_view, X_cam, base_harmonics, h
         return cov, max_idx, {"view_state": view_state, "view_harmonics": view_harmonics, "occ": occ, "proxy": proxy,
                               "sample_idx": sample_idx, "harmonics": harmonics}
     return cov, max_idx
+
+
+def sconevis_forward_clouds(scone_vis, pts, view_harmonics, seq_len, group=None):
+    """SconeVis.forward over a large point set cut into clouds of `seq_len` tokens (the reference's network input
+    size, networks/SconeVis.py:7): pts (1, P, 4) and view_harmonics (1, P, 64) with P % seq_len == 0 -> (1, P, 64).
+    Every cloud is an independent forward, so with `group` (torch.distributed, one process per GPU) the clouds are
+    partitioned across the ranks and one all-gather over NVLink (NCCL) completes the replicated result; the output is
+    bitwise the same as the single-GPU batch (rows never mix across clouds)."""
+    import torch.distributed as dist
+    P = pts.shape[1]
+    if pts.shape[0] != 1 or P % seq_len != 0:
+        raise ValueError("pts must be (1, P, 4) with P a multiple of seq_len=%d (got %s)" % (seq_len, tuple(pts.shape)))
+    n_clouds = P // seq_len
+    clouds = pts.reshape(n_clouds, seq_len, pts.shape[-1])
+    vh = view_harmonics.reshape(n_clouds, seq_len, view_harmonics.shape[-1])
+    world = dist.get_world_size(group) if (group is not None or (dist.is_available() and dist.is_initialized())) else 1
+    if world == 1:
+        return scone_vis(clouds, view_harmonics=vh).reshape(1, P, -1)
+    rank = dist.get_rank(group)
+    per = -(-n_clouds // world)
+    out = torch.empty((world * per, seq_len, 64), dtype=torch.float32, device=pts.device)
+    lo, hi = min(rank * per, n_clouds), min((rank + 1) * per, n_clouds)
+    mine = out[rank * per:(rank + 1) * per]
+    if hi > lo:
+        mine[:hi - lo] = scone_vis(clouds[lo:hi], view_harmonics=vh[lo:hi])
+    dist.all_gather_into_tensor(out.view(-1), mine.reshape(-1), group=group)
+    return out[:n_clouds].reshape(1, P, 64)
+
+
+def scone_online_loop(scone_vis, pts, X_cam, X_view, base_harmonics, h_polar, h_azim, n_steps, score_step=None,
+                      n_elev=7, n_azim=14, seq_len=2048, shard_clouds=False):
+    """The large-scene online NBV loop of BASELINE.json configs[4], the loop body of reference
+    testers/shapenet.py:89-172 from the view state onwards on a fixed proxy-point set: for `n_steps` steps
+
+        view state + view harmonics of all points for the cameras visited so far   (scone_utils.py:799-860, :934-960)
+        -> SconeVis.forward on P / seq_len clouds                                     (networks/SconeVis.py:121-162)
+        -> coverage gain of every candidate camera over all P points, argmax        (SconeVis.py:210-252, shapenet.py:172)
+        -> the chosen camera joins the visited set                                  (shapenet.py:176-180)
+
+    pts (1, P, 4) [normalised xyz, occupancy], X_cam (1, C, 3), X_view (V0, 3).  `score_step(pts, harmonics, X_cam) ->
+    (scores (1, C), best (1,))` defaults to the single-GPU kernel; pass `PeerScoreBoard.step` for the camera-sharded
+    form.  Nothing synchronises with the host inside the loop (the chosen camera is appended on the device).
+    -> (chosen (n_steps,) int64, last scores (1, C))."""
+    from . import ops
+    if score_step is None:
+        def score_step(p, h, c):
+            s = ops.coverage_gain(p, h, c, use_sigmoid=scone_vis.use_sigmoid)
+            return s, torch.argmax(s, dim=-1)
+    with torch.no_grad():
+        V0 = X_view.shape[0]
+        views = torch.empty((V0 + n_steps, 3), dtype=torch.float32, device=pts.device)
+        views[:V0] = X_view
+        chosen = torch.empty((n_steps,), dtype=torch.int64, device=pts.device)
+        scores = None
+        for s in range(n_steps):
+            vh = scone_utils.compute_view_state_harmonics(pts, views[:V0 + s], base_harmonics, h_polar, h_azim, n_elev, n_azim)
+            if shard_clouds:
+                harmonics = sconevis_forward_clouds(scone_vis, pts, vh, seq_len)
+            else:
+                n_clouds = pts.shape[1] // seq_len
+                harmonics = scone_vis(pts.reshape(n_clouds, seq_len, -1),
+                                      view_harmonics=vh.reshape(n_clouds, seq_len, 64)).reshape(1, -1, 64)
+            scores, best = score_step(pts, harmonics, X_cam)
+            views[V0 + s] = X_cam[0].index_select(0, best.reshape(-1)[:1])[0]
+            chosen[s] = best.reshape(-1)[0]
+    return chosen, scores

@@ -356,6 +356,28 @@ def view_harmonics(state, base, h_polar, n_elev, n_azim):
     return out
 
 
+def view_state_harmonics(pts, X_view, base, h_polar, n_elev, n_azim):
+    """Fused compute_view_state + compute_view_harmonics: pts (B,P,>=3), X_view (V,3), base (64,n_bins),
+    h_polar (n_bins) -> (B,P,64), bitwise equal to view_harmonics(view_state(...)) without the (B,P,n_bins) tensor."""
+    for name, t in (("pts", pts), ("X_view", X_view), ("base_harmonics", base), ("h_polar", h_polar)):
+        _require_cuda_f32(name, t)
+    n_bins = n_elev * n_azim
+    if pts.dim() != 3 or pts.shape[-1] < 3 or X_view.dim() != 2 or X_view.shape[-1] != 3:
+        raise ValueError("pts must be (B,P,>=3) and X_view (V,3)")
+    if tuple(base.shape) != (N_HARMONICS, n_bins) or h_polar.numel() != n_bins:
+        raise ValueError("base_harmonics must be (64,%d) and h_polar (%d,)" % (n_bins, n_bins))
+    pts, X_view, base, h_polar = pts.contiguous(), X_view.contiguous(), base.contiguous(), h_polar.contiguous()
+    B, P, D = pts.shape
+    out = torch.empty((B, P, N_HARMONICS), dtype=torch.float32, device=pts.device)
+    if B * P == 0:
+        return out
+    with torch.cuda.device(pts.device):
+        _lib.check(_lib.load().mac_viewstate_harm_f32(pts.data_ptr(), D, X_view.data_ptr(), base.data_ptr(), h_polar.data_ptr(),
+                                                      out.data_ptr(), B, P, X_view.shape[0], int(n_elev), int(n_azim),
+                                                      _stream_ptr(pts.device)))
+    return out
+
+
 def gather_bins(state, index):
     """state (B,P,n_bins), index (n_bins) int -> state[..., index]."""
     _require_cuda_f32("view_state", state)

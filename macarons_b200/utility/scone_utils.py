@@ -96,6 +96,13 @@ def compute_view_harmonics(view_state, base_harmonics, h_polar, h_azim, n_elev, 
     return ops.view_harmonics(view_state, base_harmonics, h_polar, n_elev, n_azim)
 
 
+def compute_view_state_harmonics(pts, X_view, base_harmonics, h_polar, h_azim, n_elev, n_azim):
+    """compute_view_harmonics(compute_view_state(pts, X_view, ...), ...) in one kernel (extension; the pair of reference
+    calls at testers/shapenet.py:126-131): same result bit for bit, the (n_cloud, seq_len, n_bins) histogram is never
+    written to memory."""
+    return ops.view_state_harmonics(pts, X_view, base_harmonics, h_polar, n_elev, n_azim)
+
+
 def compute_occupancy_probability(scone_occ, pc, X, view_harmonics, mask=None, max_points_per_pass=20000):
     """pc (n_clouds, seq_len, 3), X (n_clouds, n_sample, 3), view_harmonics (n_clouds, n_sample, 64)
     -> (n_clouds, n_sample, 1).  Like the reference, the queries are cut into passes of

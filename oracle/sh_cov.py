@@ -229,3 +229,36 @@ def visibility_gains_f64(pts, harmonics, X_cam, use_sigmoid=True):
 
 def coverage_gain_f64(pts, harmonics, X_cam, use_sigmoid=True):
     return visibility_gains_f64(pts, harmonics, X_cam, use_sigmoid).mean(axis=-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# the same float64 closed form in C + OpenMP (oracle/c/sh_cov_f64.c): full benchmark shapes in seconds
+# ----------------------------------------------------------------------------------------------
+def _c_call(name, pts, harmonics, X_cam, use_sigmoid, per_point):
+    from . import cbuild
+    pts = np.ascontiguousarray(np.asarray(pts, dtype=np.float32))
+    H = np.ascontiguousarray(np.asarray(harmonics, dtype=np.float32))
+    cam = np.ascontiguousarray(np.asarray(X_cam, dtype=np.float32))
+    B, P, D = pts.shape
+    C = cam.shape[1]
+    assert H.shape == (B, P, N_HARMONICS) and cam.shape == (B, C, 3)
+    out = np.empty((B, C, P) if per_point else (B, C), dtype=np.float64)
+    import os
+    try:   # all cores this process may use, even when the launcher exported OMP_NUM_THREADS=1 (torchrun does)
+        cbuild.load().omp_set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    rc = getattr(cbuild.load(), name)(pts.ctypes.data, D, H.ctypes.data, cam.ctypes.data, B, P, C, int(bool(use_sigmoid)),
+                                      out.ctypes.data)
+    if rc != 0:
+        raise ValueError("%s: bad arguments" % name)
+    return out
+
+
+def coverage_gain_f64_c(pts, harmonics, X_cam, use_sigmoid=True):
+    """coverage_gain_f64 computed by the C restatement on all host threads (fp32 inputs, float64 arithmetic)."""
+    return _c_call("mac_oracle_coverage_f64", pts, harmonics, X_cam, use_sigmoid, False)
+
+
+def visibility_gains_f64_c(pts, harmonics, X_cam, use_sigmoid=True):
+    return _c_call("mac_oracle_visibility_f64", pts, harmonics, X_cam, use_sigmoid, True)
