@@ -57,18 +57,28 @@ def compute_view_state(pts, X_view, n_elev, n_azim):
     return ops.view_state(pts, X_view, n_elev, n_azim)
 
 
-def view_space_bin_permutation(R, n_elev, n_azim):
-    """The n_elev*n_azim gather indices of move_view_state_to_view_space for a camera with rotation R (3,3)
-    (pytorch3d row-vector convention X_view = X_world R + T).  The reference maps the unit bin directions through
-    the inverse world-to-view transform and subtracts the camera centre (:887-897); the translations cancel,
-    (X - T) R^T - (-T R^T) = X R^T, so only the rotation matters.  Binning as in :902-924 (NB the clamps here are
-    +-(n_elev // 2), unlike compute_view_state)."""
+def view_space_bin_permutation(R, n_elev, n_azim, T=None):
+    """The n_elev*n_azim gather indices of move_view_state_to_view_space for a camera with rotation R (3,3) and
+    translation T (3,) (pytorch3d row-vector convention X_view = X_world R + T).  Host-side set-up on 98 points that
+    follows the reference statement by statement (:876-926) so that the indices are the reference's, bin for bin, also
+    for directions that land on a bin boundary: unit bin directions -> inverse of the 4x4 world-to-view matrix
+    (`torch.inverse`, fp32, as pytorch3d's Transform3d.inverse) -> minus the camera centre -> spherical coordinates ->
+    nearest bin (NB the clamps here are +-(n_elev // 2), unlike compute_view_state)."""
     R = R.detach().to(device="cpu", dtype=torch.float32).view(3, 3)
+    T = torch.zeros(3) if T is None else T.detach().to(device="cpu", dtype=torch.float32).view(3)
     n_view = n_elev * n_azim
     elev = torch.Tensor([-90. + (i + 1) / (n_elev + 1) * 180. for i in range(n_elev) for _ in range(n_azim)])
     azim = torch.Tensor([360. * j / n_azim for _ in range(n_elev) for j in range(n_azim)])
     X_ref = get_cartesian_coords(r=torch.ones(n_view, 1), elev=elev.view(-1, 1), azim=azim.view(-1, 1), in_degrees=True)
-    X_inv = X_ref @ R.transpose(0, 1)
+    M = torch.zeros(4, 4)
+    M[:3, :3], M[3, :3], M[3, 3] = R, T, 1.0
+    M_inv = torch.inverse(M.view(1, 4, 4))[0]
+
+    def transform(points):   # Transform3d.transform_points: homogeneous row vectors, divide by w
+        out = torch.cat((points, torch.ones(points.shape[0], 1)), dim=-1) @ M_inv
+        return out[:, :3] / out[:, 3:]
+
+    X_inv = transform(X_ref) - transform(torch.zeros(1, 3))
     elev_step, azim_step = np.pi / (n_elev + 1), 2 * np.pi / n_azim
     _, ray_elev, ray_azim = get_spherical_coords(X_inv.view(-1, 3))
     idx_elev = (ray_elev - ray_elev % elev_step) / elev_step
@@ -84,9 +94,10 @@ def view_space_bin_permutation(R, n_elev, n_azim):
 
 
 def move_view_state_to_view_space(view_state, fov_camera, n_elev, n_azim):
-    """'Rotate' view states (n_cloud, seq_len, n_elev*n_azim) into the view space of `fov_camera` (any object with a
-    pytorch3d-style `.R` of shape (1,3,3))."""
-    indices = view_space_bin_permutation(fov_camera.R[0], n_elev, n_azim)
+    """'Rotate' view states (n_cloud, seq_len, n_elev*n_azim) into the view space of `fov_camera` (any object with
+    pytorch3d-style `.R` (1,3,3) and `.T` (1,3)): 98 gather indices on the host, one gather kernel."""
+    T = getattr(fov_camera, "T", None)
+    indices = view_space_bin_permutation(fov_camera.R[0], n_elev, n_azim, T=None if T is None else T[0])
     return ops.gather_bins(view_state, indices)
 
 

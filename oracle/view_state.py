@@ -6,7 +6,9 @@ Reference (paths relative to /root/reference/macarons):
   utility/utils.py:113-117            floor_divide  (x - x % d) / d
   utility/scone_utils.py:714-738      get_all_harmonics_under_degree
   utility/scone_utils.py:799-860      compute_view_state
+  utility/scone_utils.py:863-930      move_view_state_to_view_space
   utility/scone_utils.py:934-960      compute_view_harmonics
+  utility/CustomGeometry.py:5-24      get_cartesian_coords
 """
 import numpy as np
 import torch
@@ -81,3 +83,51 @@ def view_harmonics(state, base, h_polar, n_elev, n_azim, point_chunk=4096):
         polar = h_polar.view(1, 1, 1, n_bins).expand(B, n, n_h, -1)
         out.append(torch.sum(vals * base * torch.sin(polar) * polar_step * azim_step, dim=-1))
     return torch.cat(out, dim=1) if len(out) != 1 else out[0]
+
+
+def cartesian_coords(r, elev, azim, in_degrees=False):
+    """CustomGeometry.py:5-24: r, elev, azim (N,1) -> (N,3); x = cos(elev) sin(azim), y = sin(elev), z = cos(elev) cos(azim)."""
+    factor = 1
+    if in_degrees:
+        factor *= np.pi / 180.
+    X = torch.stack((torch.cos(factor * elev) * torch.sin(factor * azim),
+                     torch.sin(factor * elev),
+                     torch.cos(factor * elev) * torch.cos(factor * azim)), dim=2)
+    return r * X.view(-1, 3)
+
+
+def view_space_bin_indices(fov_camera, n_elev, n_azim):
+    """scone_utils.py:876-926: for every bin of the n_elev x n_azim sphere grid, the index of the bin its direction
+    falls into after mapping through the camera's inverse world-to-view transform minus the camera centre.
+    `fov_camera` is any object with pytorch3d's FoVPerspectiveCameras interface (oracle/cameras.py stands in for it,
+    pytorch3d itself is not installed: camera convention restated, see that file's header).
+    NB the elevation clamps are +-(n_elev // 2) here, unlike compute_view_state (:838-839 vs :914-915)."""
+    n_view = n_elev * n_azim
+    candidate_dist = torch.Tensor([1. for _ in range(n_view)])
+    candidate_elev = torch.Tensor([-90. + (i + 1) / (n_elev + 1) * 180. for i in range(n_elev) for _ in range(n_azim)])
+    candidate_azim = torch.Tensor([360. * j / n_azim for _ in range(n_elev) for j in range(n_azim)])
+    X_cam_ref = cartesian_coords(r=candidate_dist.view(-1, 1), elev=candidate_elev.view(-1, 1),
+                                 azim=candidate_azim.view(-1, 1), in_degrees=True)
+    X_cam_inv = fov_camera.get_world_to_view_transform().inverse().transform_points(X_cam_ref) \
+        - fov_camera.get_camera_center()
+    elev_step = np.pi / (n_elev + 1)
+    azim_step = 2 * np.pi / n_azim
+    _, ray_elev, ray_azim = spherical_coords(X_cam_inv.view(-1, 3))
+    ray_elev, ray_azim = ray_elev.view(n_view), ray_azim.view(n_view)
+    idx_elev = float_floor_divide(ray_elev, elev_step)
+    idx_azim = float_floor_divide(ray_azim, azim_step)
+    idx_elev = torch.where(ray_elev % elev_step > elev_step / 2., idx_elev + 1, idx_elev)
+    idx_azim = torch.where(ray_azim % azim_step > azim_step / 2., idx_azim + 1, idx_azim)
+    idx_elev = torch.where(idx_elev > n_elev // 2, torch.full_like(idx_elev, n_elev // 2), idx_elev)
+    idx_elev = torch.where(idx_elev < -(n_elev // 2), torch.full_like(idx_elev, -(n_elev // 2)), idx_elev)
+    idx_azim = torch.where(idx_azim > n_azim // 2, torch.full_like(idx_azim, -(n_azim // 2)), idx_azim)
+    idx_elev = idx_elev + n_elev // 2
+    idx_azim = torch.where(idx_azim < 0, idx_azim + n_azim, idx_azim)
+    return idx_elev.long() * n_azim + idx_azim.long()
+
+
+def move_view_state_to_view_space(state, fov_camera, n_elev, n_azim):
+    """scone_utils.py:863-930: gather the bins of every point's view state with view_space_bin_indices."""
+    n_clouds, seq_len = state.shape[0], state.shape[1]
+    indices = view_space_bin_indices(fov_camera, n_elev, n_azim)
+    return torch.gather(input=state, dim=2, index=indices.view(1, 1, -1).expand(n_clouds, seq_len, -1))

@@ -119,6 +119,32 @@ def view_state_goldens():
              state_bits=np.packbits(state.numpy().astype(np.uint8), axis=-1), view_harmonics=vh)
 
 
+def move_view_state_goldens():
+    """Row a12: the reference's move_view_state_to_view_space (scone_utils.py:863-930) run on the stand-in camera
+    (oracle/cameras.py; pytorch3d itself is not installed) for 24 seeded camera poses, incl. the identity and a pure
+    y-rotation.  Stored: the per-camera gather indices (recovered by feeding an arange 'state') and one rotated state."""
+    gen = torch.Generator().manual_seed(211)
+    aa = 1.5 * torch.randn(24, 3, generator=gen)
+    aa[0] = 0.0
+    aa[1] = torch.tensor([0.0, 2 * np.pi * 3 / 14, 0.0])
+    T = torch.randn(24, 3, generator=gen)
+    probe = torch.arange(98, dtype=torch.float32).view(1, 1, 98)
+    indices = []
+    for i in range(24):
+        cam = o_cams.FoVPerspectiveCameras(R=o_cams.axis_angle_to_matrix(aa[i:i + 1]), T=T[i:i + 1], zfar=100.0)
+        got = ref_su.move_view_state_to_view_space(probe, cam, 7, 14)
+        must_equal(got, o_vs.move_view_state_to_view_space(probe, cam, 7, 14), "move_view_state indices %d" % i)
+        indices.append(got.view(98).long())
+    pts, X_view = synth.view_state_inputs(2, 400, 6, 212)
+    state = ref_su.compute_view_state(pts, X_view, 7, 14)
+    cam = o_cams.FoVPerspectiveCameras(R=o_cams.axis_angle_to_matrix(aa[5:6]), T=T[5:6], zfar=100.0)
+    moved = ref_su.move_view_state_to_view_space(state, cam, 7, 14)
+    must_equal(moved, o_vs.move_view_state_to_view_space(state, cam, 7, 14), "move_view_state state")
+    save("move_view_state", seed=211, state_seed=212, axis_angle=aa, T=T, indices=torch.stack(indices),
+         state_bits=np.packbits(state.numpy().astype(np.uint8), axis=-1),
+         moved_bits=np.packbits(moved.numpy().astype(np.uint8), axis=-1), moved_camera=5)
+
+
 def sampling_goldens():
     gen = torch.Generator().manual_seed(301)
     N = 20000
@@ -327,11 +353,15 @@ if __name__ == "__main__":
     if "--macarons-only" in sys.argv:
         macarons_cov_goldens()
         raise SystemExit(0)
+    if "--move-view-state-only" in sys.argv:
+        move_view_state_goldens()
+        raise SystemExit(0)
     if "--nets-only" in sys.argv:
         nets_goldens()
         raise SystemExit(0)
     covgain_goldens()
     view_state_goldens()
+    move_view_state_goldens()
     sampling_goldens()
     nets_goldens()
     macarons_cov_goldens()

@@ -97,3 +97,16 @@ def test_argument_errors_without_gpu():
     with pytest.raises(NameError):       # number of cameras != number of depth maps (reference :2472-2473)
         mu.get_signed_distance_to_depth_maps(camera, s["X_world"], torch.zeros(3, 4, 4, 1), torch.ones(3, 4, 4, 1, dtype=torch.bool),
                                              fov_camera=cams)
+
+
+def test_view_space_bin_permutation_matches_reference_golden():
+    """Host side of row a12: the 98 gather indices the product derives on the host must equal, bin for bin, the indices
+    the reference function produced for the 24 golden camera poses (scone_utils.py:876-926)."""
+    from conftest import load_golden
+    from oracle import cameras as o_cams
+    from macarons_b200.utility import scone_utils
+    g = load_golden("move_view_state")
+    aa, T = torch.from_numpy(g["axis_angle"]), torch.from_numpy(g["T"])
+    for i in range(aa.shape[0]):
+        R = o_cams.axis_angle_to_matrix(aa[i:i + 1])[0]
+        assert np.array_equal(scone_utils.view_space_bin_permutation(R, 7, 14, T=T[i]).numpy(), g["indices"][i]), i

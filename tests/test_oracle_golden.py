@@ -103,6 +103,29 @@ def test_view_state_pole_bins_wrap():
     assert (up < 14).all() and (down >= 84).all()
 
 
+def _golden_cameras(g):
+    from oracle import cameras as o_cams
+    aa, T = torch.from_numpy(g["axis_angle"]), torch.from_numpy(g["T"])
+    return [o_cams.FoVPerspectiveCameras(R=o_cams.axis_angle_to_matrix(aa[i:i + 1]), T=T[i:i + 1], zfar=100.0)
+            for i in range(aa.shape[0])]
+
+
+def test_move_view_state_oracle_matches_reference_golden():
+    """Row a12 (scone_utils.py:863-930): gather indices for 24 camera poses and one rotated state, as produced by the
+    reference function itself on the stand-in camera."""
+    g = load_golden("move_view_state")
+    cams = _golden_cameras(g)
+    for i, cam in enumerate(cams):
+        assert np.array_equal(o_vs.view_space_bin_indices(cam, 7, 14).numpy(), g["indices"][i]), i
+    assert np.array_equal(g["indices"][0], np.arange(98))                       # identity rotation
+    i, j = np.arange(98) // 14, np.arange(98) % 14                              # +y rotation by 3 azimuth bins
+    shift = (g["indices"][1] % 14 - j) % 14    # the reference's own fp32 rounding moves a few bins by one more step
+    assert np.array_equal(g["indices"][1] // 14, i) and (shift == 3).mean() > 0.9 and set(shift.tolist()) <= {2, 3, 4}
+    state = torch.from_numpy(np.unpackbits(g["state_bits"], axis=-1)[..., :98].astype(np.float32))
+    moved = o_vs.move_view_state_to_view_space(state, cams[int(g["moved_camera"])], 7, 14)
+    assert np.array_equal(moved.numpy(), np.unpackbits(g["moved_bits"], axis=-1)[..., :98].astype(np.float32))
+
+
 def test_sampling_matches_golden():
     g = load_golden("sampling_20k")
     gen = torch.Generator().manual_seed(int(g["seed"]))
