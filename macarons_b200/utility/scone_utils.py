@@ -21,12 +21,15 @@ from .spherical_harmonics import clear_spherical_harmonics_cache, get_spherical_
 def get_all_harmonics_under_degree(degree, n_elev, n_azim, device):
     """-> (base (degree^2, n_elev*n_azim), h_polar, h_azim): the SH basis at the bin centres, bins elevation-major,
     elev_i = -pi/2 + (i+1) pi / (n_elev+1), azim_j = 2 pi j / n_azim."""
-    h_elev = torch.Tensor([-np.pi / 2 + (i + 1) / (n_elev + 1) * np.pi for i in range(n_elev) for _ in range(n_azim)]).to(device)
+    # 98 bin centres x 64 basis functions, once per run: evaluated on the host (the reference's torch CPU arithmetic,
+    # ~1000 tiny element-wise ops) and copied to `device`, instead of ~1000 device launches of a few threads each
+    h_elev = torch.Tensor([-np.pi / 2 + (i + 1) / (n_elev + 1) * np.pi for i in range(n_elev) for _ in range(n_azim)])
     h_polar = -h_elev + np.pi / 2
-    h_azim = torch.Tensor([2 * np.pi * j / n_azim for _ in range(n_elev) for j in range(n_azim)]).to(device)
+    h_azim = torch.Tensor([2 * np.pi * j / n_azim for _ in range(n_elev) for j in range(n_azim)])
     clear_spherical_harmonics_cache()
     z = torch.cat([get_spherical_harmonics(l, h_polar, h_azim) for l in range(degree)], dim=-1)
-    return z.transpose(dim0=0, dim1=1), h_polar, h_azim
+    clear_spherical_harmonics_cache()
+    return z.transpose(dim0=0, dim1=1).contiguous().to(device), h_polar.to(device), h_azim.to(device)
 
 
 def get_cameras_on_sphere(params, device, pole_cameras=False, n_elev=None, n_azim=None, camera_dist=None):

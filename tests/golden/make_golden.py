@@ -342,10 +342,39 @@ def depth_goldens():
              disp3=d3, disp4=d4)
 
 
+# full-resolution cases (BASELINE.json configs[2]: 256x256; reference default 256x456): the four disparity maps are
+# stored sub-sampled (row / column strides 8, 4, 2, 1 -> 32 x W/8 values each) to keep the fixtures small
+DEPTH_FULL_CASES = [("depth_256x456", 1, 256, 456, 603), ("depth_256x256", 1, 256, 256, 604)]
+DEPTH_FULL_STRIDES = (8, 4, 2, 1)
+
+
+def depth_full_goldens():
+    import warnings
+    warnings.filterwarnings("ignore", message="Default grid_sample")
+    for name, B, H, W, seed in DEPTH_FULL_CASES:
+        model = reference_many_depth(H, W)
+        sd = synth.seeded_state_dict(model.state_dict(), NET_WEIGHT_SEED)
+        model.load_state_dict(sd)
+        x, x_alpha, R, T, zfar, gt_pose = synth.depth_inputs(B, H, W, seed)
+        with torch.no_grad():
+            pose, d1, d2, d3, d4 = model(x, x_alpha, R, T, zfar, "cpu", gt_pose=gt_pose)
+            o = o_depth.many_depth_forward(sd, x, x_alpha, R, T, zfar, gt_pose)
+        for a, b, what in zip((pose, d1, d2, d3, d4), o, ("pose", "disp1", "disp2", "disp3", "disp4")):
+            must_equal(a, b, name + " " + what)
+        st = DEPTH_FULL_STRIDES
+        save(name, B=B, H=H, W=W, seed=seed, weight_seed=NET_WEIGHT_SEED, weights_digest=synth.state_dict_digest(sd),
+             input_digest=digest(x, x_alpha, gt_pose), strides=np.asarray(st),
+             disp1=d1[..., ::st[0], ::st[0]], disp2=d2[..., ::st[1], ::st[1]], disp3=d3[..., ::st[2], ::st[2]],
+             disp4=d4[..., ::st[3], ::st[3]])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     if "--depth-only" in sys.argv:
         depth_goldens()
+        raise SystemExit(0)
+    if "--depth-full-only" in sys.argv:
+        depth_full_goldens()
         raise SystemExit(0)
     if "--depth-io-only" in sys.argv:
         depth_io_goldens()
@@ -367,4 +396,5 @@ if __name__ == "__main__":
     macarons_cov_goldens()
     depth_io_goldens()
     depth_goldens()
+    depth_full_goldens()
     print("all oracle == reference checks passed (bitwise)")

@@ -35,8 +35,37 @@ def _worker(rank, world, port, ret):
             s, b = board.step(*d)
             board.check()
             ok_fused = ok_fused and torch.equal(s, full) and torch.equal(b, full.argmax(-1))
+        # B = 32 clouds (BASELINE config 4 shape, reduced): sharded == single GPU bit for bit
+        pts4, harm4, cams4 = synth.covgain_inputs(8, 512, 64, seed=78)
+        d4 = [t.to(dev) for t in (pts4, harm4, cams4)]
+        full4 = ops.coverage_gain(*d4)
+        board4 = parallel.PeerScoreBoard(8, 64, dev)
+        s4, b4 = board4.step(*d4)
+        board4.check()
+        ok_fused = ok_fused and torch.equal(s4, full4) and torch.equal(b4, full4.argmax(-1))
+        # online loop: clouds of the SconeVis forward sharded over the ranks + camera-sharded scoring reproduces the
+        # single-GPU loop (same chosen camera sequence, same final scores)
+        import contextlib
+        import io
+        from macarons_b200 import nbv
+        from macarons_b200.networks.SconeVis import SconeVis
+        from macarons_b200.utility import scone_utils
+        with contextlib.redirect_stdout(io.StringIO()):
+            vis = SconeVis()
+        vis.load_state_dict(synth.seeded_state_dict(vis.state_dict(), 5))
+        vis = vis.to(dev).eval()
+        ptsL = synth.covgain_inputs(1, 5 * 256, 1, seed=79)[0].to(dev)
+        camsL = synth.fibonacci_cameras(37)[None].contiguous().to(dev)
+        view0 = synth.sphere_cameras(1, 1.5, torch.Generator().manual_seed(3)).to(dev)
+        base, h_polar, h_azim = scone_utils.get_all_harmonics_under_degree(8, 7, 14, dev)
+        boardL = parallel.PeerScoreBoard(1, 37, dev)
+        solo, solo_scores = nbv.scone_online_loop(vis, ptsL, camsL, view0, base, h_polar, h_azim, 6, seq_len=256)
+        shard, shard_scores = nbv.scone_online_loop(vis, ptsL, camsL, view0, base, h_polar, h_azim, 6, seq_len=256,
+                                                    score_step=lambda p, h, c: boardL.step(p, h, c), shard_clouds=True)
+        boardL.check()
+        ok_loop = torch.equal(solo, shard) and torch.equal(solo_scores, shard_scores)
         out = [None] * world
-        dist.all_gather_object(out, (ok_nccl, ok_fused))
+        dist.all_gather_object(out, (ok_nccl, ok_fused and ok_loop))
         if rank == 0:
             ret.put(out)
     finally:

@@ -88,6 +88,63 @@ def test_sconeocc_forward(name, cuda_device):
     assert ((got > 0.1) != (want > 0.1))[..., 0][agree].float().mean().item() <= 1e-3
 
 
+def test_sconeocc_64cube_against_oracle_subset(cuda_device):
+    """BASELINE.json configs[1]: 4096-point cloud, 64^3 = 262 144 queries in ONE forward (max_points_per_pass = 300 000,
+    configs/scone/coverage_gain/coverage_gain_pretraining_config.json:27).  The oracle evaluates a random subset of 4096
+    queries with the same RNG draws (the sub-samples of a forward depend on the cloud size only, SconeOcc.py:269, :311);
+    a query's output does not depend on the other queries."""
+    g = load_golden("sconeocc_cfg1")
+    occ, sd = _load(SconeOcc(), g, cuda_device)
+    gen = torch.Generator().manual_seed(6464)
+    pc = synth.airplane_surface(4096, gen)[None]
+    lin = (torch.arange(64, dtype=torch.float32) + 0.5) / 64 - 0.5
+    x = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), dim=-1).view(1, -1, 3)
+    vh = 0.3 * torch.randn(1, 64 ** 3, 64, generator=gen)
+    subset = torch.randperm(64 ** 3, generator=gen)[:4096]
+    torch.manual_seed(64)
+    with torch.no_grad():
+        got = scone_utils.compute_occupancy_probability(occ, pc.to(cuda_device), x.to(cuda_device), vh.to(cuda_device),
+                                                        max_points_per_pass=300000).cpu()
+    torch.manual_seed(64)
+    with torch.no_grad():
+        want = o_nets.scone_occ_forward(sd, pc, x[:, subset], vh[:, subset])
+    assert got.shape == (1, 64 ** 3, 1) and torch.isfinite(got).all()
+    agree = _knn_agreement(occ, pc, x[:, subset], 64, cuda_device)
+    scale = max(1.0, want.abs().max().item())
+    err = (got[:, subset] - want).abs()[..., 0]
+    print("SconeOcc 64^3 subset: kNN sets agree on %.4f of queries; max err (agreeing) %.2e, overall %.2e, scale %.2f"
+          % (agree.float().mean().item(), err[agree].max().item(), err.max().item(), scale))
+    assert agree.float().mean().item() >= 0.99
+    assert err[agree].max().item() <= NET_RTOL * scale
+    assert err.max().item() <= 0.05 * scale
+    assert ((got[:, subset] > 0.1) != (want > 0.1))[..., 0][agree].float().mean().item() <= 1e-3
+
+
+def test_knn16_sets_against_float64(cuda_device):
+    """Index work vs the exact answer: the 16-NN SETS of the CUDA kernel and of the reference's fp32 arithmetic
+    (cdist + topk, utils.py:1497-1509) against a float64 cdist.  The kernel sums (x-y)^2 directly (exact fp32
+    distances), cdist uses |x|^2 + |y|^2 - 2xy (cancellation): where the two fp32 paths disagree the 16th and 17th
+    neighbours are closer than that rounding.  Both mismatch rates are printed and bounded; the kernel must not be
+    further from float64 than the reference is."""
+    gen = torch.Generator().manual_seed(161)
+    x = torch.rand(1, 20000, 3, generator=gen) - 0.5
+    pc = torch.rand(1, 4096, 3, generator=gen) - 0.5
+    got = ops.knn16(x.to(cuda_device), pc.to(cuda_device), return_dists=False).cpu().long().sort(-1)[0]
+    ref32 = o_nets.knn_points(x, pc, 16)[2].sort(-1)[0]
+    d64 = torch.cdist(x.double(), pc.double())
+    truth = d64.topk(16, dim=-1, largest=False)[1].sort(-1)[0]
+    cuda_bad = (got != truth).any(-1).float().mean().item()
+    ref_bad = (ref32 != truth).any(-1).float().mean().item()
+    print("kNN sets differing from float64: CUDA %.2e, reference fp32 %.2e; CUDA vs reference %.2e"
+          % (cuda_bad, ref_bad, (got != ref32).any(-1).float().mean().item()))
+    assert cuda_bad <= ref_bad + 1e-4 and ref_bad <= 5e-3
+    # every disagreement with float64 is a near-tie between the 16th and 17th neighbour
+    bad = (got != truth).any(-1)[0]
+    if bad.any():
+        top17 = d64[0, bad].topk(17, dim=-1, largest=False)[0]
+        assert ((top17[:, 16] - top17[:, 15]) <= 1e-6).all()
+
+
 def test_sconeocc_is_chunk_invariant(cuda_device):
     g = load_golden("sconeocc_small")
     occ, _ = _load(SconeOcc(), g, cuda_device)

@@ -45,6 +45,19 @@ def test_float64_closed_form_matches_golden(name):
     assert np.abs(cov64 - g["coverage"]).max() <= COVERAGE_ATOL * max(1.0, scale)
 
 
+@pytest.mark.parametrize("name", COVGAIN_CASES)
+def test_c_float64_oracle_equals_numpy_closed_form(name):
+    """oracle/c/sh_cov_f64.c (OpenMP, used for full benchmark shapes) against oracle/sh_cov.py's numpy closed form."""
+    g = load_golden(name)
+    pts, harm, cams = _inputs(g)
+    sig = bool(g["use_sigmoid"])
+    a = sh_cov.visibility_gains_f64(pts.numpy(), harm.numpy(), cams.numpy(), use_sigmoid=sig)
+    b = sh_cov.visibility_gains_f64_c(pts.numpy(), harm.numpy(), cams.numpy(), use_sigmoid=sig)
+    assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(a).max())
+    c = sh_cov.coverage_gain_f64_c(pts.numpy(), harm.numpy(), cams.numpy(), use_sigmoid=sig)
+    assert np.abs(c - a.mean(-1)).max() <= 1e-12 * max(1.0, np.abs(a).max())
+
+
 def test_reference_fp32_conditioning():
     """Documents the reference's own fp32 error on per-point values (see tests/tolerances.py)."""
     g = load_golden("covgain_cfg2_sigmoid")

@@ -193,6 +193,36 @@ def test_sample_proxy_points_matches_reference_golden(cuda_device):
     assert torch.all(res[:, 3] > float(g["min_occ"]))
 
 
+def test_sample_proxy_draws_against_float64(cuda_device):
+    """Index work vs the exact answer: the 2048 draws of the CUDA sampler and of the reference's fp32 arithmetic
+    (fp32 cumsum of fp32 quotients, scone_utils.py:1046-1056) against an inverse-CDF look-up in float64.  A draw can
+    only differ where its uniform is within fp32 rounding of a CDF step; both sides' mismatch rates against float64 are
+    printed and bounded."""
+    gen = torch.Generator().manual_seed(909)
+    N, n_sample = 100000, 2048
+    X = torch.rand(N, 3, generator=gen) - 0.5
+    preds = torch.rand(N, 1, generator=gen)
+    vh = torch.randn(N, 64, generator=gen)
+    bad_cuda = bad_ref = total = 0
+    for rep in range(8):
+        u = torch.rand(n_sample, generator=gen)
+        res, _, inv = scone_utils.sample_proxy_points(X.to(cuda_device), preds.to(cuda_device), vh.to(cuda_device), n_sample,
+                                                      0.1, return_index=True, samples=u.to(cuda_device))
+        want_res, _, want_inv = o_sampling.sample_proxy_points(X, preds, vh, n_sample, 0.1, u=u)
+        keep = preds[:, 0] > 0.1
+        p64 = preds[keep, 0].double()
+        cdf64 = torch.cumsum(p64 / p64.sum(), dim=0)
+        pick = torch.searchsorted(cdf64, u.double()).clamp(max=cdf64.numel() - 1)
+        truth = torch.cat((X[keep][pick], preds[keep][pick]), dim=-1)
+        bad_cuda += (res.cpu()[inv.cpu()] != truth).any(-1).sum().item()
+        bad_ref += (want_res[want_inv] != truth).any(-1).sum().item()
+        total += n_sample
+    print("proxy draws differing from the float64 inverse CDF: CUDA %.2e, reference fp32 %.2e (of %d draws)"
+          % (bad_cuda / total, bad_ref / total, total))
+    assert bad_cuda / total <= 5e-3 and bad_ref / total <= 5e-3
+    assert bad_cuda <= 2 * bad_ref + 8       # the kernel is not further from the exact draw than the reference is
+
+
 def test_sample_proxy_points_edge_cases(cuda_device):
     gen = torch.Generator().manual_seed(8)
     X = torch.rand(50, 3, generator=gen)
