@@ -240,6 +240,8 @@ def path_stages(dev):
         views = synth.sphere_cameras(10, 1.5, torch.Generator().manual_seed(1)).to(dev)
         out["view_state_plus_harmonics_200704_pts_10_views_ms"] = timed(lambda: scone_utils.compute_view_harmonics(
             scone_utils.compute_view_state(big, views, 7, 14), base, h_polar, h_azim, 7, 14))
+        out["view_state_harmonics_fused_200704_pts_10_views_ms"] = timed(lambda: scone_utils.compute_view_state_harmonics(
+            big, views, base, h_polar, h_azim, 7, 14), iters=10)
         resnet = MD.ResNet18Trunk()
         depth = MD.ManyDepth(MD.DepthDecoder(MD.FeatureExtractor(resnet), resnet), None)
         depth.load_state_dict(synth.seeded_state_dict(depth.state_dict(), 5))
@@ -436,6 +438,18 @@ def run_ours(args, cfg):
     for i in range(2):
         e2e_step(i)
     barrier()
+    # the floor of this box's host link: the same bytes, pinned host -> device, plain async copies, nothing else
+    floor_each = []
+    if world == 1:
+        dst = [torch.empty_like(t, device=dev) for t in pinned[0]]
+        for i in range(7):
+            torch.cuda.synchronize()
+            t_i = time.perf_counter()
+            for d_t, s_t in zip(dst, pinned[i % 2]):
+                d_t.copy_(s_t, non_blocking=True)
+            torch.cuda.synchronize()
+            floor_each.append(1e3 * (time.perf_counter() - t_i))
+        del dst
     t0 = time.perf_counter()
     e2e_each = []
     for i in range(e2e_steps):
@@ -522,6 +536,7 @@ def run_ours(args, cfg):
             "e2e": {"value": B * C * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "ms_per_step_median": e2e_median_ms,
+                    "pinned_h2d_copy_alone_ms": statistics.median(floor_each[2:]) if floor_each else None,
                     "api": ("mac_covgain_host (C ABI, pinned HOST buffers in, host scores out; 8 H2D slices overlapped with the "
                             "kernel) + argmax on the host") if world == 1 else
                            "pinned host tensors -> each rank uploads 1/N of the point rows + NCCL all-gather over NVLink "

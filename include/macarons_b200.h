@@ -80,6 +80,16 @@ int mac_visibility_f32(const float *pts, int pts_dim, const float *harmonics, co
                        float *out, int B, int P, int C, int cam_begin, int cam_end, int act,
                        void *stream);
 
+/* Backward of mac_covgain_f32 (per_point = 0: grad_out (B, C)) and of mac_visibility_f32 (per_point = 1: grad_out
+ * (B, C, P)) with respect to the harmonics: grad_harmonics (B, P, 64) = sum over ALL C cameras of
+ * grad * act'(z) * Y_k(ray).  This is what autograd computes through SconeVis.compute_coverage_gain /
+ * compute_visibilities (/root/reference/macarons/networks/SconeVis.py:164-252) in the reference's training loops
+ * (/root/reference/macarons/trainers/pretrain_scone_vis.py:162-225, train_macarons.py:423-444), where the points and
+ * the camera positions are data (no gradient).  Deterministic (fixed summation order). */
+int mac_covgain_backward_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams,
+                             const float *grad_out, float *grad_harmonics, int B, int P, int C, int act, int per_point,
+                             void *stream);
+
 /* Host-buffer form of mac_covgain_f32 (the call a non-torch caller makes): copies pts/harmonics/
  * cams to the device `device` (pinned staging is the caller's business), runs the kernel, copies
  * the [cam_begin, cam_end) columns of `out` back and synchronises.  Device buffers are cached per

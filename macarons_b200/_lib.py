@@ -32,6 +32,10 @@ SYMBOLS = {
 }
 
 
+SYMBOLS["mac_covgain_backward_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                      ctypes.c_void_p])
+
 MAX_PEERS = 16
 
 

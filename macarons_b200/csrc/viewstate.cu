@@ -110,17 +110,23 @@ __global__ void __launch_bounds__(256) view_harmonics_kernel(const float *__rest
     float *sinp = st + 32 * (n_bins + 1);  // [n_bins]
     for (int j = threadIdx.x; j < n_bins; j += blockDim.x) sinp[j] = sinf(h_polar[j]);
     const int k = threadIdx.x & 63, g = threadIdx.x >> 6;  // 4 point groups x 64 coefficients
+    const int lane = threadIdx.x & 31;
     for (long long p0 = blockIdx.x * 32ll; p0 < n_pts; p0 += gridDim.x * 32ll) {
         __syncthreads();
         const int n = static_cast<int>(n_pts - p0 < 32 ? n_pts - p0 : 32);
         for (int i = threadIdx.x; i < n * n_bins; i += blockDim.x) st[(i / n_bins) * (n_bins + 1) + i % n_bins] = state[p0 * n_bins + i];
         __syncthreads();
-        for (int q = g; q < n; q += 4) {
+        for (int q = g; q < n; q += 4) {   // q is uniform across each warp (a group = 2 warps)
             const float *s = st + q * (n_bins + 1);
             float acc = 0.f;
-            for (int j = 0; j < n_bins; ++j) {
-                const float sj = s[j];
-                if (sj != 0.f) acc += (((sj * W[j * 64 + k]) * sinp[j]) * polar_step) * azim_step;
+            for (int j0 = 0; j0 < n_bins; j0 += 32) {
+                unsigned m = __ballot_sync(0xffffffffu, j0 + lane < n_bins && s[j0 + lane] != 0.f);
+                while (m) {   // ascending bins; products rounded one by one like the reference's element-wise torch ops
+                    const int j = j0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const float term = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(s[j], W[j * 64 + k]), sinp[j]), polar_step), azim_step);
+                    acc = __fadd_rn(acc, term);
+                }
             }
             out[(p0 + q) * 64 + k] = acc;
         }
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(256) viewstate_harm_kernel(const ViewStatePara
     unsigned *mask = reinterpret_cast<unsigned *>(spts + 3 * kFusedPts);  // [kFusedPts][4]
     for (int i = threadIdx.x; i < n_bins * 64; i += blockDim.x) {
         const int j = i >> 6, k = i & 63;
-        T[i] = (((1.0f * base[k * n_bins + j]) * sinf(h_polar[j])) * polar_step) * azim_step;
+        T[i] = __fmul_rn(__fmul_rn(__fmul_rn(base[k * n_bins + j], sinf(h_polar[j])), polar_step), azim_step);
     }
     for (int i = threadIdx.x; i < p.V * 3; i += blockDim.x) sviews[i] = p.views[i];
     const int k = threadIdx.x & 63, g = threadIdx.x >> 6;
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(256) viewstate_harm_kernel(const ViewStatePara
                 while (m) {   // ascending bins; uniform across the 64 threads of the group
                     const int j = w * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    acc += T[j * 64 + k];
+                    acc = __fadd_rn(acc, T[j * 64 + k]);
                 }
             }
             out[(p0 + q) * 64 + k] = acc;

@@ -45,4 +45,4 @@ class Macarons(nn.Module):
         clear_spherical_harmonics_cache()
         if not self.visibility.use_sigmoid:
             raise NameError("WARNING! ReLU has been used in visibility model.")
-        return ops.visibility_gains(pts, harmonics, X_cam, use_sigmoid=True)
+        return ops.sh_integration(pts, harmonics, X_cam, use_sigmoid=True, per_point=True)

