@@ -259,6 +259,22 @@ int mac_sconeocc_forward_f32(const mac_sconeocc_w_t *w, const float *pc_global, 
                              const int *n_scale_pts, const float *x, const float *view_harmonics, float *out, int B,
                              int Q, int chunk, void *workspace, size_t workspace_bytes, void *stream);
 
+/* SconeOcc over a ragged batch of cells: the per-cell `macarons(mode='occupancy', ...)` calls of
+ * compute_scene_occupancy_probability_field, /root/reference/macarons/utility/macarons_utils.py:1443-1518 (one call per
+ * occupied cell, each with its own neighbourhood cloud and sub-samples) as ONE forward.
+ *   pc_global (n_cells, Sg, 3): the <= seq_len global-transformer points of every cell, zero rows after lens_g[c]
+ *   lens_g (n_cells) device ints
+ *   pc_scale[s] (total_s, 3), scale_off[s] (n_cells + 1 device ints): the clouds of all cells at scale s, concatenated,
+ *       cell c = rows [scale_off[s][c], scale_off[s][c+1]) (>= 16 each); pc_scale / scale_off are HOST arrays of 3 pointers
+ *   x (Qtot, 3), view_harmonics (Qtot, 64): the queries of all cells, cell-major; q_off (n_cells + 1 device ints);
+ *   cell_of_q (Qtot device ints); max_q = largest number of queries of one cell
+ *   -> out (Qtot) occupancy values; per query the arithmetic of mac_sconeocc_forward_f32 on its own cell. */
+size_t mac_sconeocc_cells_workspace_bytes(int n_cells, int Sg, int chunk, long long Qtot);
+int mac_sconeocc_forward_cells_f32(const mac_sconeocc_w_t *w, int n_cells, const float *pc_global, int Sg, const int *lens_g,
+                                   const float *const *pc_scale, const int *const *scale_off, const float *x,
+                                   const float *view_harmonics, const int *q_off, const int *cell_of_q, int max_q, float *out,
+                                   long long Qtot, int chunk, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * View state (rows a10-a12): spherical histogram of the visited cameras around every point and its
  * projection onto the SH basis.
@@ -312,6 +328,11 @@ int mac_sample_proxy_points_f32(const float *X, const float *preds, const float 
  *      mac_sample_proxy_points_f32 (rows >= counts[2c+1] are left untouched), counts (C, 2) = (points kept, unique
  *      picks), volume (C) = sum of the kept occupancies (`fov_proxy_volume`, :1621; may be null).
  * ------------------------------------------------------------------------------------------- */
+/* Camera.get_points_in_fov for ONE camera, /root/reference/macarons/utility/macarons_utils.py:2400-2435:
+ * X (N, 3), cam (36 floats, same layout as a row of `cams` above), ndc_bounds (HOST, 4 floats), fov_range < 0 = no range
+ * test -> mask (N) bytes, 1 where the point projects inside the image, lies in front of the camera and within range. */
+int mac_points_in_fov_f32(const float *X, const float *cam, const float *ndc_bounds, float fov_range, int N,
+                          unsigned char *mask, void *stream);
 size_t mac_fov_sample_proxy_workspace_bytes(int N, int C);
 int mac_fov_sample_proxy_f32(const float *X, const float *preds, const float *view_harmonics, const float *cams,
                              const float *ndc_bounds, float fov_range, float min_occ, const float *u, int N, int C,

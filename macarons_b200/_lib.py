@@ -86,6 +86,14 @@ SYMBOLS["mac_sconeocc_forward_f32"] = (ctypes.c_int, [ctypes.c_void_p, _c_float_
                                                       ctypes.c_void_p])
 
 
+SYMBOLS["mac_sconeocc_cells_workspace_bytes"] = (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong])
+SYMBOLS["mac_sconeocc_forward_cells_f32"] = (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_float_p, ctypes.c_int,
+                                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_float_p,
+                                                            _c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                            _c_float_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p,
+                                                            ctypes.c_size_t, ctypes.c_void_p])
+
+
 SYMBOLS["mac_view_state_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p])
 SYMBOLS["mac_view_harmonics_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
@@ -105,6 +113,10 @@ SYMBOLS["mac_fov_sample_proxy_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, _c
                                                       ctypes.c_float, ctypes.c_float, _c_float_p, ctypes.c_int, ctypes.c_int,
                                                       ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p,
                                                       _c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])
+
+
+SYMBOLS["mac_points_in_fov_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int,
+                                                   ctypes.c_void_p, ctypes.c_void_p])
 
 
 SYMBOLS["mac_unproject_depth_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -7,6 +7,11 @@
 namespace mac {
 
 int knn16(const float *x, const float *pc, int *idx, float *dist, int B, int Q, int N, cudaStream_t stream);
+// ragged batch of cells: queries [q_off[c], q_off[c+1]) against points [n_off[c], n_off[c+1]) of a concatenated cloud;
+// writes GLOBAL point rows (offsets on the device, n_cells + 1 ints each; max_q = largest query count of a cell)
+int knn16_cells(const float *x, const float *pc, const int *q_off, const int *n_off, int *idx, int n_cells, int max_q,
+                cudaStream_t stream);
+int gather_rows(const float *table, const int *row_of, float *out, long long rows, int N, cudaStream_t stream);
 int embed_first(const float *in, int ld_in, int in_dim, const float *pc, const float *x, const int *idx, int Q, int N,
                 const float *w, const float *b, int inner, int append, float *out, int ldo, long long T,
                 cudaStream_t stream);

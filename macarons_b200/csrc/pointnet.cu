@@ -93,6 +93,72 @@ __global__ void __launch_bounds__(64) knn16_kernel(const float *__restrict__ x, 
     }
 }
 
+// Ragged form for a batch of cells: cell c owns the queries [q_off[c], q_off[c+1]) of one flat
+// query array and the points [n_off[c], n_off[c+1]) of one concatenated cloud; the indices written are GLOBAL rows of the
+// concatenated cloud, so the neighbour gather of embed_first works on the flat arrays.  Same scan as knn16_kernel.
+__global__ void __launch_bounds__(64) knn16_cells_kernel(const float *__restrict__ x, const float *__restrict__ pc,
+                                                          const int *__restrict__ q_off, const int *__restrict__ n_off,
+                                                          int *__restrict__ idx_out)
+{
+    __shared__ float sp[kKnnTile * 3];
+    const int c = blockIdx.y;
+    const int q0 = q_off[c], Q = q_off[c + 1] - q0;
+    if (static_cast<int>(blockIdx.x) * 64 >= Q) return;   // uniform per block
+    const int n0 = n_off[c], N = n_off[c + 1] - n0;
+    const int q = blockIdx.x * 64 + threadIdx.x;
+    const bool live = q < Q;
+    const float *xb = x + static_cast<size_t>(q0 + (live ? q : 0)) * 3;
+    const float qx = xb[0], qy = xb[1], qz = xb[2];
+    const float *pcb = pc + static_cast<size_t>(n0) * 3;
+
+    float bd[kKnn];
+    int bi[kKnn];
+#pragma unroll
+    for (int i = 0; i < kKnn; ++i) bd[i] = FLT_MAX, bi[i] = 0;
+    for (int t0 = 0; t0 < N; t0 += kKnnTile) {
+        const int n = min(kKnnTile, N - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n * 3; i += blockDim.x) sp[i] = pcb[static_cast<size_t>(t0) * 3 + i];
+        __syncthreads();
+        for (int j = 0; j < n; ++j) {
+            const float dx = qx - sp[3 * j], dy = qy - sp[3 * j + 1], dz = qz - sp[3 * j + 2];
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (d < bd[kKnn - 1]) {
+                bd[kKnn - 1] = d;
+                bi[kKnn - 1] = t0 + j;
+#pragma unroll
+                for (int i = kKnn - 1; i > 0; --i) {
+                    if (bd[i] < bd[i - 1]) {
+                        const float td = bd[i];
+                        bd[i] = bd[i - 1];
+                        bd[i - 1] = td;
+                        const int ti = bi[i];
+                        bi[i] = bi[i - 1];
+                        bi[i - 1] = ti;
+                    }
+                }
+            }
+        }
+    }
+    if (live) {
+        int *io = idx_out + static_cast<size_t>(q0 + q) * kKnn;
+#pragma unroll
+        for (int i = 0; i < kKnn; i += 4)
+            *reinterpret_cast<int4 *>(io + i) = make_int4(n0 + bi[i], n0 + bi[i + 1], n0 + bi[i + 2], n0 + bi[i + 3]);
+    }
+}
+
+// out[r, :] = table[row_of[r], :]   (N % 4 == 0): the per-cell bias of the first head layer for a flat batch of queries
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ table, const int *__restrict__ row_of,
+                                                          float *__restrict__ out, long long rows, int n4)
+{
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < rows * n4; i += gridDim.x * 256ll) {
+        const long long r = i / n4;
+        const int c = static_cast<int>(i - r * n4);
+        reinterpret_cast<float4 *>(out)[i] = __ldg(reinterpret_cast<const float4 *>(table) + static_cast<size_t>(row_of[r]) * n4 + c);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // First embedding layer: h = GELU(W1 p + b1), p in R^IN (IN = 3 or 4); one thread per (token, 4 features).
 // GATHER: p = pc[b, idx[b, q, j]] - x[b, q]  (token = (b*Q + q)*16 + j); otherwise p = in[token].
@@ -527,6 +593,29 @@ int knn16(const float *x, const float *pc, int *idx, float *dist, int B, int Q, 
     MAC_REQUIRE((reinterpret_cast<uintptr_t>(idx) & 15u) == 0, "idx must be 16-byte aligned");
     dim3 grid((Q + 63) / 64, B);   // 64 queries per CTA: 16384-query passes still fill the 148 SMs
     knn16_kernel<<<grid, 64, 0, stream>>>(x, pc, idx, dist, Q, N);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+int knn16_cells(const float *x, const float *pc, const int *q_off, const int *n_off, int *idx, int n_cells, int max_q,
+                cudaStream_t stream)
+{
+    MAC_REQUIRE(x && pc && q_off && n_off && idx, "null tensor pointer");
+    MAC_REQUIRE(n_cells > 0 && n_cells <= 65535 && max_q > 0, "kNN over cells needs 1..65535 cells (got %d) and queries", n_cells);
+    MAC_REQUIRE((reinterpret_cast<uintptr_t>(idx) & 15u) == 0, "idx must be 16-byte aligned");
+    dim3 grid((max_q + 63) / 64, n_cells);
+    knn16_cells_kernel<<<grid, 64, 0, stream>>>(x, pc, q_off, n_off, idx);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}
+
+int gather_rows(const float *table, const int *row_of, float *out, long long rows, int N, cudaStream_t stream)
+{
+    MAC_REQUIRE(table && row_of && out && rows > 0 && N > 0 && N % 4 == 0, "gather_rows needs N %% 4 == 0");
+    const long long want = (rows * (N / 4) + 255) / 256;
+    gather_rows_kernel<<<static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(table, row_of, out, rows, N / 4);
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return MAC_OK;

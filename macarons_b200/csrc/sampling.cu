@@ -262,6 +262,33 @@ __global__ void __launch_bounds__(1024) sample_pick_kernel(SampleParams p)
     }
 }
 
+
+// Field-of-view mask of N points for ONE camera (Camera.get_points_in_fov, reference utility/macarons_utils.py:2400-2435):
+// the Selector's geometric predicate without the occupancy test.
+__global__ void __launch_bounds__(256) points_in_fov_kernel(const SampleParams p, unsigned char *__restrict__ mask)
+{
+    __shared__ Selector sel;
+    if (threadIdx.x == 0) {
+        sel = make_selector(p, 0);
+        sel.min_occ = -1.f;
+    }
+    __syncthreads();
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < p.N; i += gridDim.x * 256) {
+        const float x = sel.X[3 * i], y = sel.X[3 * i + 1], z = sel.X[3 * i + 2];
+        const float px = fmaf(x, sel.P[0], fmaf(y, sel.P[4], fmaf(z, sel.P[8], sel.P[12])));
+        const float py = fmaf(x, sel.P[1], fmaf(y, sel.P[5], fmaf(z, sel.P[9], sel.P[13])));
+        const float pw = fmaf(x, sel.P[3], fmaf(y, sel.P[7], fmaf(z, sel.P[11], sel.P[15])));
+        const float vz = fmaf(x, sel.Vz[0], fmaf(y, sel.Vz[1], fmaf(z, sel.Vz[2], sel.Vz[3])));
+        const float nx = __fdiv_rn(px, pw), ny = __fdiv_rn(py, pw);
+        bool in = nx >= sel.ndc[0] && nx <= sel.ndc[1] && ny >= sel.ndc[2] && ny <= sel.ndc[3] && vz > 0.f;
+        if (sel.range >= 0.f) {
+            const float dx = x - sel.centre[0], dy = y - sel.centre[1], dz = z - sel.centre[2];
+            in = in && sqrtf(dx * dx + dy * dy + dz * dz) < sel.range;
+        }
+        mask[i] = in ? 1 : 0;
+    }
+}
+
 }  // namespace
 
 }  // namespace mac
@@ -328,5 +355,21 @@ extern "C" int mac_fov_sample_proxy_f32(const float *X, const float *preds, cons
     sample_pick_kernel<<<C, 1024, 0, st>>>(p);
     MAC_CUDA(cudaGetLastError());
     count_launch(2);
+    return MAC_OK;
+}
+
+extern "C" int mac_points_in_fov_f32(const float *X, const float *cam, const float *ndc_bounds, float fov_range, int N,
+                                     unsigned char *mask, void *stream)
+{
+    MAC_REQUIRE(X && cam && ndc_bounds && mask, "null pointer");
+    MAC_REQUIRE(N >= 0, "N must be non-negative");
+    if (N == 0) return MAC_OK;
+    SampleParams p{};
+    p.X = X, p.N = N, p.cams = cam, p.fov_range = fov_range;
+    for (int i = 0; i < 4; ++i) p.ndc[i] = ndc_bounds[i];
+    const int want = (N + 255) / 256;
+    points_in_fov_kernel<<<want < 148 * 8 ? want : 148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, mask);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
     return MAC_OK;
 }

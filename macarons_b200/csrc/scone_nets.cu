@@ -340,3 +340,127 @@ extern "C" int mac_sconeocc_forward_f32(const mac_sconeocc_w_t *w, const float *
     }
     return MAC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// SconeOcc over a ragged batch of cells: the per-cell `macarons(mode='occupancy', ...)` calls
+// of compute_scene_occupancy_probability_field (/root/reference/macarons/utility/macarons_utils.py:1443-1518) as ONE forward.
+// Every cell has its own partial cloud (own sub-samples, own global feature) and its own queries; the queries of all cells
+// form one flat array, so the neighbourhood transformers, the x embedding and the head run over full 128-row tiles whatever
+// the cell sizes are.  Per query the arithmetic is that of mac_sconeocc_forward_f32 for its cell alone.
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t mac_sconeocc_cells_workspace_bytes(int n_cells, int Sg, int chunk, long long Qtot)
+{
+    if (n_cells <= 0 || Sg <= 0 || chunk <= 0 || Qtot <= 0 || Qtot > (1ll << 30)) return 0;
+    return sconeocc_workspace(n_cells, Sg, chunk, static_cast<int>(Qtot)) + align256(static_cast<size_t>(chunk) * 512 * 4);
+}
+
+extern "C" int mac_sconeocc_forward_cells_f32(const mac_sconeocc_w_t *w, int n_cells, const float *pc_global, int Sg,
+                                              const int *lens_g, const float *const *pc_scale, const int *const *scale_off,
+                                              const float *x, const float *vh, const int *q_off, const int *cell_of_q,
+                                              int max_q, float *out, long long Qtot, int chunk, void *workspace,
+                                              size_t workspace_bytes, void *stream)
+{
+    MAC_REQUIRE(w && pc_global && lens_g && pc_scale && scale_off && x && vh && q_off && cell_of_q && out && workspace,
+                "null pointer");
+    MAC_REQUIRE(n_cells > 0 && Qtot > 0 && Qtot <= (1ll << 30) && Sg > 0 && chunk > 0 && max_q > 0,
+                "n_cells, Qtot, Sg, chunk, max_q must be positive");
+    MAC_REQUIRE(w->n_scale == 3, "SconeOcc kernels are built for 3 neighbourhood scales");
+    if (int rc = check_pct(w->global_pct)) return rc;
+    for (int s = 0; s < w->n_scale; ++s) {
+        if (int rc = check_pct(w->local_pct[s])) return rc;
+        MAC_REQUIRE(w->local_pct[s].linear0.N == 128, "local feature must be 2 x 128");
+        MAC_REQUIRE(pc_scale[s] && scale_off[s], "scale %d: null cloud / offsets", s);
+    }
+    MAC_REQUIRE(w->global_pct.linear0.N == 256 && w->global_dim == 512 && w->lin1.K == kFeat && w->lin1.N == 512 &&
+                    w->xemb1_n == 128 && w->xemb3.N == 512 && w->lin3.N == 1,
+                "unexpected SconeOcc head shape");
+    const size_t need = mac_sconeocc_cells_workspace_bytes(n_cells, Sg, chunk, Qtot);
+    if (workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return MAC_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int D = 128, B = n_cells;
+    const long long Q = Qtot;
+    const long long Tg = static_cast<long long>(B) * Sg, Tl = static_cast<long long>(chunk) * 16;
+    const long long Tm = Tg > Tl ? Tg : Tl;
+    Bump ws{static_cast<unsigned char *>(workspace), 0, workspace_bytes};
+    float *h = ws.f(Tm * 128);
+    EncBufs e = carve_enc(ws, Tm, D, 192, attn_dense_tc_scratch_floats(B, Sg, 32));
+    float *g0 = ws.f(Tg * 256);
+    float *gfeat = ws.f(static_cast<size_t>(B) * 512);
+    float *bias1 = ws.f(static_cast<size_t>(B) * 512);
+    int *idx_all[3];
+    for (int s = 0; s < 3; ++s) idx_all[s] = reinterpret_cast<int *>(ws.f(static_cast<size_t>(Q) * 16));
+    float *feat = ws.f(static_cast<size_t>(chunk) * kFeat);
+    float *xe1 = ws.f(static_cast<size_t>(chunk) * 128);
+    float *xe2 = ws.f(static_cast<size_t>(chunk) * 256);
+    float *l1 = ws.f(static_cast<size_t>(chunk) * 512);
+    float *l2 = ws.f(static_cast<size_t>(chunk) * 256);
+    float *l3 = ws.f(static_cast<size_t>(chunk) * 4);
+    float *qbias = ws.f(static_cast<size_t>(chunk) * 512);
+
+    // ---- global feature of every cell: ragged batch of B clouds of lens_g[c] <= Sg points ----
+    {
+        const mac_pct_w_t &g = w->global_pct;
+        if (int rc = embed_first(pc_global, 3, 3, nullptr, nullptr, nullptr, 0, 0, g.emb1_w, g.emb1_b, g.inner, 1, h, 128, Tg, st)) return rc;
+        if (int rc = lin(h, 128, g.emb2, g.emb2.bias, e.x, D, Tg, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st, LnIn(),
+                         e.stats))
+            return rc;
+        if (int rc = encoder_stack(g.enc, g.n_enc, e, Tg, D, g.dqk, g.dv, false, B, Sg, st, lens_g)) return rc;
+        LnIn fin;
+        fin.stats = e.stats, fin.g = g.ln_g, fin.b = g.ln_b;
+        if (int rc = lin(e.x, D, g.linear0, g.linear0.bias, g0, 256, Tg, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st, fin))
+            return rc;
+        if (int rc = colpool(g0, 256, B, Sg, 256, gfeat, gfeat + 256, 512, st, lens_g)) return rc;
+        if (int rc = bias_gemv(w->lin1_wg, w->lin1_wg_ld, w->lin1_b, gfeat, 512, 512, 512, bias1, B, st)) return rc;
+    }
+
+    // ---- 16 nearest points of every query in its own cell's cloud, three scales (global rows of the concatenated clouds) ----
+    for (int s = 0; s < w->n_scale; ++s)
+        if (int rc = knn16_cells(x, pc_scale[s], q_off, scale_off[s], idx_all[s], B, max_q, st)) return rc;
+
+    // ---- flat query loop: neighbourhood transformers + x embedding + head ----
+    for (long long q0 = 0; q0 < Q; q0 += chunk) {
+        const int nq = static_cast<int>(Q - q0 < chunk ? Q - q0 : chunk);
+        const long long T = static_cast<long long>(nq) * 16;
+        const float *xq = x + static_cast<size_t>(q0) * 3;
+        for (int s = 0; s < w->n_scale; ++s) {
+            const mac_pct_w_t &l = w->local_pct[s];
+            // indices are global rows: "one cloud" of unspecified size holding every cell's points
+            if (int rc = embed_first(nullptr, 0, 3, pc_scale[s], xq, idx_all[s] + static_cast<size_t>(q0) * 16, nq, 0, l.emb1_w,
+                                     l.emb1_b, l.inner, 1, h, 128, T, st))
+                return rc;
+            if (int rc = lin(h, 128, l.emb2, l.emb2.bias, e.x, D, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st,
+                             LnIn(), e.stats))
+                return rc;
+            if (int rc = encoder_stack(l.enc, l.n_enc, e, T, D, l.dqk, l.dv, true, 0, 0, st)) return rc;
+            LnIn fin;
+            fin.stats = e.stats, fin.g = l.ln_g, fin.b = l.ln_b;
+            if (int rc = lin(e.x, D, l.linear0, l.linear0.bias, feat + s * 256, kFeat, T, MAC_LIN_NONE, nullptr, 0, nullptr, 0,
+                             nullptr, nullptr, 16, st, fin))
+                return rc;
+        }
+        if (int rc = embed_first(xq, 3, 3, nullptr, nullptr, nullptr, 0, 0, w->xemb1_w, w->xemb1_b, w->xemb1_n, 0, xe1, 128, nq, st))
+            return rc;
+        if (int rc = lin(xe1, 128, w->xemb2, w->xemb2.bias, xe2, 256, nq, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+            return rc;
+        if (int rc = lin(xe2, 256, w->xemb3, w->xemb3.bias, feat + 768, kFeat, nq, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr,
+                         nullptr, 0, st))
+            return rc;
+        MAC_CUDA(cudaMemcpy2DAsync(feat + 1280, kFeat * sizeof(float), vh + static_cast<size_t>(q0) * 64, 64 * sizeof(float),
+                                   64 * sizeof(float), nq, cudaMemcpyDeviceToDevice, st));
+        // per-query bias of linear1 = its cell's [b1 + W_g . global feature]: added before the GELU as a "residual"
+        if (int rc = gather_rows(bias1, cell_of_q + q0, qbias, nq, 512, st)) return rc;
+        if (int rc = linear_forward(feat, kFeat, w->lin1.hi, w->lin1.lo, w->lin1.ldw, nullptr, l1, 512, nq, w->lin1.N, w->lin1.K,
+                                    MAC_LIN_GELU, qbias, 512, nullptr, 0, nullptr, nullptr, kLnEps, 0, st, /*res_first=*/1, nullptr,
+                                    nullptr, nullptr, nullptr))
+            return rc;
+        if (int rc = lin(l1, 512, w->lin2, w->lin2.bias, l2, 256, nq, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+            return rc;
+        if (int rc = lin(l2, 256, w->lin3, w->lin3.bias, l3, 4, nq, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st))
+            return rc;
+        MAC_CUDA(cudaMemcpy2DAsync(out + q0, sizeof(float), l3, 4 * sizeof(float), sizeof(float), nq, cudaMemcpyDeviceToDevice, st));
+    }
+    return MAC_OK;
+}

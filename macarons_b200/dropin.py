@@ -31,11 +31,13 @@ _TABLE = (
                                                                   "move_view_state_to_view_space", "compute_view_harmonics",
                                                                   "compute_occupancy_probability", "sample_proxy_points")),
     ("utility.macarons_utils", "macarons_b200.utility.macarons_utils", ("compute_occupancy_probability",
+                                                                        "compute_scene_occupancy_probability_field",
                                                                         "predict_coverage_gain_for_single_camera",
                                                                         "get_distance_factor", "get_distance_factor_threshold",
                                                                         "get_distance_factor_smooth")),
 )
-_CAMERA_METHODS = ("project_depth_in_3D", "compute_partial_point_cloud", "get_signed_distance_to_depth_maps")
+_CAMERA_METHODS = ("project_depth_in_3D", "compute_partial_point_cloud", "get_signed_distance_to_depth_maps",
+                   "get_points_in_fov")
 
 
 def install(package="macarons", depth=True):

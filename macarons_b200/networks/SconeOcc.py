@@ -108,3 +108,51 @@ class SconeOcc(nn.Module):
         out = ops.sconeocc_forward(netpack.pack_sconeocc(self), pc_global, clouds, x, view_harmonics,
                                    chunk=self.queries_per_pass)
         return out.view(pc.shape[0], x.shape[1], self.output_dim)
+
+    def forward_cells(self, clouds, queries, view_harmonics):
+        """Batched form of a loop of forward calls over cells with their own clouds (extension; the reference calls the
+        network once per occupied cell, utility/macarons_utils.py:1443-1518): `clouds[c]` (N_c, 3), `queries[c]`
+        (Q_c, 3), `view_harmonics[c]` (Q_c, 64) -> list of (Q_c, 1) outputs, those of `self(clouds[c][None],
+        queries[c][None], view_harmonics[c][None])[0]` called in the same order: the random sub-samples of every cell
+        are drawn here on the host in exactly that order (`draw_subsamples`), then ONE ragged CUDA forward runs."""
+        if self.training and self.dropout is not None:
+            raise NotImplementedError("the fused SconeOcc forward has no dropout: call .eval() (dropout=%r)" % self.dropout)
+        ops.refuse_grad("SconeOcc.forward_cells", *clouds, *queries, *view_harmonics, module=self)
+        n_cells = len(clouds)
+        if n_cells == 0:
+            return []
+        dev = clouds[0].device
+        sizes = [int(c.shape[0]) for c in clouds]
+        n_q = [int(q.shape[0]) for q in queries]
+        cloud_off = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+        Sg = min(self.seq_len, max(sizes))
+        # host side: index arithmetic only (which rows of the concatenated cloud every sub-sample consists of)
+        g_rows = np.zeros((n_cells, Sg), dtype=np.int64)
+        g_len = np.zeros(n_cells, dtype=np.int32)
+        scale_rows = [[], []]
+        scale_off = [np.zeros(n_cells + 1, dtype=np.int64) for _ in range(2)]
+        for c, n in enumerate(sizes):
+            global_idx, scale_idx = self.draw_subsamples(n)
+            g_len[c] = global_idx.numel()
+            g_rows[c, :g_len[c]] = cloud_off[c] + global_idx.numpy()
+            rows = np.arange(n, dtype=np.int64)
+            for s, idx in enumerate(scale_idx):
+                rows = rows[idx.numpy()]
+                scale_rows[s].append(cloud_off[c] + rows)
+                scale_off[s][c + 1] = scale_off[s][c] + rows.shape[0]
+        as_dev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+        all_pc = torch.cat([c.reshape(-1, 3) for c in clouds]).to(torch.float32)
+        pc_global = all_pc.index_select(0, as_dev(g_rows.reshape(-1), torch.int64)).view(n_cells, Sg, 3)
+        pad = np.arange(Sg)[None, :] >= g_len[:, None]
+        if pad.any():
+            pc_global = pc_global * as_dev(~pad, torch.float32).unsqueeze(-1)          # zero rows behind lens_g[c]
+        pc_scales = [all_pc] + [all_pc.index_select(0, as_dev(np.concatenate(r), torch.int64)) for r in scale_rows]
+        scale_offs = [as_dev(cloud_off, torch.int32)] + [as_dev(o, torch.int32) for o in scale_off]
+        q_off = np.concatenate(([0], np.cumsum(n_q))).astype(np.int64)
+        x = torch.cat([q.reshape(-1, 3) for q in queries]).to(torch.float32)
+        vh = torch.cat([v.reshape(-1, view_harmonics[0].shape[-1]) for v in view_harmonics]).to(torch.float32)
+        cell_of_q = as_dev(np.repeat(np.arange(n_cells, dtype=np.int32), n_q), torch.int32)
+        out = ops.sconeocc_forward_cells(netpack.pack_sconeocc(self), pc_global, as_dev(g_len, torch.int32), pc_scales,
+                                         scale_offs, x, vh, as_dev(q_off, torch.int32), cell_of_q, max(n_q),
+                                         chunk=self.queries_per_pass)
+        return [out[q_off[c]:q_off[c + 1]].view(-1, self.output_dim) for c in range(n_cells)]

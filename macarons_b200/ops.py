@@ -374,6 +374,43 @@ def sconeocc_forward(w, pc_global, pc_scales, x, view_harmonics, chunk=65536):
     return out
 
 
+def sconeocc_forward_cells(w, pc_global, lens_g, pc_scales, scale_offs, x, view_harmonics, q_off, cell_of_q, max_q,
+                           chunk=65536):
+    """Ragged batch of cells through mac_sconeocc_forward_cells_f32 (see include/macarons_b200.h).  pc_global
+    (n_cells,Sg,3); lens_g (n_cells) int32; pc_scales: 3 concatenated clouds (total_s,3); scale_offs: 3 int32 offset
+    vectors (n_cells+1); x (Qtot,3); view_harmonics (Qtot,64); q_off (n_cells+1) int32; cell_of_q (Qtot) int32
+    -> (Qtot,) occupancy values."""
+    import ctypes
+    for name, t in (("pc_global", pc_global), ("x", x), ("view_harmonics", view_harmonics)):
+        _require_cuda_f32(name, t)
+    n_cells, Sg, _ = pc_global.shape
+    Qtot = x.shape[0]
+    dev = x.device
+    if tuple(x.shape) != (Qtot, 3) or tuple(view_harmonics.shape) != (Qtot, N_HARMONICS) or len(pc_scales) != 3 or len(scale_offs) != 3:
+        raise ValueError("inconsistent SconeOcc cell-batch shapes")
+    for t, n in ((lens_g, n_cells), (q_off, n_cells + 1), (cell_of_q, Qtot)) + tuple((o, n_cells + 1) for o in scale_offs):
+        if t.dtype != torch.int32 or t.device != dev or t.numel() != n or not t.is_contiguous():
+            raise ValueError("offset / length vectors must be contiguous int32 CUDA tensors of the right size")
+    pc_global, x, view_harmonics = pc_global.contiguous(), x.contiguous(), view_harmonics.contiguous()
+    pc_scales = [p.contiguous() for p in pc_scales]
+    for p in pc_scales:
+        _require_cuda_f32("pc_scale", p)
+    out = torch.empty((Qtot,), dtype=torch.float32, device=dev)
+    if Qtot == 0:
+        return out
+    chunk = int(min(chunk, Qtot))
+    ptrs = (ctypes.c_void_p * 3)(*[p.data_ptr() for p in pc_scales])
+    offs = (ctypes.c_void_p * 3)(*[o.data_ptr() for o in scale_offs])
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ws = _net_workspace(dev, lib.mac_sconeocc_cells_workspace_bytes(n_cells, Sg, chunk, Qtot))
+        _lib.check(lib.mac_sconeocc_forward_cells_f32(ctypes.byref(w), n_cells, pc_global.data_ptr(), Sg, lens_g.data_ptr(),
+                                                      ptrs, offs, x.data_ptr(), view_harmonics.data_ptr(), q_off.data_ptr(),
+                                                      cell_of_q.data_ptr(), int(max_q), out.data_ptr(), Qtot, chunk,
+                                                      ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+    return out
+
+
 # ---- view state and proxy sampling (csrc/viewstate.cu, csrc/sampling.cu) --------------------------
 def view_state(pts, X_view, n_elev, n_azim):
     """pts (B,P,>=3), X_view (V,3) -> (B,P,n_elev*n_azim) fp32 {0,1}."""
@@ -506,6 +543,24 @@ def fov_sample_proxy(X_world, preds, view_harmonics, cams, ndc_bounds, fov_range
                                                 inverse.data_ptr(), counts.data_ptr(), volume.data_ptr(), ws.data_ptr(),
                                                 ws.numel(), _stream_ptr(dev)))
     return res, res_h, inverse, counts, volume
+
+
+def points_in_fov(X_world, cam_row, ndc_bounds, fov_range):
+    """X_world (N,3), cam_row (36,) [full projection | world-to-view | centre | pad] -> bool mask (N,)."""
+    import ctypes
+    _require_cuda_f32("X_world", X_world)
+    _require_cuda_f32("cam_row", cam_row)
+    if X_world.dim() != 2 or X_world.shape[1] != 3 or cam_row.numel() != 36:
+        raise ValueError("expected X_world (N,3) and a 36-float camera row")
+    X_world, cam_row = X_world.contiguous(), cam_row.contiguous()
+    N = X_world.shape[0]
+    mask = torch.empty((N,), dtype=torch.uint8, device=X_world.device)
+    ndc = (ctypes.c_float * 4)(*[float(v) for v in ndc_bounds])
+    with torch.cuda.device(X_world.device):
+        _lib.check(_lib.load().mac_points_in_fov_f32(X_world.data_ptr(), cam_row.data_ptr(), ctypes.cast(ndc, ctypes.c_void_p),
+                                                     -1.0 if fov_range is None else float(fov_range), N, mask.data_ptr(),
+                                                     _stream_ptr(X_world.device)))
+    return mask.bool()
 
 
 def unproject_depth(depth, cams, H, W):

@@ -2,6 +2,7 @@
 kernels of this package (same names, argument meaning and return values):
 
     compute_occupancy_probability               reference :1194-1230
+    compute_scene_occupancy_probability_field   reference :1395-1540 (all occupied cells in ONE ragged SconeOcc forward)
     predict_coverage_gain_for_single_camera     reference :1580-1738
     get_distance_factor / _threshold / _smooth  reference :1741-1788
 
@@ -200,6 +201,117 @@ def predict_coverage_gain_for_single_camera(params, macarons, proxy_scene, surfa
     return dummy_pts, dummy_vh, gains, (torch.mean(gains, dim=-1) * 0.).view(-1, 1)
 
 
+# ---- occupancy probability field of the whole scene (reference :1395-1540) ----------------------------------------------
+def _scone_occ(macarons, params):
+    model = macarons.module if (getattr(params, "jz", False) or getattr(params, "ddp", False)) else macarons
+    return model.occupancy
+
+
+def compute_scene_occupancy_probability_field(params, macarons, camera, surface_scene, proxy_scene, device,
+                                              use_supervision_occ_mask=True, prediction_camera=None,
+                                              use_supervision_occ_instead_of_predicted=False):
+    """Reference signature and return values (:1395-1540): (X_world (N,3), view_harmonics (N,64), occ_probs (N,1)) =
+    every proxy point that has been in a field of view and is not carved away, cell by cell (cells in sorted index
+    order, points in ascending proxy index inside a cell), followed by the out-of-field points with zero harmonics and
+    their stored probability; `proxy_scene.proxy_proba` is updated like the reference does.
+
+    The reference calls the occupancy network once per occupied cell (and per 20 000-query pass inside a cell), each
+    call on the cell's own 27-cell neighbourhood cloud.  Here the host loop only collects index tensors; the bin
+    permutation (`move_view_state_to_view_space`: one permutation for the whole scene), the view harmonics and the
+    normalisation run once over all kept proxy points, and ALL cells go through ONE ragged SconeOcc forward
+    (`SconeOcc.forward_cells`, csrc/scone_nets.cu) whose random sub-samples are drawn in the reference's call order."""
+    from . import scone_utils
+    occ_mask = (proxy_scene.proxy_supervision_occ > 0.)[..., 0]
+    all_fov_mask = (proxy_scene.out_of_field < 1.)[..., 0]
+    keep_mask = occ_mask * all_fov_mask if use_supervision_occ_mask else all_fov_mask
+    fovs_proxy_points = proxy_scene.proxy_points[keep_mask]
+    proxy_scene.proxy_proba[occ_mask * all_fov_mask] = 0.
+    proxy_cells = proxy_scene.get_englobing_cells(fovs_proxy_points)
+    base_harmonics, h_polar, h_azim = scone_utils.get_all_harmonics_under_degree(
+        params.harmonic_degree, params.view_state_n_elev, params.view_state_n_azim, device)
+    if prediction_camera is None:
+        if camera is None:
+            raise NameError("Both camera and prediction_camera are equal to None.")
+        prediction_camera = camera.fov_camera_0
+    view_transform = prediction_camera.get_world_to_view_transform()
+    k_min = 2 * 2 * params.k_for_knn
+    max_pass = 20000                       # max_points_per_pass of the reference's per-cell call (:1508)
+
+    # ---- host loop: which proxy points and which surface points belong to every occupied cell ----
+    cell_rows, cell_clouds, cell_centres, cell_diags = [], [], [], []
+    for proxy_cell in proxy_cells:
+        cell = proxy_scene.cells[proxy_scene.get_key_from_idx(proxy_cell)]
+        cloud = surface_scene.get_pt_cloud_from_cells(surface_scene.get_neighboring_cells(proxy_cell), return_features=False)
+        _, indices = proxy_scene.get_pt_cloud_from_cells(proxy_cell, return_features=True)
+        mask = proxy_scene.get_proxy_mask_from_indices(indices)
+        if use_supervision_occ_mask:
+            mask = mask * occ_mask
+        rows = torch.nonzero(mask).view(-1)                 # ascending proxy index, like boolean-mask indexing
+        if cloud.shape[0] > k_min and rows.numel() > 0:
+            cell_rows.append(rows)
+            cell_clouds.append(cloud)
+            cell_centres.append(cell.center.view(1, 3))
+            cell_diags.append(params.prediction_neighborhood_size * torch.linalg.norm(cell.x_max - cell.x_min))
+
+    n_harm = params.n_harmonics
+    if cell_rows:
+        counts = [int(r.numel()) for r in cell_rows]
+        rows_all = torch.cat(cell_rows)
+        X_cells = proxy_scene.proxy_points[rows_all]
+        # prediction view space, one centre / diagonal per cell (:1466-1484)
+        centres = view_transform.transform_points(torch.cat(cell_centres)).view(-1, 3)
+        diags = torch.stack([d.reshape(()) for d in cell_diags]).to(torch.float32)
+        q_centre = torch.repeat_interleave(centres, torch.tensor(counts, device=centres.device), dim=0)
+        q_diag = torch.repeat_interleave(diags, torch.tensor(counts, device=diags.device)).view(-1, 1)
+        X_norm = normalize_points_in_prediction_box(view_transform.transform_points(X_cells).view(-1, 3), q_centre, q_diag)
+        n_pc = [int(c.shape[0]) for c in cell_clouds]
+        pc_all = view_transform.transform_points(torch.cat(cell_clouds)).view(-1, 3)
+        pc_all = normalize_points_in_prediction_box(
+            pc_all, torch.repeat_interleave(centres, torch.tensor(n_pc, device=centres.device), dim=0),
+            torch.repeat_interleave(diags, torch.tensor(n_pc, device=diags.device)).view(-1, 1))
+        # view states -> prediction view space -> harmonics, all cells at once (:1487-1498)
+        states = scone_utils.move_view_state_to_view_space(
+            proxy_scene.view_states[rows_all].view(1, -1, params.n_view_state_cameras), prediction_camera,
+            n_elev=params.view_state_n_elev, n_azim=params.view_state_n_azim)
+        harmonics = scone_utils.compute_view_harmonics(states, base_harmonics, h_polar, h_azim, params.view_state_n_elev,
+                                                       params.view_state_n_azim).view(-1, n_harm)
+        if use_supervision_occ_instead_of_predicted:
+            probs = proxy_scene.proxy_supervision_occ[rows_all]
+        else:
+            # one entry per (cell, pass of <= 20 000 queries): every pass of the reference is a separate forward with its
+            # own sub-samples of the cell's cloud
+            clouds, queries, vhs = [], [], []
+            q0 = p0 = 0
+            for n_q, n_p in zip(counts, n_pc):
+                for lo in range(0, n_q, max_pass):
+                    up = min(lo + max_pass, n_q)
+                    clouds.append(pc_all[p0:p0 + n_p])
+                    queries.append(X_norm[q0 + lo:q0 + up])
+                    vhs.append(harmonics[q0 + lo:q0 + up])
+                q0, p0 = q0 + n_q, p0 + n_p
+            probs = torch.cat(_scone_occ(macarons, params).forward_cells(clouds, queries, vhs)).view(-1, 1)
+        proxy_scene.proxy_proba[rows_all] = probs
+    else:
+        X_cells = torch.zeros(0, 3, device=device)
+        harmonics = torch.zeros(0, n_harm, device=device)
+        probs = torch.zeros(0, 1, device=device)
+
+    # ---- out-of-field points: zero harmonics, stored (default) probability (:1522-1538) ----
+    oof_mask = (proxy_scene.out_of_field > 0.)[..., 0]
+    oof_X = proxy_scene.proxy_points[oof_mask]
+    X_world = torch.vstack((X_cells.view(-1, 3), oof_X))
+    view_harmonics = torch.vstack((harmonics, torch.zeros(len(oof_X), n_harm, device=device)))
+    occ_probs = torch.vstack((probs, proxy_scene.proxy_proba[oof_mask]))
+    return X_world, view_harmonics, occ_probs
+
+
+def compute_depth_from_disparity(params, disp):
+    """depth = 1 / (a disp + b), a = 1/znear - 1/zfar, b = 1/zfar   [reference utility/depth_model_utils.py:844-848]"""
+    a = 1. / params.znear - 1. / params.zfar
+    b = 1. / params.zfar
+    return 1. / (a * disp + b)
+
+
 # ---- depth-side helpers (reference: methods of `Camera`, macarons_utils.py:2339-2500) -----------------------------------
 # They take the reference's Camera object (or anything with image_height, image_width, zfar, gathering_factor, fov_camera)
 # as first argument, so a maintainer binds them back as methods: `Camera.project_depth_in_3D = project_depth_in_3D`, ...
@@ -234,6 +346,18 @@ def compute_partial_point_cloud(camera, depth, mask, images=None, fov_cameras=No
     if images is None:
         return world_points
     return world_points, (0. + images.view(1, -1, 3))[points_mask][points_indices]
+
+
+def get_points_in_fov(camera, pts, return_mask=False, fov_camera=None, fov_range=None):
+    """Points of pts (n_point, 3) inside the field of view of `fov_camera` (default: the camera's current one) and closer
+    than `fov_range` to its centre  [reference Camera.get_points_in_fov :2400-2435]; one kernel (csrc/sampling.cu)."""
+    own = fov_camera is None
+    row = _camera_rows(camera.fov_camera if own else fov_camera, pts.device)[0]
+    if own:    # the reference measures the range from self.X_cam for the camera's own field of view (:2412-2414)
+        row = torch.cat((row[:32], camera.X_cam.reshape(-1)[:3].to(row), row[35:]))
+    fov_mask = ops.points_in_fov(pts.to(torch.float32), row, (camera.min_ndc_x, camera.max_ndc_x, camera.min_ndc_y,
+                                                               camera.max_ndc_y), fov_range)
+    return (pts[fov_mask], fov_mask) if return_mask else pts[fov_mask]
 
 
 def get_signed_distance_to_depth_maps(camera, pts, depth_maps, mask, fov_camera=None):

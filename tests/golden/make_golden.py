@@ -276,6 +276,46 @@ def macarons_cov_goldens():
 
 
 
+SCENE_FIELD_CASES = [("scene_field_s31", 31, 6000, 9000), ("scene_field_s32", 32, 3000, 5000)]
+
+
+def scene_field_goldens():
+    """the reference's `Scene` / `Cell` bookkeeping (utility/macarons_utils.py:2503-2932) and
+    its `compute_scene_occupancy_probability_field` (:1395-1540) -- one SconeOcc call per occupied cell -- on the synthetic
+    three-frame scene of tests/scene_case.py; the oracle (oracle/scene.py) must reproduce it bit for bit."""
+    import copy
+    from macarons.utility import macarons_utils as ref_mu
+    import scene_case
+    from oracle import scene as o_scene
+    occ = SconeOcc()
+    occ_sd = synth.seeded_state_dict(occ.state_dict(), NET_WEIGHT_SEED)
+    occ.load_state_dict(occ_sd)
+    occ.eval()
+    macarons = Macarons(None, occ, None)
+    params = scene_case.params()
+    pred = scene_case.prediction_camera()
+    for name, seed, n_proxy, n_surface in SCENE_FIELD_CASES:
+        surface_scene, proxy_scene = scene_case.build(ref_mu.Scene, "cpu", seed, n_proxy=n_proxy, n_surface=n_surface)
+        state_digest, counts = scene_case.scene_digest(surface_scene, proxy_scene)
+        o_surface, o_proxy = copy.deepcopy(surface_scene), copy.deepcopy(proxy_scene)
+        with torch.no_grad():
+            torch.manual_seed(seed + 1000)
+            X_world, vh, probs = ref_mu.compute_scene_occupancy_probability_field(params, macarons, None, surface_scene,
+                                                                                  proxy_scene, "cpu", prediction_camera=pred)
+            torch.manual_seed(seed + 1000)
+            oX, ovh, oprobs = o_scene.scene_occupancy_field(params, occ_sd, o_surface, o_proxy, pred)
+        must_equal(X_world, oX, name + " X_world")
+        must_equal(vh, ovh, name + " view harmonics")
+        must_equal(probs, oprobs, name + " occupancy")
+        must_equal(proxy_scene.proxy_proba, o_proxy.proxy_proba, name + " proxy_proba")
+        n_oof = int((proxy_scene.out_of_field > 0.).sum())
+        save(name, seed=seed, n_proxy=n_proxy, n_surface=n_surface, weight_seed=NET_WEIGHT_SEED,
+             weights_digest=synth.state_dict_digest(occ_sd), scene_digest=state_digest, cell_counts=np.asarray(counts),
+             n_points=X_world.shape[0], n_out_of_field=n_oof, X_world_digest=digest(X_world),
+             X_world_head=X_world[:64], view_harmonics_stride8=vh[:X_world.shape[0] - n_oof:8],
+             occupancy=probs[:X_world.shape[0] - n_oof, 0], proxy_proba=proxy_scene.proxy_proba[:, 0])
+
+
 def depth_io_goldens():
     """`Camera.project_depth_in_3D`, `compute_partial_point_cloud` and `get_signed_distance_to_depth_maps` of the reference
     (utility/macarons_utils.py:2339-2500), called unbound on a stand-in for `self` (the Camera constructor needs a renderer)."""
@@ -373,6 +413,9 @@ if __name__ == "__main__":
     if "--depth-only" in sys.argv:
         depth_goldens()
         raise SystemExit(0)
+    if "--scene-only" in sys.argv:
+        scene_field_goldens()
+        raise SystemExit(0)
     if "--depth-full-only" in sys.argv:
         depth_full_goldens()
         raise SystemExit(0)
@@ -394,6 +437,7 @@ if __name__ == "__main__":
     sampling_goldens()
     nets_goldens()
     macarons_cov_goldens()
+    scene_field_goldens()
     depth_io_goldens()
     depth_goldens()
     depth_full_goldens()

@@ -43,7 +43,12 @@ assert ref_mu.predict_coverage_gain_for_single_camera is our_mu.predict_coverage
 assert ref_mu.predict_coverage_gains_for_cameras is our_mu.predict_coverage_gains_for_cameras
 assert ref_mu.Camera.project_depth_in_3D is our_mu.project_depth_in_3D
 assert ref_mu.Camera.get_signed_distance_to_depth_maps is our_mu.get_signed_distance_to_depth_maps
-assert set(report["camera_methods"]) == {"project_depth_in_3D", "compute_partial_point_cloud", "get_signed_distance_to_depth_maps"}
+assert ref_mu.Camera.get_points_in_fov is our_mu.get_points_in_fov
+assert set(report["camera_methods"]) == {"project_depth_in_3D", "compute_partial_point_cloud", "get_signed_distance_to_depth_maps",
+                                         "get_points_in_fov"}
+assert ref_mu.compute_scene_occupancy_probability_field is our_mu.compute_scene_occupancy_probability_field
+# the reference's own Scene stays (control plane), but the view-state binning it calls is now the CUDA kernel
+assert ref_mu.Scene.update_proxy_view_states.__globals__["compute_view_state"] is our_su.compute_view_state
 # the control plane is untouched: loaders, optimiser wrappers, the factory functions (which now build OUR classes)
 assert ref_mu.load_params is original_loader
 assert ref_mac_mod.MacaronsWrapper.__module__ == "macarons.networks.Macarons"
