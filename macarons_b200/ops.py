@@ -423,6 +423,8 @@ def view_state(pts, X_view, n_elev, n_azim):
     out = torch.empty((B, P, n_elev * n_azim), dtype=torch.float32, device=pts.device)
     if B * P == 0:
         return out
+    if X_view.shape[0] == 0:      # no camera visited yet: empty histogram
+        return out.zero_()
     with torch.cuda.device(pts.device):
         _lib.check(_lib.load().mac_view_state_f32(pts.data_ptr(), D, X_view.data_ptr(), out.data_ptr(), B, P,
                                                   X_view.shape[0], int(n_elev), int(n_azim), _stream_ptr(pts.device)))
@@ -462,6 +464,8 @@ def view_state_harmonics(pts, X_view, base, h_polar, n_elev, n_azim):
     out = torch.empty((B, P, N_HARMONICS), dtype=torch.float32, device=pts.device)
     if B * P == 0:
         return out
+    if X_view.shape[0] == 0:
+        return out.zero_()
     with torch.cuda.device(pts.device):
         _lib.check(_lib.load().mac_viewstate_harm_f32(pts.data_ptr(), D, X_view.data_ptr(), base.data_ptr(), h_polar.data_ptr(),
                                                       out.data_ptr(), B, P, X_view.shape[0], int(n_elev), int(n_azim),

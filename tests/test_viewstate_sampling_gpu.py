@@ -127,7 +127,7 @@ def test_fused_view_state_harmonics_is_bitwise_the_two_kernel_path(cuda_device):
         two = scone_utils.compute_view_harmonics(scone_utils.compute_view_state(pts, X_view, 7, 14), base, h_polar, h_azim, 7, 14)
         n0 = ops.launch_count()
         one = scone_utils.compute_view_state_harmonics(pts, X_view, base, h_polar, h_azim, 7, 14)
-        assert ops.launch_count() == n0 + 1
+        assert ops.launch_count() == n0 + (1 if V > 0 else 0)
         assert torch.equal(one, two), (B, P, V)
     g = load_golden("view_state_10views")
     pts, _ = synth.view_state_inputs(int(g["B"]), int(g["P"]), int(g["V"]), int(g["seed"]))
