@@ -139,26 +139,34 @@ __global__ void __launch_bounds__(256) view_harmonics_kernel(const float *__rest
 // T[j][k] = ((1 * base[k][j]) * sin(polar_j)) * polar_step * azim_step  -- bit for bit the term the two-kernel path adds for a
 // state of 1.0, in the same ascending-bin order, so both paths give identical results.
 // Traffic: 4*pts_dim B read + 256 B written per point (vs + 2 * 4 * n_bins B for the materialised histogram).
-constexpr int kFusedPts = 64;  // points per block iteration
-__global__ void __launch_bounds__(256) viewstate_harm_kernel(const ViewStateParams p, const float *__restrict__ base,
-                                                             const float *__restrict__ h_polar, float *__restrict__ out,
-                                                             float polar_step, float azim_step)
+constexpr int kFusedPts = 64;   // points per block iteration
+// T[k][j] row stride = n_bins | 1 (odd: the reads of one bin by the 64 coefficient threads hit 32 distinct banks)
+// The binning is a long dependent chain (sqrt, 4 IEEE divisions, asinf, cosf, acosf, two exact remainders: ~600 issued
+// instructions per ray incl. divergent slow paths), i.e. latency bound: 8 CTAs x 8 warps per SM (32 registers) hide it.
+__global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateParams p, const float *__restrict__ base,
+                                                                const float *__restrict__ h_polar, float *__restrict__ out,
+                                                                float polar_step, float azim_step)
 {
     extern __shared__ float sm[];
     const int n_bins = p.n_elev * p.n_azim;
-    float *T = sm;                                                        // [n_bins][64]
-    float *sviews = T + n_bins * 64;                                      // [V][3]
+    const int kTStride = n_bins | 1;
+    float *T = sm;                                                        // [64][kTStride]
+    float *sinp = T + 64 * kTStride;                                      // [n_bins]
+    float *sviews = sinp + kMaxBins;                                      // [V][3]
     float *spts = sviews + 3 * p.V;                                       // [kFusedPts][3]
     unsigned *mask = reinterpret_cast<unsigned *>(spts + 3 * kFusedPts);  // [kFusedPts][4]
-    for (int i = threadIdx.x; i < n_bins * 64; i += blockDim.x) {
-        const int j = i >> 6, k = i & 63;
-        T[i] = __fmul_rn(__fmul_rn(__fmul_rn(base[k * n_bins + j], sinf(h_polar[j])), polar_step), azim_step);
-    }
+    for (int j = threadIdx.x; j < n_bins; j += blockDim.x) sinp[j] = sinf(h_polar[j]);
     for (int i = threadIdx.x; i < p.V * 3; i += blockDim.x) sviews[i] = p.views[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_bins * 64; i += blockDim.x) {   // coalesced read of base (64, n_bins)
+        const int k = i / n_bins, j = i - k * n_bins;
+        T[k * kTStride + j] = __fmul_rn(__fmul_rn(__fmul_rn(base[i], sinp[j]), polar_step), azim_step);
+    }
     const int k = threadIdx.x & 63, g = threadIdx.x >> 6;
+    const float *Tk = T + k * kTStride;
     for (long long p0 = blockIdx.x * static_cast<long long>(kFusedPts); p0 < p.n_pts;
          p0 += gridDim.x * static_cast<long long>(kFusedPts)) {
-        __syncthreads();   // previous iteration's masks consumed (and, first time, T / sviews written)
+        __syncthreads();   // previous iteration's masks consumed (and, first time, T written)
         const int n = static_cast<int>(p.n_pts - p0 < kFusedPts ? p.n_pts - p0 : kFusedPts);
         for (int i = threadIdx.x; i < n * 3; i += blockDim.x) spts[i] = p.pts[(p0 + i / 3) * p.pts_dim + i % 3];
         for (int i = threadIdx.x; i < kFusedPts * 4; i += blockDim.x) mask[i] = 0u;
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(256) viewstate_harm_kernel(const ViewStatePara
                 while (m) {   // ascending bins; uniform across the 64 threads of the group
                     const int j = w * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    acc = __fadd_rn(acc, T[j * 64 + k]);
+                    acc = __fadd_rn(acc, Tk[j]);
                 }
             }
             out[(p0 + q) * 64 + k] = acc;
@@ -280,14 +288,14 @@ extern "C" int mac_viewstate_harm_f32(const float *pts, int pts_dim, const float
     p.azim_wrap = -((n_azim + 1) / 2);
     p.elev_shift = n_elev / 2;
     const int n_bins = n_elev * n_azim;
-    const size_t smem = (static_cast<size_t>(n_bins) * 64 + 3 * static_cast<size_t>(V) + 3 * kFusedPts) * sizeof(float) +
+    const size_t smem = (64 * static_cast<size_t>(n_bins | 1) + kMaxBins + 3 * static_cast<size_t>(V) + 3 * kFusedPts) * sizeof(float) +
                         kFusedPts * 4 * sizeof(unsigned);
     static DeviceOnce once;
     if (int rc = ensure_dynamic_smem(once, viewstate_harm_kernel, 96 * 1024)) return rc;
     const long long want = (p.n_pts + kFusedPts - 1) / kFusedPts;
     int device = 0;
     MAC_CUDA(cudaGetDevice(&device));
-    const long long resident = static_cast<long long>(sm_count(device)) * 4;   // 4 CTAs / SM (<= 32 KB of table each)
+    const long long resident = static_cast<long long>(sm_count(device)) * 8;   // 8 CTAs / SM (~27 KB of shared memory each)
     const int grid = static_cast<int>(want < resident ? want : resident);
     viewstate_harm_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
         p, base, h_polar, out, static_cast<float>(M_PI / (n_elev + 1)), static_cast<float>(2.0 * M_PI / n_azim));
