@@ -418,20 +418,27 @@ def run_ours(args, cfg):
             p_h, h_h = pinned_np[i % 2]
             s = torch.from_numpy(ops.coverage_gain_host(p_h, h_h, cams_np, use_sigmoid=vis.use_sigmoid, device=local_rank))
             return s, parallel.nbv_argmax(s)
-        # N > 1: every rank uploads 1/N of the point rows from pinned host memory and one NCCL all-gather over NVLink
-        # completes the (replicated) point set on every GPU: each input byte crosses PCIe once, not N times
+        # N > 1: the step partitioned over the POINTS: every rank uploads only its own rows (tile-aligned 1/N of every
+        # cloud) from pinned host memory, integrates all C cameras over them and exchanges exact int64 partial sums
+        # inside the scoring kernel (PeerScoreBoard.step_points): each input byte crosses one PCIe link once, nothing is
+        # replicated over NVLink first, and the scores are bitwise those of the camera-sharded `value` step
         p_h, h_h = pinned[i % 2]
-        pts = parallel.upload_rows_sharded(p_h.view(B * P, -1), dev, buf=e2e_bufs[0]).view(B, P, -1)
-        harm = parallel.upload_rows_sharded(h_h.view(B * P, 64), dev, buf=e2e_bufs[1]).view(B, P, 64)
         cam_d = cams_pin.to(dev, non_blocking=True)
         if board is not None:
-            s, b = board.step(pts, harm, cam_d, use_sigmoid=vis.use_sigmoid)
-        else:
+            e2e_bufs[0].copy_(p_h[:, p0:p1], non_blocking=True)
+            e2e_bufs[1].copy_(h_h[:, p0:p1], non_blocking=True)
+            s, b = board.step_points(e2e_bufs[0], e2e_bufs[1], cam_d, P, use_sigmoid=vis.use_sigmoid)
+        else:   # no peer board: replicate the points (1/N upload + NCCL all-gather), camera-sharded step + NCCL gather
+            pts = parallel.upload_rows_sharded(p_h.view(B * P, -1), dev, buf=e2e_bufs[0]).view(B, P, -1)
+            harm = parallel.upload_rows_sharded(h_h.view(B * P, 64), dev, buf=e2e_bufs[1]).view(B, P, 64)
             s, b = parallel.sharded_coverage_gain(vis.compute_coverage_gain, pts, harm, cam_d)
         return s.cpu(), b.cpu()
 
     e2e_bufs = [None, None]
-    if world > 1:
+    p0, p1 = parallel.point_partition(P, world, rank)
+    if world > 1 and board is not None:
+        e2e_bufs = [torch.empty((B, p1 - p0, host_sets[0][0].shape[-1]), device=dev), torch.empty((B, p1 - p0, 64), device=dev)]
+    elif world > 1:
         n_rows = -(-(B * P) // world) * world
         e2e_bufs = [torch.empty((n_rows, host_sets[0][0].shape[-1]), device=dev), torch.empty((n_rows, 64), device=dev)]
 
@@ -458,6 +465,16 @@ def run_ours(args, cfg):
         e2e_each.append(1e3 * (time.perf_counter() - t_i))
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
+    if world == 1:   # the link floor again, after the timed loop (host memory / link state drifts between runs)
+        dst = [torch.empty_like(t, device=dev) for t in pinned[0]]
+        for i in range(6):
+            torch.cuda.synchronize()
+            t_i = time.perf_counter()
+            for d_t, s_t in zip(dst, pinned[i % 2]):
+                d_t.copy_(s_t, non_blocking=True)
+            torch.cuda.synchronize()
+            floor_each.append(1e3 * (time.perf_counter() - t_i))
+        del dst
     e2e_median_ms = statistics.median(e2e_each)   # reported next to the mean: single steps occasionally take +0.4 ms (host jitter)
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
@@ -501,6 +518,9 @@ def run_ours(args, cfg):
             check["reference_fp32_err_vs_f64_top4"] = float(np.abs(ref32 - truth[:1, top]).max())
         if single is not None:
             check["bitwise_equal_to_single_gpu"] = bool(torch.equal(single.cpu(), scores.cpu()))
+            e2e_set = dev_sets[(e2e_steps - 1) % 2]
+            check["e2e_point_sharded_bitwise_equal_to_single_gpu"] = bool(torch.equal(
+                ops.coverage_gain(e2e_set[0], e2e_set[1], cams, use_sigmoid=vis.use_sigmoid).cpu(), s_host))
             check["argmax_equal_to_single_gpu"] = bool(torch.equal(single.argmax(-1).cpu(), best.reshape(-1).cpu()))
 
     # ---- BASELINE.json configs[4] as the online loop SURVEY.md section 8d defines (cfg5 only): 50 NBV steps, each = view
@@ -539,9 +559,10 @@ def run_ours(args, cfg):
                     "pinned_h2d_copy_alone_ms": statistics.median(floor_each[2:]) if floor_each else None,
                     "api": ("mac_covgain_host (C ABI, pinned HOST buffers in, host scores out; 8 H2D slices overlapped with the "
                             "kernel) + argmax on the host") if world == 1 else
-                           "pinned host tensors -> each rank uploads 1/N of the point rows + NCCL all-gather over NVLink "
-                           "(parallel.upload_rows_sharded) -> scoring step (same as value) -> scores, argmax .cpu(); "
-                           "h2d bytes are the total over all ranks"},
+                           "pinned host tensors -> each rank uploads its own 1/N of the point rows -> point-partitioned "
+                           "scoring step (PeerScoreBoard.step_points: all cameras over the local points, exact int64 partial "
+                           "sums exchanged over NVLink inside the kernel, bitwise the scores of `value`) -> scores, argmax "
+                           ".cpu(); h2d bytes are the total over all ranks"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,

@@ -125,6 +125,10 @@ typedef struct mac_peer_board {
     unsigned int epoch;
     float *scores[MAC_MAX_PEERS];
     unsigned int *flags[MAC_MAX_PEERS];
+    /* point-sharded steps only (mac_covgain_push_partial_argmax_f32), else unused: partials[r] = rank r's region of
+     * world * B * C exact fixed-point sums (int64, slot [s * B * C + i] written by rank s) followed by world * B * C
+     * u32 non-finite markers, as mapped into this process */
+    void *partials[MAC_MAX_PEERS];
 } mac_peer_board_t;
 
 int mac_covgain_push_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams, int B,
@@ -143,6 +147,17 @@ int mac_covgain_push_argmax_f32(const float *pts, int pts_dim, const float *harm
                                 int C, int cam_begin, int cam_end, int act, void *workspace, size_t workspace_bytes,
                                 const mac_peer_board_t *board, long long *best, int *status, void *ev_begin,
                                 void *ev_end, void *stream);
+
+/* The same step partitioned over the POINTS instead of the cameras (an extension for callers whose points arrive from
+ * the host: every rank then uploads and reads only its own rows): this rank integrates ALL C cameras over its P_local
+ * points (pts / harmonics hold only those rows), the finishing CTA stores the exact fixed-point partial sums into slot
+ * `rank` of every peer's partial region (board->partials), raises the flags, waits for all ranks, adds the `world` partial
+ * sums of every camera -- integer additions, so the scores are bitwise those of one GPU integrating all p_total points --
+ * writes the (B, C) means into its own score board (board->scores[rank]) and takes the argmax. */
+size_t mac_covgain_partial_region_bytes(int world, int B, int C);
+int mac_covgain_push_partial_argmax_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams, int B,
+                                        int P_local, int p_total, int C, int act, void *workspace, size_t workspace_bytes,
+                                        const mac_peer_board_t *board, long long *best, int *status, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused linear layer on tcgen05 tensor cores (building block of SconeOcc / SconeVis; replaces the

@@ -42,7 +42,8 @@ MAX_PEERS = 16
 class PeerBoard(ctypes.Structure):
     """mac_peer_board_t of include/macarons_b200.h"""
     _fields_ = [("world", ctypes.c_int), ("rank", ctypes.c_int), ("epoch", ctypes.c_uint),
-                ("scores", ctypes.c_void_p * MAX_PEERS), ("flags", ctypes.c_void_p * MAX_PEERS)]
+                ("scores", ctypes.c_void_p * MAX_PEERS), ("flags", ctypes.c_void_p * MAX_PEERS),
+                ("partials", ctypes.c_void_p * MAX_PEERS)]
 
 
 SYMBOLS["mac_covgain_push_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p,
@@ -54,6 +55,12 @@ SYMBOLS["mac_covgain_push_argmax_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_in
                                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
                                                          ctypes.POINTER(PeerBoard), ctypes.c_void_p, ctypes.c_void_p,
                                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p])
+SYMBOLS["mac_covgain_partial_region_bytes"] = (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
+SYMBOLS["mac_covgain_push_partial_argmax_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p,
+                                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                                 ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                                                 ctypes.POINTER(PeerBoard), ctypes.c_void_p, ctypes.c_void_p,
+                                                                 ctypes.c_void_p])
 SYMBOLS["mac_gather_wait_argmax"] = (ctypes.c_int, [_c_float_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint,
                                                     ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                     ctypes.c_void_p])

@@ -78,6 +78,10 @@ struct CovgainParams {
     // flags of all ranks on the LOCAL board and writes the replicated NBV index: the whole sharded step is one launch
     long long *best;
     int *status;
+    // point-sharded form (push_partial != 0): the finishing CTA pushes the exact partial sums of ALL cameras over this rank's
+    // points into slot push_rank of every peer's partial region, waits, adds the push_world partials and takes the argmax
+    int push_partial;
+    unsigned long long *part_dst[MAC_MAX_PEERS];
 };
 
 struct Ray {
@@ -324,6 +328,43 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
         __syncthreads();
         if (is_last && !prm.finalize) {
             if (threadIdx.x == 0) *prm.done = 0u, *prm.next_task = 0u;   // partial sums stay in the workspace for the next point slice
+        } else if (is_last && prm.push_partial) {
+            __threadfence();
+            const size_t BC = static_cast<size_t>(prm.B) * prm.C;
+            for (size_t i = threadIdx.x; i < BC; i += WARPS * 32) {
+                const unsigned long long q = atomicExch(prm.acc + i, 0ull);
+                const unsigned int bad = atomicExch(prm.flags + i, 0u);
+                for (int r = 0; r < prm.push_world; ++r) {   // peer-mapped stores into slot push_rank
+                    prm.part_dst[r][prm.push_rank * BC + i] = q;
+                    reinterpret_cast<unsigned int *>(prm.part_dst[r] + prm.push_world * BC)[prm.push_rank * BC + i] = bad;
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x < prm.push_world) st_release_sys(prm.push_flag[threadIdx.x] + prm.push_rank, prm.push_epoch);
+            if (threadIdx.x == 0) *prm.done = 0u, *prm.next_task = 0u;
+            __syncthreads();
+            if (wait_for_ranks<WARPS * 32>(prm.push_flag[prm.push_rank], prm.push_world, prm.push_epoch, prm.status)) {
+                const unsigned long long *mine = prm.part_dst[prm.push_rank];
+                const unsigned int *mine_bad = reinterpret_cast<const unsigned int *>(mine + prm.push_world * BC);
+                float *scores = prm.push_dst[prm.push_rank];
+                const double unfix = 1.0 / static_cast<double>(SIGMOID ? kFixSigmoid : kFixRelu);
+                for (size_t i = threadIdx.x; i < BC; i += WARPS * 32) {
+                    long long total = 0;
+                    unsigned int bad = 0;
+                    for (int r = 0; r < prm.push_world; ++r) {
+                        total += static_cast<long long>(__ldcg(mine + r * BC + i));   // integer sum: order-independent, exact
+                        bad |= __ldcg(mine_bad + r * BC + i);
+                    }
+                    const float t = static_cast<float>(static_cast<double>(total) * unfix);
+                    const float score = bad ? __int_as_float(0x7fc00000) : __fdiv_rn(t, static_cast<float>(prm.mean_count));
+                    scores[i] = score;
+                    if (prm.out) prm.out[i] = score;
+                }
+                __threadfence();
+                __syncthreads();
+                argmax_rows<WARPS * 32>(scores, prm.B, prm.C, prm.best);
+            }
         } else if (is_last) {
             __threadfence();
             const int nloc = prm.cam_end - prm.cam_begin;
@@ -391,7 +432,7 @@ int make_harmonics_map(CUtensorMap *map, const float *harm, int B, int P)
 int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *harm, const float *cams, float *out,
                     int B, int P, int C, int cam_begin, int cam_end, int act, void *workspace,
                     size_t workspace_bytes, void *stream, const mac_peer_board_t *board = nullptr, int mean_count = 0,
-                    int finalize = 1, long long *best = nullptr, int *status = nullptr)
+                    int finalize = 1, long long *best = nullptr, int *status = nullptr, bool push_partial = false)
 {
     MAC_REQUIRE(pts && harm && cams && (out || board), "null tensor pointer");
     if (board) {
@@ -432,6 +473,13 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
         }
         prm.best = best;
         prm.status = status;
+        if (push_partial) {
+            prm.push_partial = 1;
+            for (int r = 0; r < board->world; ++r) {
+                MAC_REQUIRE(board->partials[r], "peer board: partial region %d is null", r);
+                prm.part_dst[r] = static_cast<unsigned long long *>(board->partials[r]);
+            }
+        }
     }
     if (reduce) {
         const size_t need = mac_covgain_workspace_bytes(B, C);
@@ -596,4 +644,27 @@ extern "C" int mac_covgain_push_argmax_f32(const float *pts, int pts_dim, const 
         return rc;
     if (ev_end) MAC_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_end), st));
     return MAC_OK;
+}
+
+extern "C" size_t mac_covgain_partial_region_bytes(int world, int B, int C)
+{
+    if (world <= 0 || B <= 0 || C <= 0) return 0;
+    return static_cast<size_t>(world) * B * C * (sizeof(unsigned long long) + sizeof(unsigned int));
+}
+
+extern "C" int mac_covgain_push_partial_argmax_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams,
+                                                   int B, int P_local, int p_total, int C, int act, void *workspace,
+                                                   size_t workspace_bytes, const mac_peer_board_t *board, long long *best,
+                                                   int *status, void *stream)
+{
+    if (!board || !best || !status) {
+        mac::set_error("mac_covgain_push_partial_argmax_f32 needs a peer board, best and status");
+        return MAC_ERR_INVALID_ARGUMENT;
+    }
+    if (p_total < P_local || P_local <= 0) {
+        mac::set_error("bad point partition: P_local=%d of p_total=%d", P_local, p_total);
+        return MAC_ERR_INVALID_ARGUMENT;
+    }
+    return mac::plan_and_launch(true, pts, pts_dim, harmonics, cams, nullptr, B, P_local, C, 0, C, act, workspace,
+                                workspace_bytes, stream, board, p_total, 1, best, status, true);
 }

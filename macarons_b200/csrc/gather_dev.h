@@ -15,14 +15,12 @@ __device__ __forceinline__ bool score_better(float av, int ai, float bv, int bi)
     return ai < bi;
 }
 
-// Called by all NT threads of ONE CTA.
+// Called by all NT threads of ONE CTA: wait (bounded, ~2 s) until the `world` arrival flags have reached `epoch`.
+// Returns false (and raises the sticky *status) if a peer never arrived.
 template <int NT>
-__device__ void wait_scores_and_argmax(const float *scores, const unsigned int *flags, int world, unsigned int epoch, int B,
-                                       int C, long long *best, int *status)
+__device__ bool wait_for_ranks(const unsigned int *flags, int world, unsigned int epoch, int *status)
 {
     __shared__ int timed_out;
-    __shared__ float s_val[NT];
-    __shared__ int s_idx[NT];
     if (threadIdx.x == 0) timed_out = 0;
     __syncthreads();
     if (threadIdx.x < world) {
@@ -40,9 +38,19 @@ __device__ void wait_scores_and_argmax(const float *scores, const unsigned int *
     }
     __syncthreads();
     if (timed_out) {
+        // *status is sticky: a timeout of an earlier step stays visible until the host clears it (PeerScoreBoard.check)
         if (threadIdx.x == 0) *status = 1;
-        return;
+        return false;
     }
+    return true;
+}
+
+// best[b] = first maximum of scores[b, :] (all NT threads of one CTA)
+template <int NT>
+__device__ void argmax_rows(const float *scores, int B, int C, long long *best)
+{
+    __shared__ float s_val[NT];
+    __shared__ int s_idx[NT];
     for (int b = 0; b < B; ++b) {
         float v = 0.f;
         int idx = 0x7fffffff;
@@ -71,7 +79,14 @@ __device__ void wait_scores_and_argmax(const float *scores, const unsigned int *
         if (threadIdx.x == 0) best[b] = s_idx[0];
         __syncthreads();
     }
-    // *status is sticky: a timeout of an earlier step stays visible until the host clears it (PeerScoreBoard.check)
+}
+
+template <int NT>
+__device__ void wait_scores_and_argmax(const float *scores, const unsigned int *flags, int world, unsigned int epoch, int B,
+                                       int C, long long *best, int *status)
+{
+    if (!wait_for_ranks<NT>(flags, world, epoch, status)) return;
+    argmax_rows<NT>(scores, B, C, best);
 }
 
 }  // namespace mac

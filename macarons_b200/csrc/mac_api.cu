@@ -1,5 +1,6 @@
 // C-ABI plumbing: version / error reporting / launch counter, and the host-buffer entry points.
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mac_common.h"
@@ -16,7 +17,8 @@ struct HostCache {  // per-thread device staging for the *_host entry points
     size_t bytes = 0;
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t copy_stream = nullptr;  // host -> device slices
-    cudaEvent_t landed[8] = {};
+    cudaStream_t copy_stream2 = nullptr; // optional second copy queue (MAC_HOST_COPY_STREAMS=2)
+    cudaEvent_t landed[64] = {};
 };
 thread_local HostCache g_cache;
 }  // namespace
@@ -62,6 +64,7 @@ extern "C" void mac_host_release(void)
     }
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    if (c.copy_stream2) cudaStreamDestroy(c.copy_stream2);
     for (cudaEvent_t e : c.landed)
         if (e) cudaEventDestroy(e);
     c = mac::HostCache();
@@ -96,6 +99,7 @@ extern "C" int mac_covgain_host(const float *pts, int pts_dim, const float *harm
         MAC_CUDA(cudaMalloc(&c.buf, need));
         MAC_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         MAC_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        MAC_CUDA(cudaStreamCreateWithFlags(&c.copy_stream2, cudaStreamNonBlocking));
         for (cudaEvent_t &e : c.landed) MAC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c.device = device;
         c.bytes = need;
@@ -111,20 +115,27 @@ extern "C" int mac_covgain_host(const float *pts, int pts_dim, const float *harm
                              c.stream));
     // One cloud with many points: the points arrive in slices on a copy stream while the kernel integrates the
     // previous slice (the partial sums stay in the fixed-point workspace between the slice launches).
-    const int n_slices = (B == 1 && P >= (1 << 16)) ? 8 : 1;
+    // MAC_HOST_SLICES / MAC_HOST_SKIP_KERNEL: tuning / diagnosis knobs of tools/bench_e2e.py (read once)
+    static const int env_slices = [] { const char *e = getenv("MAC_HOST_SLICES"); return e ? atoi(e) : 0; }();
+    static const bool skip_kernel = [] { const char *e = getenv("MAC_HOST_SKIP_KERNEL"); return e && atoi(e) != 0; }();
+    int n_slices = (B == 1 && P >= (1 << 16)) ? 8 : 1;
+    if (env_slices >= 1 && env_slices <= 64 && B == 1) n_slices = env_slices;
     if (n_slices > 1) {
         const int per = ((P + n_slices - 1) / n_slices + 31) / 32 * 32;
+        static const int copy_streams = [] { const char *e = getenv("MAC_HOST_COPY_STREAMS"); return e ? atoi(e) : 1; }();
         int k = 0;
         for (int p0 = 0; p0 < P; p0 += per, ++k) {
             const int np = P - p0 < per ? P - p0 : per;
+            cudaStream_t cs = (copy_streams == 2 && (k & 1)) ? c.copy_stream2 : c.copy_stream;
             MAC_CUDA(cudaMemcpyAsync(d_pts + static_cast<size_t>(p0) * pts_dim, pts + static_cast<size_t>(p0) * pts_dim,
-                                     sizeof(float) * np * static_cast<size_t>(pts_dim), cudaMemcpyHostToDevice, c.copy_stream));
+                                     sizeof(float) * np * static_cast<size_t>(pts_dim), cudaMemcpyHostToDevice, cs));
             MAC_CUDA(cudaMemcpyAsync(d_harm + static_cast<size_t>(p0) * MAC_N_HARMONICS,
                                      harmonics + static_cast<size_t>(p0) * MAC_N_HARMONICS,
                                      sizeof(float) * np * static_cast<size_t>(MAC_N_HARMONICS), cudaMemcpyHostToDevice,
-                                     c.copy_stream));
-            MAC_CUDA(cudaEventRecord(c.landed[k], c.copy_stream));
+                                     cs));
+            MAC_CUDA(cudaEventRecord(c.landed[k], cs));
             MAC_CUDA(cudaStreamWaitEvent(c.stream, c.landed[k], 0));
+            if (skip_kernel) continue;
             const int rc = covgain_accumulate(d_pts + static_cast<size_t>(p0) * pts_dim, pts_dim,
                                               d_harm + static_cast<size_t>(p0) * MAC_N_HARMONICS, d_cams, d_out, np, C, cam_begin,
                                               cam_end, act, d_ws, n_ws, P, p0 + np >= P ? 1 : 0, c.stream);

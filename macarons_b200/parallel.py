@@ -21,6 +21,15 @@ def camera_partition(n_cameras, world_size, rank):
     return c0, c0 + base + (1 if rank < rem else 0)
 
 
+def point_partition(n_points, world_size, rank, tile=32):
+    """Contiguous block [p0, p1) of rank `rank` when the POINTS are partitioned (PeerScoreBoard.step_points): whole
+    32-point tiles (the unit whose float sum the scoring kernel converts to exact fixed point), the first n_tiles % W
+    ranks get one tile more.  Tile-aligned boundaries make the partial sums add up to bitwise the single-GPU result."""
+    n_tiles = -(-int(n_points) // tile)
+    t0, t1 = camera_partition(n_tiles, world_size, rank)
+    return min(t0 * tile, n_points), min(t1 * tile, n_points)
+
+
 def _world(group):
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
@@ -104,8 +113,11 @@ class PeerScoreBoard:
         self.rank, self.world = _world(group)
         self.epoch = 0
         n_scores = self.B * self.C
-        self._flag_off = 2 * n_scores            # in 4-byte words: [board 0 | board 1 | flags(world) | pad]
-        words = self._flag_off + 64
+        self._flag_off = 2 * n_scores            # in 4-byte words: [board 0 | board 1 | flags(world) | pad | partials 0 | 1]
+        # partial-sum regions of the point-sharded step: per parity world * B * C int64 + world * B * C u32
+        self._part_off = self._flag_off + 64
+        self._part_words = 3 * self.world * n_scores
+        words = self._part_off + 2 * self._part_words
         if self.world > 1:
             grp = group if group is not None else dist.group.WORLD
             self._buf = symm_mem.empty(words, dtype=torch.float32, device=self.device)
@@ -132,6 +144,7 @@ class PeerScoreBoard:
             for r, b in enumerate(bases):
                 cb.scores[r] = b + 4 * parity * n_scores
                 cb.flags[r] = b + 4 * self._flag_off
+                cb.partials[r] = b + 4 * (self._part_off + parity * self._part_words)
             self._c_boards.append(cb)
             self._views.append(self._board(parity))
 
@@ -180,6 +193,35 @@ class PeerScoreBoard:
         _lib.check(self._lib.mac_covgain_push_argmax_f32(
             key[0], D, key[1], key[2], self.B, P, self.C, c0, c1, ops.ACT_SIGMOID if use_sigmoid else ops.ACT_RELU,
             ws.data_ptr(), ws.numel(), board, self.best.data_ptr(), self.status.data_ptr(), ev0, ev1, stream))
+        return self._views[parity], self.best
+
+    def step_points(self, pts_local, harmonics_local, X_cam, n_points_total, use_sigmoid=True):
+        """The step partitioned over the POINTS: this rank holds only its rows `point_partition(n_points_total, W, rank)`
+        of the clouds (pts_local (B, P_local, D), harmonics_local (B, P_local, 64)), integrates ALL cameras over them and
+        exchanges exact fixed-point partial sums (mac_covgain_push_partial_argmax_f32).  -> ((B, C) scores, (B,) argmax),
+        bitwise those of `step` / of one GPU.  Meant for inputs that arrive from the host: every rank uploads and reads
+        1 / W of the rows, and nothing has to be replicated over NVLink first."""
+        from . import _lib, ops
+        if torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                return self.step_points(pts_local, harmonics_local, X_cam, n_points_total, use_sigmoid=use_sigmoid)
+        p_c, h_c, x_c, B, P, D, C = ops._prep(pts_local, harmonics_local, X_cam)
+        if (B, C) != (self.B, self.C):
+            raise ValueError("board is (%d, %d), inputs are (%d, %d)" % (self.B, self.C, B, C))
+        p0, p1 = point_partition(n_points_total, self.world, self.rank)
+        if P != p1 - p0 or P == 0:
+            raise ValueError("rank %d of %d must hold rows [%d, %d) of the %d points (got %d rows)"
+                             % (self.rank, self.world, p0, p1, n_points_total, P))
+        self.epoch += 1
+        parity = self.epoch & 1
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ws = ops._workspace(self.device, B, C)
+        board = self._c_boards[parity]
+        board.epoch = self.epoch & 0xFFFFFFFF
+        _lib.check(self._lib.mac_covgain_push_partial_argmax_f32(
+            p_c.data_ptr(), D, h_c.data_ptr(), x_c.data_ptr(), B, P, int(n_points_total), C,
+            ops.ACT_SIGMOID if use_sigmoid else ops.ACT_RELU, ws.data_ptr(), ws.numel(), board, self.best.data_ptr(),
+            self.status.data_ptr(), stream))
         return self._views[parity], self.best
 
     def check(self):

@@ -276,6 +276,11 @@ def test_fused_push_and_argmax_single_rank(cuda_device):
         board.check()
         assert torch.equal(scores, want)
         assert torch.equal(best, want.argmax(-1))
+    # point-partitioned form at world size 1: all points are "local"
+    for _ in range(2):
+        scores, best = board.step_points(*d, 900)
+        board.check()
+        assert torch.equal(scores, want) and torch.equal(best, want.argmax(-1))
     # ties and NaN follow torch.argmax: first maximum, NaN is maximal
     s = torch.tensor([[0.5, 0.7, 0.7, 0.1], [0.2, float("nan"), 0.9, float("nan")]], device=cuda_device)
     flags = torch.full((1,), 5, dtype=torch.int32, device=cuda_device)

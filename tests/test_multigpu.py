@@ -43,6 +43,14 @@ def _worker(rank, world, port, ret):
         s4, b4 = board4.step(*d4)
         board4.check()
         ok_fused = ok_fused and torch.equal(s4, full4) and torch.equal(b4, full4.argmax(-1))
+        # the step partitioned over the points (each rank holds only its rows): exact partial sums -> bitwise equal
+        p0, p1 = parallel.point_partition(3000, world, rank)
+        for _ in range(3):
+            sp, bp = board.step_points(d[0][:, p0:p1].contiguous(), d[1][:, p0:p1].contiguous(), d[2], 3000)
+            board.check()
+            ok_fused = ok_fused and torch.equal(sp, full) and torch.equal(bp, full.argmax(-1))
+        s_again, _ = board.step(*d)          # the two kinds of step can be mixed on one board
+        ok_fused = ok_fused and torch.equal(s_again, full)
         # online loop: clouds of the SconeVis forward sharded over the ranks + camera-sharded scoring reproduces the
         # single-GPU loop (same chosen camera sequence, same final scores)
         import contextlib

@@ -58,6 +58,18 @@ def _worker(rank, world, port, C, ret):
         dist.destroy_process_group()
 
 
+def test_point_partition_is_tile_aligned_and_covers():
+    for P in (1, 31, 32, 33, 2048, 200704, 200705):
+        for W in (1, 2, 3, 8):
+            blocks = [parallel.point_partition(P, W, r) for r in range(W)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == P
+            for (a0, a1), (b0, b1) in zip(blocks, blocks[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert all(b0 % 32 == 0 for b0, b1 in blocks if b1 > b0)
+            sizes = [b1 - b0 for b0, b1 in blocks]
+            assert max(sizes) - min(sizes) <= 32 + 31
+
+
 @pytest.mark.parametrize("world,C", [(2, 9), (3, 7), (2, 1)])
 def test_sharded_coverage_gain_gloo(world, C):
     ctx = mp.get_context("spawn")

@@ -21,6 +21,17 @@ def wall(fn, n=20):
     torch.cuda.synchronize()
     return 1e3 * (time.perf_counter() - t0) / n
 
+if len(sys.argv) > 1 and sys.argv[1] == "quick":
+    pn, hn, cn = pp.numpy(), hp.numpy(), cams.numpy()
+    ops.coverage_gain_host(pn, hn, cn, device=0)
+    ts = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        ops.coverage_gain_host(pn, hn, cn, device=0)
+        ts.append(1e3 * (time.perf_counter() - t0))
+    ts.sort()
+    print("mac_covgain_host median %.3f ms min %.3f ms" % (ts[len(ts) // 2], ts[0]))
+    sys.exit(0)
 print("H2D pinned 54.6 MB        %.3f ms" % wall(lambda: (dp.copy_(pp, non_blocking=True), dh.copy_(hp, non_blocking=True))))
 print("H2D pageable              %.3f ms" % wall(lambda: (dp.copy_(pts), dh.copy_(harm)), 5))
 dc = cams.to(dev)
