@@ -424,7 +424,10 @@ def run_ours(args, cfg):
         # replicated over NVLink first, and the scores are bitwise those of the camera-sharded `value` step
         p_h, h_h = pinned[i % 2]
         cam_d = cams_pin.to(dev, non_blocking=True)
-        if board is not None:
+        if board is not None and B == 1:
+            # one cloud: the rows arrive in slices on a copy stream, slice k is integrated while slice k+1 is in flight
+            s, b = board.step_points_from_host(p_h, h_h, cam_d, use_sigmoid=vis.use_sigmoid, slices=4, bufs=e2e_bufs)
+        elif board is not None:
             e2e_bufs[0].copy_(p_h[:, p0:p1], non_blocking=True)
             e2e_bufs[1].copy_(h_h[:, p0:p1], non_blocking=True)
             s, b = board.step_points(e2e_bufs[0], e2e_bufs[1], cam_d, P, use_sigmoid=vis.use_sigmoid)

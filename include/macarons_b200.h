@@ -154,6 +154,12 @@ int mac_covgain_push_argmax_f32(const float *pts, int pts_dim, const float *harm
  * `rank` of every peer's partial region (board->partials), raises the flags, waits for all ranks, adds the `world` partial
  * sums of every camera -- integer additions, so the scores are bitwise those of one GPU integrating all p_total points --
  * writes the (B, C) means into its own score board (board->scores[rank]) and takes the argmax. */
+/* Accumulate a slice of the points of ONE cloud (B = 1) into the workspace without finishing: lets a caller whose points
+ * arrive in slices (host -> device copies on another stream) integrate slice k while slice k+1 is in flight; the call that
+ * carries the last slice (mac_covgain_push_partial_argmax_f32, or mac_covgain_f32 over the remaining rows with the same
+ * workspace) adds these sums to its own. */
+int mac_covgain_accumulate_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams, int P_slice, int C,
+                               int act, void *workspace, size_t workspace_bytes, void *stream);
 size_t mac_covgain_partial_region_bytes(int world, int B, int C);
 int mac_covgain_push_partial_argmax_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams, int B,
                                         int P_local, int p_total, int C, int act, void *workspace, size_t workspace_bytes,

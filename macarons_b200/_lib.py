@@ -55,6 +55,9 @@ SYMBOLS["mac_covgain_push_argmax_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_in
                                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
                                                          ctypes.POINTER(PeerBoard), ctypes.c_void_p, ctypes.c_void_p,
                                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p])
+SYMBOLS["mac_covgain_accumulate_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_int,
+                                                        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                                        ctypes.c_void_p])
 SYMBOLS["mac_covgain_partial_region_bytes"] = (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
 SYMBOLS["mac_covgain_push_partial_argmax_f32"] = (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, _c_float_p,
                                                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -668,3 +668,13 @@ extern "C" int mac_covgain_push_partial_argmax_f32(const float *pts, int pts_dim
     return mac::plan_and_launch(true, pts, pts_dim, harmonics, cams, nullptr, B, P_local, C, 0, C, act, workspace,
                                 workspace_bytes, stream, board, p_total, 1, best, status, true);
 }
+
+extern "C" int mac_covgain_accumulate_f32(const float *pts, int pts_dim, const float *harmonics, const float *cams, int P_slice,
+                                          int C, int act, void *workspace, size_t workspace_bytes, void *stream)
+{
+    // finalize = 0: the exact partial sums of this slice of ONE cloud stay in the workspace; a later
+    // mac_covgain_f32-family call on the same workspace (e.g. mac_covgain_push_partial_argmax_f32 with the last slice) adds
+    // its own points and finishes.  mean_count is irrelevant here.
+    return mac::plan_and_launch(true, pts, pts_dim, harmonics, cams, reinterpret_cast<float *>(workspace) /* unused, non-null */,
+                                1, P_slice, C, 0, C, act, workspace, workspace_bytes, stream, nullptr, P_slice, 0);
+}

@@ -224,6 +224,59 @@ class PeerScoreBoard:
             self.status.data_ptr(), stream))
         return self._views[parity], self.best
 
+    def step_points_from_host(self, pts_host, harmonics_host, X_cam, use_sigmoid=True, slices=4, bufs=None):
+        """`step_points` for ONE cloud (B = 1) whose points live in (pinned) host memory: pts_host (1, P, D) and
+        harmonics_host (1, P, 64) are the FULL host tensors; this rank copies only its rows, in `slices` pieces on a copy
+        stream, and integrates piece k (mac_covgain_accumulate_f32) while piece k+1 crosses PCIe; the last piece goes
+        through the fused exchange.  `bufs`: optional (pts, harmonics) device buffers of at least this rank's row count.
+        -> ((1, C) scores, (1,) argmax), bitwise those of `step`."""
+        from . import _lib, ops
+        if self.B != 1 or pts_host.shape[0] != 1:
+            raise ValueError("step_points_from_host handles one cloud (B = 1)")
+        P, D = pts_host.shape[1], pts_host.shape[2]
+        p0, p1 = point_partition(P, self.world, self.rank)
+        n = p1 - p0
+        if n == 0:
+            raise ValueError("rank %d of %d has no points (P = %d)" % (self.rank, self.world, P))
+        with torch.cuda.device(self.device):
+            if bufs is None:
+                bufs = (torch.empty((1, n, D), dtype=torch.float32, device=self.device),
+                        torch.empty((1, n, 64), dtype=torch.float32, device=self.device))
+            d_pts, d_harm = bufs[0][:, :n], bufs[1][:, :n]
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            main = torch.cuda.current_stream(self.device)
+            per = max(32, -(-(-(-n // max(1, int(slices)))) // 32) * 32)          # whole tiles per slice
+            bounds = list(range(0, n, per)) + [n]
+            events = []
+            self._copy_stream.wait_stream(main)            # the buffers may still be read by the previous step
+            with torch.cuda.stream(self._copy_stream):
+                for a, b in zip(bounds, bounds[1:]):
+                    d_pts[:, a:b].copy_(pts_host[:, p0 + a:p0 + b], non_blocking=True)
+                    d_harm[:, a:b].copy_(harmonics_host[:, p0 + a:p0 + b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                    events.append(ev)
+            x_c = X_cam.contiguous()
+            ws = ops._workspace(self.device, 1, self.C)
+            act = ops.ACT_SIGMOID if use_sigmoid else ops.ACT_RELU
+            for k, (a, b) in enumerate(zip(bounds, bounds[1:])):
+                main.wait_event(events[k])
+                last = k == len(bounds) - 2
+                if not last:
+                    _lib.check(self._lib.mac_covgain_accumulate_f32(d_pts[:, a:b].data_ptr(), D, d_harm[:, a:b].data_ptr(),
+                                                                    x_c.data_ptr(), b - a, self.C, act, ws.data_ptr(),
+                                                                    ws.numel(), main.cuda_stream))
+                else:
+                    self.epoch += 1
+                    parity = self.epoch & 1
+                    board = self._c_boards[parity]
+                    board.epoch = self.epoch & 0xFFFFFFFF
+                    _lib.check(self._lib.mac_covgain_push_partial_argmax_f32(
+                        d_pts[:, a:b].data_ptr(), D, d_harm[:, a:b].data_ptr(), x_c.data_ptr(), 1, b - a, int(P), self.C, act,
+                        ws.data_ptr(), ws.numel(), board, self.best.data_ptr(), self.status.data_ptr(), main.cuda_stream))
+            return self._views[parity], self.best
+
     def check(self):
         """Synchronises; raises if a wait timed out (a peer never arrived) in any step since the last check: the
         device-side status is sticky and is cleared here."""

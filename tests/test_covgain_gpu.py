@@ -281,6 +281,14 @@ def test_fused_push_and_argmax_single_rank(cuda_device):
         scores, best = board.step_points(*d, 900)
         board.check()
         assert torch.equal(scores, want) and torch.equal(best, want.argmax(-1))
+    # ... and one cloud uploaded from pinned host memory in slices (accumulate + fused finish)
+    p1, h1, c1 = synth.covgain_inputs(1, 4100, 21, seed=32)
+    want1 = ops.coverage_gain(p1.to(cuda_device), h1.to(cuda_device), c1.to(cuda_device))
+    board1 = parallel.PeerScoreBoard(1, 21, cuda_device)
+    for n_slices in (1, 2, 5):
+        s1, b1 = board1.step_points_from_host(p1.pin_memory(), h1.pin_memory(), c1.to(cuda_device), slices=n_slices)
+        board1.check()
+        assert torch.equal(s1, want1) and torch.equal(b1, want1.argmax(-1))
     # ties and NaN follow torch.argmax: first maximum, NaN is maximal
     s = torch.tensor([[0.5, 0.7, 0.7, 0.1], [0.2, float("nan"), 0.9, float("nan")]], device=cuda_device)
     flags = torch.full((1,), 5, dtype=torch.int32, device=cuda_device)

@@ -49,6 +49,14 @@ def _worker(rank, world, port, ret):
             sp, bp = board.step_points(d[0][:, p0:p1].contiguous(), d[1][:, p0:p1].contiguous(), d[2], 3000)
             board.check()
             ok_fused = ok_fused and torch.equal(sp, full) and torch.equal(bp, full.argmax(-1))
+        # one cloud from pinned host memory, uploaded in slices by each rank (its own rows only)
+        pts1, harm1, cams1 = synth.covgain_inputs(1, 5000, 33, seed=80)
+        full1 = ops.coverage_gain(pts1.to(dev), harm1.to(dev), cams1.to(dev))
+        board1 = parallel.PeerScoreBoard(1, 33, dev)
+        for n_slices in (1, 3, 4):
+            sh, bh = board1.step_points_from_host(pts1.pin_memory(), harm1.pin_memory(), cams1.to(dev), slices=n_slices)
+            board1.check()
+            ok_fused = ok_fused and torch.equal(sh, full1) and torch.equal(bh, full1.argmax(-1))
         s_again, _ = board.step(*d)          # the two kinds of step can be mixed on one board
         ok_fused = ok_fused and torch.equal(s_again, full)
         # online loop: clouds of the SconeVis forward sharded over the ranks + camera-sharded scoring reproduces the
