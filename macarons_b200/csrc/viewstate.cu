@@ -16,10 +16,33 @@ namespace {
 
 constexpr int kMaxBins = 128;
 
-// torch.remainder on fp32: fmod, then shifted into [0, d) for d > 0
-__device__ __forceinline__ float torch_remainder(float x, float d)
+// torch.remainder on fp32 for d > 0: fmod, then shifted into [0, d).  fmodf itself (a bit-serial long division in libdevice,
+// ~60 divergent instructions) is replaced by an exact equivalent for the small quotients that occur here (|x / d| < 2^22):
+// with n = trunc(x / d) the remainder x - n d is exactly representable, so ONE fma returns it without rounding; n comes
+// from a reciprocal multiply and is corrected by at most one step.  Non-finite or huge inputs take the library path.
+__device__ __forceinline__ float exact_fmod_pos(float ax, float d, float rd)   // ax >= 0
 {
-    float m = fmodf(x, d);
+    float n = truncf(ax * rd);
+    float r = fmaf(-n, d, ax);
+    if (r < 0.f) {
+        n -= 1.f;
+        r = fmaf(-n, d, ax);
+    } else if (r >= d) {
+        n += 1.f;
+        r = fmaf(-n, d, ax);
+    }
+    return r;
+}
+__device__ __forceinline__ float torch_remainder(float x, float d, float rd)
+{
+    const float ax = fabsf(x);
+    float m;
+    if (ax < 4194304.f * d) {
+        m = exact_fmod_pos(ax, d, rd);
+        m = x < 0.f ? -m : m;   // fmod carries the sign of x (and -0.0 for exact multiples, like fmodf)
+    } else {
+        m = fmodf(x, d);
+    }
     if (m != 0.f && m < 0.f) m += d;
     return m;
 }
@@ -31,6 +54,7 @@ struct ViewStateParams {
     long long n_pts;
     int pts_dim, V, n_elev, n_azim;
     float elev_step, azim_step, half_elev_step, half_azim_step;
+    float inv_elev_step, inv_azim_step;   // approximate reciprocals (exact_fmod_pos corrects the quotient)
     int elev_lo;         // Python -n_elev // 2
     int azim_hi;         // n_azim // 2
     int azim_wrap;       // Python -n_azim // 2
@@ -51,7 +75,7 @@ __device__ __forceinline__ int view_bin(const ViewStateParams &p, float dx, floa
     if (cos_azim >= 1.f) azim = 0.f;
     if (dx < 0.f) azim = -azim;
 
-    const float re = torch_remainder(elev, p.elev_step), ra = torch_remainder(azim, p.azim_step);
+    const float re = torch_remainder(elev, p.elev_step, p.inv_elev_step), ra = torch_remainder(azim, p.azim_step, p.inv_azim_step);
     float ie = (elev - re) / p.elev_step, ia = (azim - ra) / p.azim_step;
     if (re > p.half_elev_step) ie += 1.f;
     if (ra > p.half_azim_step) ia += 1.f;
@@ -62,8 +86,14 @@ __device__ __forceinline__ int view_bin(const ViewStateParams &p, float dx, floa
     if (ia < 0.f) ia += static_cast<float>(p.n_azim);
     const int n_bins = p.n_elev * p.n_azim;
     int idx = static_cast<int>(ie) * p.n_azim + static_cast<int>(ia);   // NaN rays -> 0 like a garbage long cast
-    idx %= n_bins;
-    if (idx < 0) idx += n_bins;
+    // Python modulo n_bins: one conditional step covers every finite ray (idx in [-n_azim, n_bins + n_azim))
+    if (idx >= -n_bins && idx < 2 * n_bins) {
+        if (idx >= n_bins) idx -= n_bins;
+        if (idx < 0) idx += n_bins;
+    } else {
+        idx %= n_bins;
+        if (idx < 0) idx += n_bins;
+    }
     return idx;
 }
 
@@ -140,7 +170,6 @@ __global__ void __launch_bounds__(256) view_harmonics_kernel(const float *__rest
 // state of 1.0, in the same ascending-bin order, so both paths give identical results.
 // Traffic: 4*pts_dim B read + 256 B written per point (vs + 2 * 4 * n_bins B for the materialised histogram).
 constexpr int kFusedPts = 64;   // points per block iteration
-// T[k][j] row stride = n_bins | 1 (odd: the reads of one bin by the 64 coefficient threads hit 32 distinct banks)
 // The binning is a long dependent chain (sqrt, 4 IEEE divisions, asinf, cosf, acosf, two exact remainders: ~600 issued
 // instructions per ray incl. divergent slow paths), i.e. latency bound: 8 CTAs x 8 warps per SM (32 registers) hide it.
 __global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateParams p, const float *__restrict__ base,
@@ -149,21 +178,20 @@ __global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateP
 {
     extern __shared__ float sm[];
     const int n_bins = p.n_elev * p.n_azim;
-    const int kTStride = n_bins | 1;
-    float *T = sm;                                                        // [64][kTStride]
-    float *sinp = T + 64 * kTStride;                                      // [n_bins]
+    float *T = sm;                                                        // [n_bins][64]
+    float *sinp = T + n_bins * 64;                                        // [n_bins]
     float *sviews = sinp + kMaxBins;                                      // [V][3]
     float *spts = sviews + 3 * p.V;                                       // [kFusedPts][3]
     unsigned *mask = reinterpret_cast<unsigned *>(spts + 3 * kFusedPts);  // [kFusedPts][4]
     for (int j = threadIdx.x; j < n_bins; j += blockDim.x) sinp[j] = sinf(h_polar[j]);
     for (int i = threadIdx.x; i < p.V * 3; i += blockDim.x) sviews[i] = p.views[i];
     __syncthreads();
-    for (int i = threadIdx.x; i < n_bins * 64; i += blockDim.x) {   // coalesced read of base (64, n_bins)
+    for (int i = threadIdx.x; i < n_bins * 64; i += blockDim.x) {   // coalesced read of base (64, n_bins), transposed store
         const int k = i / n_bins, j = i - k * n_bins;
-        T[k * kTStride + j] = __fmul_rn(__fmul_rn(__fmul_rn(base[i], sinp[j]), polar_step), azim_step);
+        T[j * 64 + k] = __fmul_rn(__fmul_rn(__fmul_rn(base[i], sinp[j]), polar_step), azim_step);
     }
-    const int k = threadIdx.x & 63, g = threadIdx.x >> 6;
-    const float *Tk = T + k * kTStride;
+    // phase 2 mapping: 16 threads per point, 4 consecutive coefficients per thread (one LDS.128 per set bin and thread)
+    const int k4 = (threadIdx.x & 15) * 4, g = threadIdx.x >> 4;
     for (long long p0 = blockIdx.x * static_cast<long long>(kFusedPts); p0 < p.n_pts;
          p0 += gridDim.x * static_cast<long long>(kFusedPts)) {
         __syncthreads();   // previous iteration's masks consumed (and, first time, T written)
@@ -179,18 +207,20 @@ __global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateP
             atomicOr(&mask[q * 4 + (b >> 5)], 1u << (b & 31));
         }
         __syncthreads();
-        for (int q = g; q < n; q += 4) {
-            float acc = 0.f;
+        for (int q = g; q < n; q += 16) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 unsigned m = mask[q * 4 + w];
-                while (m) {   // ascending bins; uniform across the 64 threads of the group
+                while (m) {   // ascending bins
                     const int j = w * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    acc = __fadd_rn(acc, Tk[j]);
+                    const float4 t = *reinterpret_cast<const float4 *>(T + j * 64 + k4);
+                    acc.x = __fadd_rn(acc.x, t.x), acc.y = __fadd_rn(acc.y, t.y);
+                    acc.z = __fadd_rn(acc.z, t.z), acc.w = __fadd_rn(acc.w, t.w);
                 }
             }
-            out[(p0 + q) * 64 + k] = acc;
+            *reinterpret_cast<float4 *>(out + (p0 + q) * 64 + k4) = acc;
         }
     }
 }
@@ -224,6 +254,7 @@ extern "C" int mac_view_state_f32(const float *pts, int pts_dim, const float *vi
     const double es = M_PI / (n_elev + 1), as = 2.0 * M_PI / n_azim;
     p.elev_step = static_cast<float>(es), p.azim_step = static_cast<float>(as);
     p.half_elev_step = static_cast<float>(es / 2.0), p.half_azim_step = static_cast<float>(as / 2.0);
+    p.inv_elev_step = 1.0f / p.elev_step, p.inv_azim_step = 1.0f / p.azim_step;
     p.elev_lo = -((n_elev + 1) / 2);    // Python floor division -n_elev // 2
     p.azim_hi = n_azim / 2;
     p.azim_wrap = -((n_azim + 1) / 2);  // Python -n_azim // 2
@@ -283,12 +314,13 @@ extern "C" int mac_viewstate_harm_f32(const float *pts, int pts_dim, const float
     const double es = M_PI / (n_elev + 1), as = 2.0 * M_PI / n_azim;
     p.elev_step = static_cast<float>(es), p.azim_step = static_cast<float>(as);
     p.half_elev_step = static_cast<float>(es / 2.0), p.half_azim_step = static_cast<float>(as / 2.0);
+    p.inv_elev_step = 1.0f / p.elev_step, p.inv_azim_step = 1.0f / p.azim_step;
     p.elev_lo = -((n_elev + 1) / 2);
     p.azim_hi = n_azim / 2;
     p.azim_wrap = -((n_azim + 1) / 2);
     p.elev_shift = n_elev / 2;
     const int n_bins = n_elev * n_azim;
-    const size_t smem = (64 * static_cast<size_t>(n_bins | 1) + kMaxBins + 3 * static_cast<size_t>(V) + 3 * kFusedPts) * sizeof(float) +
+    const size_t smem = (64 * static_cast<size_t>(n_bins) + kMaxBins + 3 * static_cast<size_t>(V) + 3 * kFusedPts) * sizeof(float) +
                         kFusedPts * 4 * sizeof(unsigned);
     static DeviceOnce once;
     if (int rc = ensure_dynamic_smem(once, viewstate_harm_kernel, 96 * 1024)) return rc;
