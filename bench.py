@@ -248,6 +248,10 @@ def path_stages(dev):
         depth = depth.to(dev).eval()
         d = [t.to(dev) for t in synth.depth_inputs(1, 256, 456, 7)]
         out["manydepth_forward_256x456_ms"] = timed(lambda: depth(d[0], d[1], d[2], d[3], d[4], dev, gt_pose=d[5]))
+    try:
+        out.update(chained_configs(dev, timed, vis, occ, depth_256=None))
+    except Exception as exc:   # informational
+        out["chained_configs_error"] = "%s: %s" % (type(exc).__name__, exc)
     out["note"] = "fp32-accurate (3xTF32) tcgen05 linear layers; reference on 8 CPU threads: SconeVis 140 ms, SconeOcc 64^3 ~77 s (SURVEY section 6)"
     return out
 
@@ -312,6 +316,83 @@ def online_loop(args, cfg, dev, vis, board, world, rank, n_steps=50, seq_len=204
         if rank == 0:   # single-GPU rerun of the same loop on rank 0: the sharded loop must reproduce it bit for bit
             solo, _ = nbv.scone_online_loop(vis, pts, cams, X_view, base, h_polar, h_azim, n_steps, seq_len=seq_len)
             out["same_sequence_as_single_gpu"] = bool(torch.equal(solo, chosen))
+    return out
+
+
+def chained_configs(dev, timed, vis, occ, depth_256=None):
+    """BASELINE.json configs[1..3] as CHAINED steps through the package's public API (device time, CUDA events):
+      cfg2  SCONE step: view harmonics -> SconeOcc on a 64^3 grid -> proxy sampling -> SconeVis -> 64 candidates -> argmax
+      cfg3  full MACARONS NBV step: depth 256x256 -> partial cloud -> scene update -> occupancy field (one ragged SconeOcc
+            forward over all occupied cells) -> 128 candidate poses -> argmax, on a scene populated by 3 earlier frames
+      cfg4  32 clouds x (64^3 grid + 256 candidates): what every GPU runs when depth / occupancy are replicated and only
+            the camera axis is sharded (north_star); at N GPUs the coverage part shrinks to 256 / N cameras per cloud."""
+    import contextlib
+    import io
+    import types
+    import torch
+    import synth
+    from macarons_b200 import nbv
+    from macarons_b200.networks import ManyDepth as MD
+    from macarons_b200.networks.Macarons import Macarons
+    from macarons_b200.utility import cameras, scene, scone_utils
+    out = {}
+    gen = torch.Generator().manual_seed(2)
+    base, h_polar, h_azim = scone_utils.get_all_harmonics_under_degree(8, 7, 14, dev)
+    lin = (torch.arange(64, dtype=torch.float32) + 0.5) / 64 - 0.5
+    X = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), dim=-1).view(1, -1, 3).to(dev)
+    X_view = synth.sphere_cameras(2, 1.5, gen).to(dev)
+
+    def scone_step(seed, n_cams):
+        pc = synth.airplane_surface(4096, torch.Generator().manual_seed(seed))[None].to(dev)
+        return nbv.scone_nbv_step(occ, vis, pc, X, X_view, synth.fibonacci_cameras(n_cams).to(dev), base, h_polar, h_azim,
+                                  seq_len=2048, max_points_per_pass=300000)
+
+    out["cfg2_scone_step_64cube_grid_64_candidates_ms"] = timed(lambda: scone_step(1, 64), iters=2)
+    out["cfg4_32_clouds_64cube_grid_256_candidates_per_gpu_ms"] = timed(lambda: [scone_step(100 + b, 256) for b in range(32)],
+                                                                        iters=1)
+
+    # ---- cfg3 ----
+    H = W = 256
+    with contextlib.redirect_stdout(io.StringIO()):
+        resnet = MD.ResNet18Trunk()
+        depth = MD.ManyDepth(MD.DepthDecoder(MD.FeatureExtractor(resnet), resnet, input_height=H, input_width=W), None)
+    depth.load_state_dict(synth.seeded_state_dict(depth.state_dict(), 5))
+    macarons = Macarons(depth.to(dev).eval(), occ, vis)
+    params = types.SimpleNamespace(harmonic_degree=8, view_state_n_elev=7, view_state_n_azim=14, n_view_state_cameras=98,
+                                   n_harmonics=64, k_for_knn=16, prediction_neighborhood_size=3, jz=False, ddp=False,
+                                   znear=0.5, zfar=750., gathering_factor=0.05, sensor_range=6.0, carving_tolerance=0.3,
+                                   seq_len=2048, min_occ_for_proxy_points=0.1, use_occ_to_sample_proxy_points=True,
+                                   distance_factor_th=17.0, image_height=H, image_width=W)
+    x_min, x_max = torch.tensor([-3.5, -2.0, -4.0]), torch.tensor([3.5, 2.5, 3.0])
+    common = dict(x_min=x_min.to(dev), x_max=x_max.to(dev), grid_l=5, grid_w=3, grid_h=5, n_proxy_points=100000, device=dev,
+                  view_state_n_elev=7, view_state_n_azim=14)
+    surface_scene = scene.Scene(cell_capacity=1000, cell_resolution=None, feature_dim=1, **common)
+    proxy_scene = scene.Scene(cell_capacity=100000, cell_resolution=0.001, feature_dim=1, score_threshold=0.95, **common)
+    proxy_scene.initialize_proxy_points()
+    nb = synth.ndc_bounds(H, W)
+    eyes = torch.tensor([[0.2, 0.4, -3.2], [2.0, 0.8, -2.0], [-2.2, 0.6, -1.5], [1.0, 1.0, 2.2], [-1.2, 0.5, 2.4]])
+    ce = (torch.rand(128, 3, generator=gen) - 0.5) * torch.tensor([6.0, 3.5, 6.0]) + torch.tensor([0.0, 0.3, -0.5])
+    cR, cT = cameras.look_at(ce, (torch.rand(128, 3, generator=gen) - 0.5) * 2.0)
+    cand = cameras.FoVCamera(cR, cT, zfar=750., device=dev)
+    timings, n_timed = {}, 0
+    for i in range(eyes.shape[0]):
+        R, T = cameras.look_at(eyes[i:i + 1], torch.zeros(1, 3))
+        cam = cameras.FoVCamera(R, T, zfar=750., device=dev)
+        camera = types.SimpleNamespace(image_height=H, image_width=W, zfar=750., gathering_factor=0.05, fov_camera=cam,
+                                       fov_camera_0=cam if i == 0 else camera0, X_cam=eyes[i:i + 1].to(dev), min_ndc_x=nb[0],
+                                       max_ndc_x=nb[1], min_ndc_y=nb[2], max_ndc_y=nb[3])
+        if i == 0:
+            camera0 = cam
+        fr = synth.depth_inputs(1, H, W, 20 + i)
+        frames = {k: v.to(dev) for k, v in zip(("x", "x_alpha", "R", "T", "zfar", "gt_pose"), fr)}
+        t = timings if i >= 3 else None
+        n_timed += i >= 3
+        cov, best, st = nbv.macarons_nbv_step(params, macarons, camera, surface_scene, proxy_scene, frames, ce.to(dev), cand,
+                                              timings=t)
+    stages = {k: v / n_timed for k, v in timings.items()}
+    out["cfg3_full_macarons_step_256x256_128_candidates_ms"] = sum(stages.values())
+    out["cfg3_stages"] = dict(stages, proxy_points=100000, proxy_points_scored=int(st["X_world"].shape[0]),
+                              scene_cells="5x3x5", frames_before_timing=3)
     return out
 
 

@@ -32,6 +32,7 @@ _TABLE = (
                                                                   "compute_occupancy_probability", "sample_proxy_points")),
     ("utility.macarons_utils", "macarons_b200.utility.macarons_utils", ("compute_occupancy_probability",
                                                                         "compute_scene_occupancy_probability_field",
+                                                                        "load_images_for_depth_model",
                                                                         "predict_coverage_gain_for_single_camera",
                                                                         "get_distance_factor", "get_distance_factor_threshold",
                                                                         "get_distance_factor_smooth")),

@@ -105,8 +105,29 @@ def scone_online_loop(scone_vis, pts, X_cam, X_view, base_harmonics, h_polar, h_
     return chosen, scores
 
 
+class _StageClock:
+    """CUDA events around the stages of a step (optional instrumentation: `timings` dict name -> milliseconds)."""
+
+    def __init__(self, timings, device):
+        self.t, self.dev, self.marks = timings, device, []
+
+    def mark(self, name):
+        if self.t is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.marks.append((name, ev))
+
+    def finish(self):
+        if self.t is None:
+            return
+        torch.cuda.synchronize(self.dev)
+        for (_, a), (name, b) in zip(self.marks, self.marks[1:]):
+            self.t[name] = self.t.get(name, 0.0) + a.elapsed_time(b)
+
+
 def macarons_nbv_step(params, macarons, camera, surface_scene, proxy_scene, frames, X_cams_world, fov_cameras, samples=None,
-                      depth_mask=None):
+                      depth_mask=None, timings=None):
     """One full MACARONS next-best-view step (BASELINE.json configs[2]; the loop body of reference testers/scene.py:352-456
     and trainers/train_macarons.py:228-315, without the simulator / renderer around it):
 
@@ -119,17 +140,21 @@ def macarons_nbv_step(params, macarons, camera, surface_scene, proxy_scene, fram
     `frames` = dict(x (1,3,H,W), x_alpha (1,n_alpha,3,H,W), R, T, zfar, gt_pose) as fed to `macarons(mode='depth', ...)`;
     `camera`: the reference's Camera or any object with image_height / image_width / zfar / gathering_factor / fov_camera /
     fov_camera_0 / X_cam / min_ndc_* / max_ndc_*; `fov_cameras`: ONE batched camera holding the C candidate poses (or a list
-    of C cameras), `X_cams_world` (C,3) their centres.  -> (coverage_gain (C,1), nbv index, dict of the stage outputs)."""
+    of C cameras), `X_cams_world` (C,3) their centres; `timings` (optional dict) receives the device time of every stage.
+    -> (coverage_gain (C,1), nbv index, dict of the stage outputs)."""
     from .utility import macarons_utils as mu
     dev = proxy_scene.proxy_points.device
     H, W = camera.image_height, camera.image_width
+    clock = _StageClock(timings, dev)
     with torch.no_grad():
+        clock.mark("start")
         pose, disp1 = macarons(mode='depth', x=frames["x"], x_alpha=frames["x_alpha"], R=frames["R"], T=frames["T"],
                                zfar=frames["zfar"], device=dev, gt_pose=frames["gt_pose"])[:2]
         depth = mu.compute_depth_from_disparity(params, disp1).permute(0, 2, 3, 1).contiguous()        # (1,H,W,1)
         mask = torch.ones(1, H, W, 1, dtype=torch.bool, device=dev) if depth_mask is None else depth_mask
         part_pc = mu.compute_partial_point_cloud(camera, depth=depth, mask=mask, fov_cameras=camera.fov_camera,
                                                  gathering_factor=params.gathering_factor, fov_range=params.sensor_range)
+        clock.mark("depth_forward_and_partial_cloud_ms")
         surface_scene.fill_cells(part_pc, features=torch.zeros(len(part_pc), 1, device=dev))
         fov_proxy_points, fov_proxy_mask = mu.get_points_in_fov(camera, proxy_scene.proxy_points, return_mask=True,
                                                                 fov_camera=None, fov_range=params.sensor_range)
@@ -141,12 +166,16 @@ def macarons_nbv_step(params, macarons, camera, surface_scene, proxy_scene, fram
         proxy_scene.update_proxy_supervision_occ(fov_proxy_mask, sgn_dists, tol=params.carving_tolerance)
         proxy_scene.update_proxy_out_of_field(fov_proxy_mask)
         surface_scene.set_all_features_to_value(value=1.)
+        clock.mark("scene_update_ms")
         X_world, view_harmonics, occ_probs = mu.compute_scene_occupancy_probability_field(params, macarons, camera,
                                                                                           surface_scene, proxy_scene, dev)
+        clock.mark("occupancy_field_ms")
         out = mu.predict_coverage_gains_for_cameras(params, macarons, proxy_scene, surface_scene, X_world, view_harmonics,
                                                     occ_probs, camera, X_cams_world, fov_cameras, samples=samples)
         coverage = out["coverage_gain"]
         best = torch.argmax(coverage.view(-1))       # strict '>' running maximum of testers/scene.py:454 = first maximum
+        clock.mark("candidate_scoring_ms")
+    clock.finish()
     stages = {"disp1": disp1, "depth": depth, "part_pc": part_pc, "fov_proxy_mask": fov_proxy_mask, "sgn_dists": sgn_dists,
               "X_world": X_world, "view_harmonics": view_harmonics, "occ_probs": occ_probs, "candidates": out}
     return coverage, best, stages

@@ -5,6 +5,7 @@ kernels of this package (same names, argument meaning and return values):
     compute_scene_occupancy_probability_field   reference :1395-1540 (all occupied cells in ONE ragged SconeOcc forward)
     predict_coverage_gain_for_single_camera     reference :1580-1738
     get_distance_factor / _threshold / _smooth  reference :1741-1788
+    load_images_for_depth_model / save_frame    reference :763-803, :2317-2335 (frames stay resident on the device)
 
 plus `predict_coverage_gains_for_cameras`, the batched form the reference does not have: the testers / trainers call
 `predict_coverage_gain_for_single_camera` once per neighbouring pose (testers/scene.py:434-456,
@@ -379,3 +380,71 @@ def get_signed_distance_to_depth_maps(camera, pts, depth_maps, mask, fov_camera=
     out = ops.signed_distance(pts, depth_maps.reshape(n_depths, H, W), mask.reshape(n_depths, H, W), rows, H, W,
                               1.1 * float(camera.zfar))
     return out.view(n_depths, -1, 1)
+
+
+# ---- frame files (reference :763-803 and the save half of Camera.capture_image :2317-2335) ---------------------------------
+# The reference writes every captured frame to `<dir>/<n>.pt` (torch.save of a dict rgb / zbuf / mask / R / T / zfar) and
+# re-reads the last n_frames + n_alpha of them from disk for EVERY depth prediction.  Here a frame that was saved (or
+# loaded once) stays resident on its device in a small per-directory cache, the files keep the reference's format (either
+# side can read the other's), and the loader fills preallocated batches instead of growing them with torch.cat.
+import os as _os
+
+_FRAME_CACHE = {}            # absolute frame path -> dict of tensors on the camera's device
+_FRAME_CACHE_LIMIT = 64      # frames kept resident (least recently used are dropped; the files remain)
+_FRAME_KEYS = ("rgb", "zbuf", "mask", "R", "T", "zfar")
+
+
+def _cache_frame(path, frame):
+    _FRAME_CACHE.pop(path, None)
+    _FRAME_CACHE[path] = frame
+    while len(_FRAME_CACHE) > _FRAME_CACHE_LIMIT:
+        _FRAME_CACHE.pop(next(iter(_FRAME_CACHE)))
+
+
+def clear_frame_cache():
+    _FRAME_CACHE.clear()
+
+
+def save_frame(camera, images, depth, fov_camera=None, dir_path=None):
+    """Store one captured frame as `<dir>/<camera.n_frames_captured>.pt` in the reference's format and advance the
+    counter (reference Camera.capture_image :2317-2335).  images (1,H,W,3), depth (1,H,W,1) z-buffer (-1 = background).
+    -> the frame's path (None when no directory is configured, like the reference which then saves nothing)."""
+    if fov_camera is None:
+        fov_camera = camera.fov_camera
+    if dir_path is None:
+        dir_path = getattr(camera, "save_dir_path", None)
+    if dir_path is None:
+        return None
+    frame = {"rgb": images, "zbuf": depth, "mask": depth > -1, "R": fov_camera.R, "T": fov_camera.T, "zfar": camera.zfar}
+    path = _os.path.abspath(_os.path.join(dir_path, str(camera.n_frames_captured) + ".pt"))
+    torch.save(frame, path)
+    _cache_frame(path, frame)
+    camera.n_frames_captured += 1
+    return path
+
+
+def load_images_for_depth_model(camera, n_frames, n_alpha, frame_nb=None, frames_dir_path=None, return_gt_zbuf=False):
+    """The last n_frames + n_alpha frames up to `frame_nb` (default: the latest captured), oldest first
+    -> (images (n,H,W,3), [zbuf (n,H,W,1),] mask (n,H,W,1) bool, R (n,3,3), T (n,3), zfar (n,))   [reference :763-803]."""
+    current = camera.n_frames_captured - 1 if frame_nb is None else frame_nb
+    if frames_dir_path is None:
+        frames_dir_path = camera.save_dir_path
+    n = n_frames + n_alpha
+    dev, H, W = camera.device, camera.image_height, camera.image_width
+    images = torch.empty(n, H, W, 3, device=dev)
+    mask = torch.empty(n, H, W, 1, device=dev)
+    R, T = torch.empty(n, 3, 3, device=dev), torch.empty(n, 3, device=dev)
+    zbuf = torch.empty(n, H, W, 1, device=dev) if return_gt_zbuf else None
+    for i in range(n):
+        path = _os.path.abspath(_os.path.join(frames_dir_path, str(current - (n - 1) + i) + ".pt"))
+        frame = _FRAME_CACHE.get(path)
+        if frame is None or frame["rgb"].device != torch.device(dev):
+            frame = torch.load(path, map_location=dev)
+        _cache_frame(path, frame)
+        images[i:i + 1], mask[i:i + 1], R[i:i + 1], T[i:i + 1] = frame["rgb"], frame["mask"], frame["R"], frame["T"]
+        if return_gt_zbuf:
+            zbuf[i:i + 1] = frame["zbuf"]
+    zfar = torch.Tensor([camera.zfar]).to(dev).expand(n)
+    if return_gt_zbuf:
+        return images, zbuf, mask.bool(), R, T, zfar
+    return images, mask.bool(), R, T, zfar

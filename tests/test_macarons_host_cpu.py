@@ -110,3 +110,77 @@ def test_view_space_bin_permutation_matches_reference_golden():
     for i in range(aa.shape[0]):
         R = o_cams.axis_angle_to_matrix(aa[i:i + 1])[0]
         assert np.array_equal(scone_utils.view_space_bin_permutation(R, 7, 14, T=T[i]).numpy(), g["indices"][i]), i
+
+
+def test_frame_files_round_trip_and_match_the_reference_loader(tmp_path):
+    """frames written by save_frame are the reference's `<n>.pt` dicts; the loader returns
+    what the reference's load_images_for_depth_model returns from the same directory (when the reference tree is here),
+    serves repeated loads from the resident cache and still reads frames it has never seen from disk."""
+    import types
+    from macarons_b200.utility import macarons_utils as mu
+    from oracle import cameras as o_cams
+    mu.clear_frame_cache()
+    gen = torch.Generator().manual_seed(4)
+    H, W = 12, 20
+    camera = types.SimpleNamespace(image_height=H, image_width=W, zfar=700., device="cpu", n_frames_captured=0,
+                                   save_dir_path=str(tmp_path), fov_camera=None)
+    frames = []
+    for i in range(5):
+        R, T = synth.look_at_RT(torch.rand(1, 3, generator=gen) * 4 + 1, torch.zeros(1, 3))
+        camera.fov_camera = o_cams.FoVPerspectiveCameras(R=R, T=T, zfar=700.)
+        rgb = torch.rand(1, H, W, 3, generator=gen)
+        zbuf = torch.where(torch.rand(1, H, W, 1, generator=gen) > 0.3, 1 + 5 * torch.rand(1, H, W, 1, generator=gen),
+                           torch.full((1, H, W, 1), -1.0))
+        path = mu.save_frame(camera, rgb, zbuf)
+        assert path.endswith("%d.pt" % i) and camera.n_frames_captured == i + 1
+        frames.append((rgb, zbuf, R, T))
+    on_disk = torch.load(str(tmp_path / "3.pt"))
+    assert set(on_disk) == {"rgb", "zbuf", "mask", "R", "T", "zfar"} and on_disk["zfar"] == 700.
+    assert torch.equal(on_disk["mask"], frames[3][1] > -1)
+    got = mu.load_images_for_depth_model(camera, n_frames=1, n_alpha=2, return_gt_zbuf=True)
+    images, zbuf, mask, R, T, zfar = got
+    assert images.shape == (3, H, W, 3) and mask.dtype == torch.bool and zfar.shape == (3,)
+    for k, i in enumerate((2, 3, 4)):      # oldest first, ending at the latest frame
+        assert torch.equal(images[k:k + 1], frames[i][0]) and torch.equal(zbuf[k:k + 1], frames[i][1])
+        assert torch.equal(R[k:k + 1], frames[i][2]) and torch.equal(T[k:k + 1], frames[i][3])
+    mu.clear_frame_cache()                   # cold: everything comes from the files
+    cold = mu.load_images_for_depth_model(camera, n_frames=1, n_alpha=2, frame_nb=3)
+    assert torch.equal(cold[0][2:3], frames[3][0]) and len(cold) == 5
+    import os
+    if os.path.isdir("/root/reference/macarons"):
+        import sys
+        sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+        import ref_shim
+        ref_shim.install()
+        from macarons.utility import macarons_utils as ref_mu
+        want = ref_mu.load_images_for_depth_model(camera, n_frames=1, n_alpha=2, return_gt_zbuf=True)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+
+
+def test_fov_camera_matches_the_pytorch3d_restatement():
+    """macarons_b200.utility.cameras.FoVCamera (the package's own camera for machines without pytorch3d) against
+    oracle/cameras.py (the restated pytorch3d conventions the reference goldens were generated with)."""
+    from macarons_b200.utility import cameras
+    from oracle import cameras as o_cams
+    gen = torch.Generator().manual_seed(12)
+    eye = (torch.rand(5, 3, generator=gen) - 0.5) * 8
+    at = (torch.rand(5, 3, generator=gen) - 0.5) * 2
+    R, T = cameras.look_at(eye, at)
+    R0, T0 = synth.look_at_RT(eye, at)
+    assert torch.allclose(R, R0, atol=1e-6) and torch.allclose(T, T0, atol=1e-5)
+    ours = cameras.FoVCamera(R, T, zfar=750.)
+    ref = o_cams.FoVPerspectiveCameras(R=R, T=T, zfar=750.)
+    pts = (torch.rand(5, 40, 3, generator=gen) - 0.5) * 6
+    for name in ("get_world_to_view_transform", "get_full_projection_transform", "get_projection_transform"):
+        a, b = getattr(ours, name)(), getattr(ref, name)()
+        assert torch.allclose(a.get_matrix(), b.get_matrix(), atol=1e-6), name
+        assert torch.allclose(a.transform_points(pts), b.transform_points(pts), rtol=1e-5, atol=1e-5), name
+    assert torch.allclose(ours.get_camera_center(), ref.get_camera_center(), atol=1e-5)
+    inv = ours.get_world_to_view_transform().inverse()
+    assert torch.allclose(inv.transform_points(ours.get_world_to_view_transform().transform_points(pts)), pts, atol=1e-4)
+    full_inv = ours.get_full_projection_transform().inverse().get_matrix()
+    assert torch.allclose(full_inv, ref.get_full_projection_transform().inverse().get_matrix(), rtol=1e-3, atol=1e-3)
+    one = ours[2]
+    assert len(one) == 1 and torch.equal(one.R, R[2:3]) and one.transform_points if hasattr(one, "transform_points") else True
+    assert ours.get_world_to_view_transform().transform_points(pts[0, :, :].reshape(-1, 3)[:7]).shape[-1] == 3
