@@ -99,12 +99,17 @@ class SconeOcc(nn.Module):
             raise NotImplementedError("attention masks are never used on the NBV path (SURVEY.md A.4)")
         if self.training and self.dropout is not None:
             raise NotImplementedError("the fused SconeOcc forward has no dropout: call .eval() (dropout=%r)" % self.dropout)
-        ops.refuse_grad("SconeOcc.forward", pc, x, view_harmonics, module=self)
         global_idx, scale_idx = self.draw_subsamples(pc.shape[1])
         clouds = [pc]
         for idx in scale_idx:
             clouds.append(clouds[-1][:, idx.to(pc.device)])
         pc_global = pc[:, global_idx.to(pc.device)]
+        if ops.wants_grad(pc, x, view_harmonics, module=self):
+            # training: CUDA forward, backward by recomputation under torch.autograd (networks/_backward.py)
+            from ._backward import SconeOccFunction
+            out = SconeOccFunction.apply(self, pc_global.contiguous(), *[c.contiguous() for c in clouds], x, view_harmonics,
+                                         *self.parameters())
+            return out.view(pc.shape[0], x.shape[1], self.output_dim)
         out = ops.sconeocc_forward(netpack.pack_sconeocc(self), pc_global, clouds, x, view_harmonics,
                                    chunk=self.queries_per_pass)
         return out.view(pc.shape[0], x.shape[1], self.output_dim)

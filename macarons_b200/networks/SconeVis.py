@@ -58,7 +58,10 @@ class SconeVis(nn.Module):
             raise NameError("view_harmonics is required (use_view_state=True, view_state_mode='end')")
         if self.training and self.dropout is not None:
             raise NotImplementedError("the fused SconeVis forward has no dropout: call .eval() (dropout=%r)" % self.dropout)
-        ops.refuse_grad("SconeVis.forward", pts, view_harmonics, module=self)
+        if ops.wants_grad(pts, view_harmonics, module=self):
+            # training: CUDA forward, backward by recomputation under torch.autograd (networks/_backward.py)
+            from ._backward import SconeVisFunction
+            return SconeVisFunction.apply(self, pts, view_harmonics, *self.parameters())
         return ops.sconevis_forward(netpack.pack_sconevis(self), pts, view_harmonics)
 
     # ---- a3/a4: SH integration over candidate cameras: CUDA kernel --------------------------------

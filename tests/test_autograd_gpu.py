@@ -108,6 +108,98 @@ def test_module_methods_are_differentiable(cuda_device):
     assert vis.compute_coverage_gain(*d).grad_fn is None
 
 
+def _oracle_param_grads(fn, sd, loss_of):
+    """Gradients of loss_of(fn(sd_with_grad)) w.r.t. every entry of the state dict, through the oracle's restatement of the
+    reference arithmetic (torch CPU autograd)."""
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    loss = loss_of(fn(sd))
+    loss.backward()
+    return loss.item(), {k: v.grad for k, v in sd.items() if v.grad is not None}
+
+
+def test_sconevis_training_step_matches_oracle_autograd(cuda_device):
+    """One iteration of trainers/pretrain_scone_vis.py:162-225 in miniature: SconeVis.forward -> compute_coverage_gain ->
+    MSE loss -> backward -> Adam step, on the mirrored classes; loss and every parameter gradient against autograd through
+    the oracle (reference arithmetic, CPU)."""
+    import contextlib
+    import io
+    from oracle import scone_nets as o_nets
+    with contextlib.redirect_stdout(io.StringIO()):
+        vis = SconeVis()
+    sd = synth.seeded_state_dict(vis.state_dict(), 5)
+    vis.load_state_dict(sd)
+    vis = vis.to(cuda_device).train()
+    pts, vh = synth.sconevis_inputs(1, 384, 41)
+    cams = synth.fibonacci_cameras(24)[None].contiguous()
+    target = torch.rand(1, 24, generator=torch.Generator().manual_seed(1))
+    opt = torch.optim.Adam(vis.parameters(), lr=1e-4)
+    harm = vis(pts.to(cuda_device), view_harmonics=vh.to(cuda_device))
+    assert harm.grad_fn is not None
+    cov = vis.compute_coverage_gain(pts.to(cuda_device), harm, cams.to(cuda_device))
+    loss = torch.nn.functional.mse_loss(cov, target.to(cuda_device))
+    opt.zero_grad()
+    loss.backward()
+
+    def fwd(sd_g):
+        h = o_nets.scone_vis_forward(sd_g, pts, vh)
+        return sh_cov.coverage_gain(pts, h, cams)
+    want_loss, want = _oracle_param_grads(fwd, sd, lambda c: torch.nn.functional.mse_loss(c, target))
+    assert abs(loss.item() - want_loss) <= 1e-5 * max(1.0, abs(want_loss))
+    got = {k: p.grad.cpu() for k, p in vis.named_parameters()}
+    assert set(got) == set(want)
+    worst = 0.0
+    for k in want:
+        scale = want[k].abs().max().item()
+        err = (got[k] - want[k]).abs().max().item()
+        worst = max(worst, err / max(scale, 1e-12))
+        assert err <= 2e-3 * scale + 1e-9, (k, err, scale)
+    print("SconeVis training step: loss %.6f (oracle %.6f); worst relative gradient error %.2e over %d tensors"
+          % (loss.item(), want_loss, worst, len(want)))
+    before = {k: p.detach().clone() for k, p in vis.named_parameters()}
+    opt.step()
+    assert any(not torch.equal(before[k], p.detach()) for k, p in vis.named_parameters())
+    # the packed weights follow the optimizer step (version counters): the next forward uses the new parameters
+    with torch.no_grad():
+        new = vis(pts.to(cuda_device), view_harmonics=vh.to(cuda_device)).cpu()
+        ref = o_nets.scone_vis_forward({k: v.detach().cpu() for k, v in vis.state_dict().items()}, pts, vh)
+    assert (new - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    assert not torch.equal(new, harm.detach().cpu())
+
+
+def test_sconeocc_gradients_match_oracle_autograd(cuda_device):
+    """trainers/pretrain_scone_occ.py:158 in miniature: SconeOcc.forward -> MSE on the occupancy -> backward."""
+    import contextlib
+    import io
+    from macarons_b200.networks.SconeOcc import SconeOcc
+    from oracle import scone_nets as o_nets
+    with contextlib.redirect_stdout(io.StringIO()):
+        occ = SconeOcc()
+    sd = synth.seeded_state_dict(occ.state_dict(), 5)
+    occ.load_state_dict(sd)
+    occ = occ.to(cuda_device).train()
+    pc, x, vh = synth.sconeocc_inputs(1, 700, 160, 77)
+    target = torch.rand(1, 160, 1, generator=torch.Generator().manual_seed(2))
+    torch.manual_seed(9)
+    out = occ(pc.to(cuda_device), x.to(cuda_device), vh.to(cuda_device))
+    assert out.shape == (1, 160, 1) and out.grad_fn is not None
+    loss = torch.nn.functional.mse_loss(out, target.to(cuda_device))
+    loss.backward()
+    torch.manual_seed(9)
+    want_loss, want = _oracle_param_grads(lambda sd_g: o_nets.scone_occ_forward(sd_g, pc, x, vh), sd,
+                                          lambda o: torch.nn.functional.mse_loss(o, target))
+    assert abs(loss.item() - want_loss) <= 1e-4 * max(1.0, abs(want_loss))
+    got = {k: p.grad.cpu() for k, p in occ.named_parameters() if p.grad is not None}
+    assert set(got) == set(want)
+    worst = 0.0
+    for k in want:
+        scale = want[k].abs().max().item()
+        err = (got[k] - want[k]).abs().max().item()
+        worst = max(worst, err / max(scale, 1e-12))
+        assert err <= 2e-2 * scale + 1e-9, (k, err, scale)     # a neighbour swapped at a kNN rounding tie moves a few entries
+    print("SconeOcc backward: loss %.6f (oracle %.6f); worst relative gradient error %.2e over %d tensors"
+          % (loss.item(), want_loss, worst, len(want)))
+
+
 def test_gradients_that_are_not_implemented_are_refused(cuda_device):
     import contextlib
     import io
@@ -120,9 +212,12 @@ def test_gradients_that_are_not_implemented_are_refused(cuda_device):
     with pytest.raises(NotImplementedError):
         vis.compute_coverage_gain(d[0], d[1], d[2].clone().requires_grad_(True))
     vh = torch.zeros(1, 64, 64, device=cuda_device)
-    with pytest.raises(NotImplementedError):
-        vis(d[0], view_harmonics=vh)                       # parameters require grad and autograd is recording
+    assert vis(d[0], view_harmonics=vh).grad_fn is not None   # parameters require grad: the training path
     with torch.no_grad():
         assert vis(d[0], view_harmonics=vh).shape == (1, 64, 64)
     vis.requires_grad_(False)
     assert vis(d[0], view_harmonics=vh).grad_fn is None    # frozen module: inference path
+    with contextlib.redirect_stdout(io.StringIO()):
+        drop = SconeVis(dropout=0.1).to(cuda_device).train()
+    with pytest.raises(NotImplementedError):
+        drop(d[0], view_harmonics=vh)                      # dropout is not implemented in the fused forward
