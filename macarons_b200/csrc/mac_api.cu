@@ -111,18 +111,39 @@ extern "C" int mac_covgain_host(const float *pts, int pts_dim, const float *harm
     float *d_out = reinterpret_cast<float *>(base + n_pts + n_harm + n_cams);
     void *d_ws = base + n_pts + n_harm + n_cams + n_out;
     MAC_CUDA(cudaMemsetAsync(d_ws, 0, n_ws, c.stream));
+    // The (small) camera upload goes FIRST into the queue that carries the point slices.  On the compute stream it would be
+    // ordered behind the memset; by the time it became ready the host had usually queued all point slices on the copy
+    // engine, which serves one direction in submission order: the cameras -- and with them every kernel -- then waited
+    // for the whole 54.6 MB (measured with MAC_HOST_TRACE: first kernel done at 1.14 ms instead of 0.21 ms, a race that
+    // made a call take 1.15 or 1.54 ms).
+    const bool sliced_upload = (B == 1 && P >= (1 << 16));
     MAC_CUDA(cudaMemcpyAsync(d_cams, cams, sizeof(float) * B * static_cast<size_t>(C) * 3, cudaMemcpyHostToDevice,
-                             c.stream));
+                             sliced_upload ? c.copy_stream : c.stream));
     // One cloud with many points: the points arrive in slices on a copy stream while the kernel integrates the
     // previous slice (the partial sums stay in the fixed-point workspace between the slice launches).
     // MAC_HOST_SLICES / MAC_HOST_SKIP_KERNEL: tuning / diagnosis knobs of tools/bench_e2e.py (read once)
     static const int env_slices = [] { const char *e = getenv("MAC_HOST_SLICES"); return e ? atoi(e) : 0; }();
     static const bool skip_kernel = [] { const char *e = getenv("MAC_HOST_SKIP_KERNEL"); return e && atoi(e) != 0; }();
-    int n_slices = (B == 1 && P >= (1 << 16)) ? 8 : 1;
-    if (env_slices >= 1 && env_slices <= 64 && B == 1) n_slices = env_slices;
+    int n_slices = sliced_upload ? 12 : 1;   // 8, 12 and 16 measure within 3 % of each other (1.19-1.26 ms at a 1.00 ms link floor)
+    if (env_slices >= 1 && env_slices <= 64 && sliced_upload) n_slices = env_slices;
+    if (sliced_upload && n_slices == 1) {   // single piece: everything on the compute stream, order the cameras there too
+        MAC_CUDA(cudaEventRecord(c.landed[0], c.copy_stream));
+        MAC_CUDA(cudaStreamWaitEvent(c.stream, c.landed[0], 0));
+    }
     if (n_slices > 1) {
         const int per = ((P + n_slices - 1) / n_slices + 31) / 32 * 32;
         static const int copy_streams = [] { const char *e = getenv("MAC_HOST_COPY_STREAMS"); return e ? atoi(e) : 1; }();
+        // MAC_HOST_TRACE=1: device timeline of every call on stderr (copy k landed / kernel k done, ms since the first copy)
+        static const bool trace = [] { const char *e = getenv("MAC_HOST_TRACE"); return e && atoi(e) != 0; }();
+        static thread_local cudaEvent_t tr_start = nullptr, tr_landed[64], tr_kdone[64];
+        if (trace && !tr_start) {
+            MAC_CUDA(cudaEventCreate(&tr_start));
+            for (int i = 0; i < 64; ++i) {
+                MAC_CUDA(cudaEventCreate(&tr_landed[i]));
+                MAC_CUDA(cudaEventCreate(&tr_kdone[i]));
+            }
+        }
+        if (trace) MAC_CUDA(cudaEventRecord(tr_start, c.copy_stream));
         int k = 0;
         for (int p0 = 0; p0 < P; p0 += per, ++k) {
             const int np = P - p0 < per ? P - p0 : per;
@@ -134,12 +155,26 @@ extern "C" int mac_covgain_host(const float *pts, int pts_dim, const float *harm
                                      sizeof(float) * np * static_cast<size_t>(MAC_N_HARMONICS), cudaMemcpyHostToDevice,
                                      cs));
             MAC_CUDA(cudaEventRecord(c.landed[k], cs));
+            if (trace) MAC_CUDA(cudaEventRecord(tr_landed[k], cs));
             MAC_CUDA(cudaStreamWaitEvent(c.stream, c.landed[k], 0));
             if (skip_kernel) continue;
             const int rc = covgain_accumulate(d_pts + static_cast<size_t>(p0) * pts_dim, pts_dim,
                                               d_harm + static_cast<size_t>(p0) * MAC_N_HARMONICS, d_cams, d_out, np, C, cam_begin,
                                               cam_end, act, d_ws, n_ws, P, p0 + np >= P ? 1 : 0, c.stream);
             if (rc != MAC_OK) return rc;
+            if (trace) MAC_CUDA(cudaEventRecord(tr_kdone[k], c.stream));
+        }
+        if (trace) {
+            MAC_CUDA(cudaStreamSynchronize(c.stream));
+            char line[2048];
+            int n = 0;
+            for (int i = 0; i < k; ++i) {
+                float a = 0.f, b = 0.f;
+                cudaEventElapsedTime(&a, tr_start, tr_landed[i]);
+                cudaEventElapsedTime(&b, tr_start, tr_kdone[i]);
+                n += snprintf(line + n, sizeof(line) - n, " %.3f/%.3f", a, b);
+            }
+            fprintf(stderr, "[mac_covgain_host] landed/kernel-done ms:%s\n", line);
         }
     } else {
         MAC_CUDA(cudaMemcpyAsync(d_pts, pts, sizeof(float) * B * static_cast<size_t>(P) * pts_dim, cudaMemcpyHostToDevice,

@@ -115,8 +115,8 @@ class PeerScoreBoard:
         n_scores = self.B * self.C
         self._flag_off = 2 * n_scores            # in 4-byte words: [board 0 | board 1 | flags(world) | pad | partials 0 | 1]
         # partial-sum regions of the point-sharded step: per parity world * B * C int64 + world * B * C u32
-        self._part_off = self._flag_off + 64
-        self._part_words = 3 * self.world * n_scores
+        self._part_off = (self._flag_off + 64 + 3) // 4 * 4                  # 16-byte aligned regions (int64 sums inside)
+        self._part_words = (3 * self.world * n_scores + 3) // 4 * 4
         words = self._part_off + 2 * self._part_words
         if self.world > 1:
             grp = group if group is not None else dist.group.WORLD

@@ -148,11 +148,12 @@ def test_sconevis_training_step_matches_oracle_autograd(cuda_device):
     got = {k: p.grad.cpu() for k, p in vis.named_parameters()}
     assert set(got) == set(want)
     worst = 0.0
+    overall = max(v.abs().max().item() for v in want.values())
     for k in want:
         scale = want[k].abs().max().item()
         err = (got[k] - want[k]).abs().max().item()
-        worst = max(worst, err / max(scale, 1e-12))
-        assert err <= 2e-3 * scale + 1e-9, (k, err, scale)
+        worst = max(worst, err / max(scale, 1e-6 * overall))
+        assert err <= 2e-3 * scale + 1e-6 * overall, (k, err, scale)
     print("SconeVis training step: loss %.6f (oracle %.6f); worst relative gradient error %.2e over %d tensors"
           % (loss.item(), want_loss, worst, len(want)))
     before = {k: p.detach().clone() for k, p in vis.named_parameters()}
@@ -191,11 +192,14 @@ def test_sconeocc_gradients_match_oracle_autograd(cuda_device):
     got = {k: p.grad.cpu() for k, p in occ.named_parameters() if p.grad is not None}
     assert set(got) == set(want)
     worst = 0.0
+    overall = max(v.abs().max().item() for v in want.values())
     for k in want:
         scale = want[k].abs().max().item()
         err = (got[k] - want[k]).abs().max().item()
-        worst = max(worst, err / max(scale, 1e-12))
-        assert err <= 2e-2 * scale + 1e-9, (k, err, scale)     # a neighbour swapped at a kNN rounding tie moves a few entries
+        worst = max(worst, err / max(scale, 1e-6 * overall))
+        # (key biases have a mathematically zero gradient -- softmax is shift invariant -- hence the absolute floor;
+        # a neighbour swapped at a kNN rounding tie moves a few entries)
+        assert err <= 2e-2 * scale + 1e-6 * overall, (k, err, scale)
     print("SconeOcc backward: loss %.6f (oracle %.6f); worst relative gradient error %.2e over %d tensors"
           % (loss.item(), want_loss, worst, len(want)))
 

@@ -32,6 +32,31 @@ if len(sys.argv) > 1 and sys.argv[1] == "quick":
     ts.sort()
     print("mac_covgain_host median %.3f ms min %.3f ms" % (ts[len(ts) // 2], ts[0]))
     sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "alt":
+    # alternating two pinned input sets: the C path vs plain torch copies of the same bytes, interleaved
+    pts2, harm2, _ = synth.covgain_inputs(1, 200704, 1, seed=2)
+    pp2, hp2 = pts2.pin_memory(), harm2.pin_memory()
+    sets_t = [(pp, hp), (pp2, hp2)]
+    sets_n = [(pp.numpy(), hp.numpy()), (pp2.numpy(), hp2.numpy())]
+    cn = cams.numpy()
+    for name, n_sets in (("one set", 1), ("two sets alternating", 2)):
+        for _ in range(3):
+            ops.coverage_gain_host(*sets_n[0], cn, device=0)
+        tc, tt = [], []
+        for i in range(24):
+            t0 = time.perf_counter()
+            ops.coverage_gain_host(*sets_n[i % n_sets], cn, device=0)
+            tc.append(1e3 * (time.perf_counter() - t0))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dp.copy_(sets_t[i % n_sets][0], non_blocking=True)
+            dh.copy_(sets_t[i % n_sets][1], non_blocking=True)
+            torch.cuda.synchronize()
+            tt.append(1e3 * (time.perf_counter() - t0))
+        tc.sort(); tt.sort()
+        print("%-22s mac_covgain_host median %.3f ms (min %.3f) | torch pinned copy median %.3f ms (min %.3f)"
+              % (name, tc[len(tc) // 2], tc[0], tt[len(tt) // 2], tt[0]))
+    sys.exit(0)
 print("H2D pinned 54.6 MB        %.3f ms" % wall(lambda: (dp.copy_(pp, non_blocking=True), dh.copy_(hp, non_blocking=True))))
 print("H2D pageable              %.3f ms" % wall(lambda: (dp.copy_(pts), dh.copy_(harm)), 5))
 dc = cams.to(dev)
