@@ -518,6 +518,8 @@ def run_ours(args, cfg):
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = ops.launch_count()
+    if board is not None:
+        board.reset_wait_stats()
     barrier()
     wall0 = time.perf_counter()
     t_begin.record()
@@ -531,10 +533,20 @@ def run_ours(args, cfg):
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     elapsed_ms = t_begin.elapsed_time(t_end)
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    # time the finishing CTA of the fused step spent waiting for the slowest peer (measured inside the kernel with
+    # %globaltimer): kernel_ms contains it, kernel_ms - peer_wait_ms is this rank's own scoring work
+    peer_wait_ms = (board.wait_stats()[0] * 1e-6) if board is not None else 0.0
     if world > 1:
         t = torch.tensor([elapsed_ms, kernel_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, kernel_ms = t.tolist()
+        w = torch.tensor([peer_wait_ms], device=dev)
+        w_min, w_max = w.clone(), w.clone()
+        dist.all_reduce(w_min, op=dist.ReduceOp.MIN)
+        dist.all_reduce(w_max, op=dist.ReduceOp.MAX)
+        peer_wait = {"min_over_ranks_ms": w_min.item(), "max_over_ranks_ms": w_max.item()}
+    else:
+        peer_wait = {"min_over_ranks_ms": peer_wait_ms, "max_over_ranks_ms": peer_wait_ms}
 
     # ---- end to end through the public API: pinned host inputs -> device, score, gather, argmax -> host ----
     e2e_steps = max(3, min(args.steps, 30))
@@ -711,6 +723,9 @@ def run_ours(args, cfg):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                          "kernel": "covgain_kernel<sigmoid,reduce>", "kernel_ms": kernel_ms,
+                         "peer_wait_inside_kernel": dict(peer_wait, note="mean time per step the finishing CTA waited for the "
+                                                         "slowest rank's scores (device %globaltimer); the rank that finishes "
+                                                         "last waits least: kernel_ms - min = the slowest rank's own work"),
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "kernel is bound by the fp32 FMA pipe, not HBM, at >= 8 cameras per point pass "
                                  "(DESIGN.md section 4); fp32_pipe is the binding roofline",

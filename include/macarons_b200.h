@@ -115,8 +115,9 @@ void mac_host_release(void);
  * mac_gather_wait_argmax enqueues a one-CTA kernel that waits (acquire loads, bounded by ~2 s) until all
  * `world` flags of the local board have reached `epoch`, then writes best[b] = index of the first maximum
  * of scores[b, :] (NaN counts as maximal, like torch.argmax); on timeout it sets status[0] = 1 and leaves best
- * untouched.  status is sticky (never reset by the device): the caller zeroes it before the first step and after
- * having handled a timeout.
+ * untouched.  `status` points to FOUR ints: status[0] is sticky (never reset by the device): the caller zeroes it before the
+ * first step and after having handled a timeout; status[1] = nanoseconds this rank waited for its slowest peer in the last
+ * step, status[2] / status[3] = accumulated nanoseconds / number of steps since the caller last zeroed them.
  * ------------------------------------------------------------------------------------------- */
 #define MAC_MAX_PEERS 16
 typedef struct mac_peer_board {

@@ -21,7 +21,11 @@ template <int NT>
 __device__ bool wait_for_ranks(const unsigned int *flags, int world, unsigned int epoch, int *status)
 {
     __shared__ int timed_out;
-    if (threadIdx.x == 0) timed_out = 0;
+    unsigned long long t_begin = 0;
+    if (threadIdx.x == 0) {
+        timed_out = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+    }
     __syncthreads();
     if (threadIdx.x < world) {
         unsigned long long t0, t;
@@ -37,9 +41,19 @@ __device__ bool wait_for_ranks(const unsigned int *flags, int world, unsigned in
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        // instrumentation: how long this rank waited for the slowest peer (status[1] = last wait in ns, status[2] += ns,
+        // status[3] += 1); the host zeroes status[1..3] when it starts a measurement
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        const unsigned long long dt = t1 - t_begin;
+        status[1] = static_cast<int>(dt > 0x7fffffffull ? 0x7fffffffull : dt);
+        status[2] += status[1];
+        status[3] += 1;
+    }
     if (timed_out) {
-        // *status is sticky: a timeout of an earlier step stays visible until the host clears it (PeerScoreBoard.check)
-        if (threadIdx.x == 0) *status = 1;
+        // status[0] is sticky: a timeout of an earlier step stays visible until the host clears it (PeerScoreBoard.check)
+        if (threadIdx.x == 0) status[0] = 1;
         return false;
     }
     return true;

@@ -132,7 +132,7 @@ class PeerScoreBoard:
         self._bases = bases
         self._flags = self._buf[self._flag_off:self._flag_off + 64].view(torch.int32)
         self.best = torch.zeros(self.B, dtype=torch.int64, device=self.device)
-        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.status = torch.zeros(4, dtype=torch.int32, device=self.device)   # [timeout flag, last wait ns, sum ns, steps]
         # per-parity C structs and board views, built once: step() only updates the epoch
         from . import _lib
         self._lib = _lib.load()
@@ -277,9 +277,18 @@ class PeerScoreBoard:
                         ws.data_ptr(), ws.numel(), board, self.best.data_ptr(), self.status.data_ptr(), main.cuda_stream))
             return self._views[parity], self.best
 
+    def reset_wait_stats(self):
+        self.status[1:].zero_()
+
+    def wait_stats(self):
+        """-> (mean nanoseconds per step this rank spent waiting for its slowest peer inside the fused step, steps) since
+        reset_wait_stats().  Synchronises."""
+        _, _, total, n = self.status.tolist()
+        return (total / n if n else 0.0), n
+
     def check(self):
         """Synchronises; raises if a wait timed out (a peer never arrived) in any step since the last check: the
         device-side status is sticky and is cleared here."""
-        if int(self.status.item()) != 0:
-            self.status.zero_()
+        if int(self.status[0].item()) != 0:
+            self.status[0] = 0
             raise RuntimeError("PeerScoreBoard: timed out waiting for a peer's scores")

@@ -293,10 +293,10 @@ def test_fused_push_and_argmax_single_rank(cuda_device):
     s = torch.tensor([[0.5, 0.7, 0.7, 0.1], [0.2, float("nan"), 0.9, float("nan")]], device=cuda_device)
     flags = torch.full((1,), 5, dtype=torch.int32, device=cuda_device)
     best = torch.zeros(2, dtype=torch.int64, device=cuda_device)
-    status = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    status = torch.zeros(4, dtype=torch.int32, device=cuda_device)
     ops.gather_wait_argmax(s, flags, 1, 5, best, status)
-    assert best.tolist() == [1, 1] and status.item() == 0
+    assert best.tolist() == [1, 1] and status[0].item() == 0 and status[3].item() == 1
     ops.gather_wait_argmax(s, flags, 1, 6, best, status)   # epoch never arrives -> bounded wait, status 1
-    assert status.item() == 1
+    assert status[0].item() == 1 and status[1].item() > 1_000_000_000      # waited ~2 s
     ops.gather_wait_argmax(s, flags, 1, 5, best, status)   # the status is sticky: a later good step does not hide the timeout
-    assert best.tolist() == [1, 1] and status.item() == 1
+    assert best.tolist() == [1, 1] and status[0].item() == 1 and status[3].item() == 3
