@@ -570,7 +570,7 @@ def run_ours(args, cfg):
         cam_d = cams_pin.to(dev, non_blocking=True)
         if board is not None and B == 1:
             # one cloud: the rows arrive in slices on a copy stream, slice k is integrated while slice k+1 is in flight
-            s, b = board.step_points_from_host(p_h, h_h, cam_d, use_sigmoid=vis.use_sigmoid, slices=4, bufs=e2e_bufs)
+            s, b = board.step_points_from_host(p_h, h_h, cam_d, use_sigmoid=vis.use_sigmoid, slices=e2e_slices, bufs=e2e_bufs)
         elif board is not None:
             e2e_bufs[0].copy_(p_h[:, p0:p1], non_blocking=True)
             e2e_bufs[1].copy_(h_h[:, p0:p1], non_blocking=True)
@@ -579,10 +579,13 @@ def run_ours(args, cfg):
             pts = parallel.upload_rows_sharded(p_h.view(B * P, -1), dev, buf=e2e_bufs[0]).view(B, P, -1)
             harm = parallel.upload_rows_sharded(h_h.view(B * P, 64), dev, buf=e2e_bufs[1]).view(B, P, 64)
             s, b = parallel.sharded_coverage_gain(vis.compute_coverage_gain, pts, harm, cam_d)
-        return s.cpu(), b.cpu()
+        s_cpu = s.cpu()                      # one device -> host read; the argmax of the (replicated) scores on the host
+        return s_cpu, parallel.nbv_argmax(s_cpu)
 
     e2e_bufs = [None, None]
     p0, p1 = parallel.point_partition(P, world, rank)
+    # upload slices of >= ~8 MB: one at N = 8 (6.8 MB per rank), two at N = 4, three or four at N = 2
+    e2e_slices = max(1, min(8, round((p1 - p0) * 272 / 8e6)))
     if world > 1 and board is not None:
         e2e_bufs = [torch.empty((B, p1 - p0, host_sets[0][0].shape[-1]), device=dev), torch.empty((B, p1 - p0, 64), device=dev)]
     elif world > 1:
