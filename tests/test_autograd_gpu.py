@@ -225,3 +225,15 @@ def test_gradients_that_are_not_implemented_are_refused(cuda_device):
         drop = SconeVis(dropout=0.1).to(cuda_device).train()
     with pytest.raises(NotImplementedError):
         drop(d[0], view_harmonics=vh)                      # dropout is not implemented in the fused forward
+
+
+def test_backward_edge_shapes(cuda_device):
+    """One point, one camera, point counts that are not a multiple of the block, more cameras than one staging pass."""
+    for B, P, C in ((1, 1, 1), (3, 129, 2), (1, 40, 1100)):
+        pts, harm, cams = synth.covgain_inputs(B, P, C, seed=P + C)
+        g = torch.randn(B, C, generator=torch.Generator().manual_seed(1))
+        got = ops.coverage_gain_backward(pts.to(cuda_device), harm.to(cuda_device), cams.to(cuda_device), g.to(cuda_device)).cpu()
+        truth = _f64_grad(pts, harm, cams, g, True, False)
+        assert np.abs(got.numpy() - truth).max() <= GRAD_RTOL * np.abs(truth).max()
+    with pytest.raises(ValueError):
+        ops.coverage_gain_backward(pts.to(cuda_device), harm.to(cuda_device), cams.to(cuda_device), g.to(cuda_device)[:, :5])

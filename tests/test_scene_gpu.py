@@ -97,3 +97,39 @@ def test_scene_occupancy_field_matches_reference_golden(name, cuda_device):
     assert np.quantile(perr, 0.98) <= NET_RTOL * scale and perr.max() <= 0.05 * scale
     assert torch.all(vh[n - n_oof:] == 0) and torch.all(probs[n - n_oof:] == 0.5)
     assert launches < 400        # one ragged forward, not one per cell (the per-cell loop takes > 100 launches per cell)
+
+
+def test_forward_cells_edge_cases(cuda_device):
+    """A cell without queries, a single cell, and the empty list."""
+    occ, _ = _occ(cuda_device)
+    gen = torch.Generator().manual_seed(3)
+    mk = lambda n, d: (torch.rand(n, d, generator=gen) - 0.5).to(cuda_device)
+    assert occ.forward_cells([], [], []) == []
+    with torch.no_grad():
+        torch.manual_seed(5)
+        outs = occ.forward_cells([mk(200, 3), mk(90, 3), mk(300, 3)], [mk(50, 3), mk(0, 3), mk(7, 3)],
+                                 [mk(50, 64), mk(0, 64), mk(7, 64)])
+    assert [tuple(o.shape) for o in outs] == [(50, 1), (0, 1), (7, 1)]
+    assert all(torch.isfinite(o).all() for o in outs)
+    with torch.no_grad():
+        torch.manual_seed(6)
+        one = occ.forward_cells([mk(500, 3)], [mk(33, 3)], [mk(33, 64)])
+    assert one[0].shape == (33, 1)
+
+
+def test_scene_field_without_observations(cuda_device):
+    """Before any frame: every proxy point is out of field -> the field is the stored default probability with zero
+    harmonics, and no network call is made (reference :1520-1538)."""
+    occ, _ = _occ(cuda_device)
+    x_min, x_max = torch.tensor([-1., -1., -1.]).to(cuda_device), torch.tensor([1., 1., 1.]).to(cuda_device)
+    common = dict(x_min=x_min, x_max=x_max, grid_l=2, grid_w=2, grid_h=2, n_proxy_points=500, device=cuda_device)
+    surface_scene = scene.Scene(cell_capacity=100, cell_resolution=None, feature_dim=1, **common)
+    proxy_scene = scene.Scene(cell_capacity=1000, cell_resolution=0.001, feature_dim=1, **common)
+    proxy_scene.initialize_proxy_points()
+    n0 = ops.launch_count()
+    X_world, vh, probs = macarons_utils.compute_scene_occupancy_probability_field(
+        scene_case.params(), Macarons(None, occ, None), None, surface_scene, proxy_scene, cuda_device,
+        prediction_camera=scene_case.prediction_camera(cuda_device))
+    assert ops.launch_count() == n0
+    assert X_world.shape == (500, 3) and torch.equal(X_world, proxy_scene.proxy_points)
+    assert torch.all(vh == 0) and torch.all(probs == 0.5)
