@@ -169,20 +169,23 @@ __global__ void __launch_bounds__(256) view_harmonics_kernel(const float *__rest
 // T[j][k] = ((1 * base[k][j]) * sin(polar_j)) * polar_step * azim_step  -- bit for bit the term the two-kernel path adds for a
 // state of 1.0, in the same ascending-bin order, so both paths give identical results.
 // Traffic: 4*pts_dim B read + 256 B written per point (vs + 2 * 4 * n_bins B for the materialised histogram).
-constexpr int kFusedPts = 64;   // points per block iteration
-// The binning is a long dependent chain (sqrt, 4 IEEE divisions, asinf, cosf, acosf, two exact remainders: ~600 issued
-// instructions per ray incl. divergent slow paths), i.e. latency bound: 8 CTAs x 8 warps per SM (32 registers) hide it.
+// Warp-autonomous mapping (no block barriers, no shared atomics, balance at the granularity of 32 points):
+//   phase 1  lane = point: the lane evaluates the reference's binning rule for its own point against the V views in turn
+//            (same view for all lanes: the long dependent chain never diverges) and ORs the bins into a 128-bit mask held in
+//            4 registers;
+//   phase 2  point by point: the mask of point q is broadcast with 4 shuffles, lane l adds the table entries
+//            T[j][2l], T[j][2l+1] of every set bin j (one conflict-free LDS.64 per bin; the loop over the bins is uniform)
+//            and the warp writes the 256-byte output row.
+// The binning is ~330 issued instructions per ray; 8 CTAs x 8 warps per SM (32 registers) keep the issue slots busy.
 __global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateParams p, const float *__restrict__ base,
                                                                 const float *__restrict__ h_polar, float *__restrict__ out,
                                                                 float polar_step, float azim_step)
 {
     extern __shared__ float sm[];
     const int n_bins = p.n_elev * p.n_azim;
-    float *T = sm;                                                        // [n_bins][64]
-    float *sinp = T + n_bins * 64;                                        // [n_bins]
-    float *sviews = sinp + kMaxBins;                                      // [V][3]
-    float *spts = sviews + 3 * p.V;                                       // [kFusedPts][3]
-    unsigned *mask = reinterpret_cast<unsigned *>(spts + 3 * kFusedPts);  // [kFusedPts][4]
+    float *T = sm;                         // [n_bins][64]
+    float *sinp = T + n_bins * 64;         // [n_bins]
+    float *sviews = sinp + kMaxBins;       // [V][3]
     for (int j = threadIdx.x; j < n_bins; j += blockDim.x) sinp[j] = sinf(h_polar[j]);
     for (int i = threadIdx.x; i < p.V * 3; i += blockDim.x) sviews[i] = p.views[i];
     __syncthreads();
@@ -190,37 +193,45 @@ __global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateP
         const int k = i / n_bins, j = i - k * n_bins;
         T[j * 64 + k] = __fmul_rn(__fmul_rn(__fmul_rn(base[i], sinp[j]), polar_step), azim_step);
     }
-    // phase 2 mapping: 16 threads per point, 4 consecutive coefficients per thread (one LDS.128 per set bin and thread)
-    const int k4 = (threadIdx.x & 15) * 4, g = threadIdx.x >> 4;
-    for (long long p0 = blockIdx.x * static_cast<long long>(kFusedPts); p0 < p.n_pts;
-         p0 += gridDim.x * static_cast<long long>(kFusedPts)) {
-        __syncthreads();   // previous iteration's masks consumed (and, first time, T written)
-        const int n = static_cast<int>(p.n_pts - p0 < kFusedPts ? p.n_pts - p0 : kFusedPts);
-        for (int i = threadIdx.x; i < n * 3; i += blockDim.x) spts[i] = p.pts[(p0 + i / 3) * p.pts_dim + i % 3];
-        for (int i = threadIdx.x; i < kFusedPts * 4; i += blockDim.x) mask[i] = 0u;
-        __syncthreads();
-        // view-major items: consecutive threads take consecutive points of the same view (conflict-free spts reads)
-        for (int i = threadIdx.x; i < n * p.V; i += blockDim.x) {
-            const int v = i / n, q = i - v * n;
-            const int b = view_bin(p, sviews[3 * v] - spts[3 * q], sviews[3 * v + 1] - spts[3 * q + 1],
-                                   sviews[3 * v + 2] - spts[3 * q + 2]);
-            atomicOr(&mask[q * 4 + (b >> 5)], 1u << (b & 31));
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long n_tiles = (p.n_pts + 31) / 32;
+    const long long warp0 = blockIdx.x * 8ll + (threadIdx.x >> 5), n_warps = gridDim.x * 8ll;
+    const float2 *T2 = reinterpret_cast<const float2 *>(T) + lane;
+    for (long long tile = warp0; tile < n_tiles; tile += n_warps) {
+        const long long pt = tile * 32 + lane;
+        unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+        if (pt < p.n_pts) {
+            const float *x = p.pts + pt * p.pts_dim;
+            const float px = x[0], py = x[1], pz = x[2];
+            for (int v = 0; v < p.V; ++v) {
+                const int b = view_bin(p, sviews[3 * v] - px, sviews[3 * v + 1] - py, sviews[3 * v + 2] - pz);
+                const unsigned bit = 1u << (b & 31);
+                const int w = b >> 5;
+                m0 |= w == 0 ? bit : 0u;
+                m1 |= w == 1 ? bit : 0u;
+                m2 |= w == 2 ? bit : 0u;
+                m3 |= w == 3 ? bit : 0u;
+            }
         }
-        __syncthreads();
-        for (int q = g; q < n; q += 16) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n = static_cast<int>(p.n_pts - tile * 32 < 32 ? p.n_pts - tile * 32 : 32);
+        float2 *o2 = reinterpret_cast<float2 *>(out + tile * 32 * 64) + lane;
+        for (int q = 0; q < n; ++q) {
+            unsigned mq[4] = {__shfl_sync(0xffffffffu, m0, q), __shfl_sync(0xffffffffu, m1, q),
+                              __shfl_sync(0xffffffffu, m2, q), __shfl_sync(0xffffffffu, m3, q)};
+            float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
-                unsigned m = mask[q * 4 + w];
-                while (m) {   // ascending bins
+                unsigned m = mq[w];
+                while (m) {   // ascending bins, uniform across the warp
                     const int j = w * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    const float4 t = *reinterpret_cast<const float4 *>(T + j * 64 + k4);
-                    acc.x = __fadd_rn(acc.x, t.x), acc.y = __fadd_rn(acc.y, t.y);
-                    acc.z = __fadd_rn(acc.z, t.z), acc.w = __fadd_rn(acc.w, t.w);
+                    const float2 t = T2[j * 32];
+                    acc.x = __fadd_rn(acc.x, t.x);
+                    acc.y = __fadd_rn(acc.y, t.y);
                 }
             }
-            *reinterpret_cast<float4 *>(out + (p0 + q) * 64 + k4) = acc;
+            o2[q * 32] = acc;
         }
     }
 }
@@ -320,11 +331,10 @@ extern "C" int mac_viewstate_harm_f32(const float *pts, int pts_dim, const float
     p.azim_wrap = -((n_azim + 1) / 2);
     p.elev_shift = n_elev / 2;
     const int n_bins = n_elev * n_azim;
-    const size_t smem = (64 * static_cast<size_t>(n_bins) + kMaxBins + 3 * static_cast<size_t>(V) + 3 * kFusedPts) * sizeof(float) +
-                        kFusedPts * 4 * sizeof(unsigned);
+    const size_t smem = (64 * static_cast<size_t>(n_bins) + kMaxBins + 3 * static_cast<size_t>(V)) * sizeof(float);
     static DeviceOnce once;
     if (int rc = ensure_dynamic_smem(once, viewstate_harm_kernel, 96 * 1024)) return rc;
-    const long long want = (p.n_pts + kFusedPts - 1) / kFusedPts;
+    const long long want = ((p.n_pts + 31) / 32 + 7) / 8;   // one 32-point tile per warp, 8 warps per CTA
     int device = 0;
     MAC_CUDA(cudaGetDevice(&device));
     const long long resident = static_cast<long long>(sm_count(device)) * 8;   // 8 CTAs / SM (~27 KB of shared memory each)
