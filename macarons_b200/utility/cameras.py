@@ -32,7 +32,8 @@ class Transform:
     def transform_points(self, points, eps=None):
         flat = points.dim() == 2
         pts = points[None] if flat else points
-        hom = torch.cat((pts, torch.ones_like(pts[..., :1])), dim=-1) @ self._m
+        m = self._m[:, None]                                    # (N, 1, 4, 4); broadcast multiply-adds, no GEMM library call
+        hom = pts[..., 0:1] * m[..., 0, :] + pts[..., 1:2] * m[..., 1, :] + pts[..., 2:3] * m[..., 2, :] + m[..., 3, :]
         w = hom[..., 3:]
         if eps is not None:
             w = torch.where(w.abs() < eps, torch.where(w < 0, -torch.ones_like(w), torch.ones_like(w)) * eps, w)

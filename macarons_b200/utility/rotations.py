@@ -3,6 +3,12 @@ takes from pytorch3d.transforms in ManyDepth.forward (networks/ManyDepth.py:740-
 import torch
 
 
+def _mm3(A, B):
+    """(..., n, 3) x (..., 3, 3) products written as a broadcast multiply + sum: a handful of 3x3 matrices per step do not
+    warrant a GEMM library call."""
+    return (A[..., :, :, None] * B[..., None, :, :]).sum(dim=-2)
+
+
 def axis_angle_to_matrix(axis_angle):
     """(..., 3) rotation vectors -> (..., 3, 3) rotation matrices (Rodrigues; column-vector convention as pytorch3d)."""
     angle = torch.norm(axis_angle, dim=-1, keepdim=True)
@@ -14,7 +20,7 @@ def axis_angle_to_matrix(axis_angle):
     zero = torch.zeros_like(x)
     K = torch.stack((zero, -z, y, z, zero, -x, -y, x, zero), dim=-1).reshape(axis_angle.shape[:-1] + (3, 3))
     eye = torch.eye(3, dtype=axis_angle.dtype, device=axis_angle.device)
-    return eye + a[..., None] * K + b[..., None] * (K @ K)
+    return eye + a[..., None] * K + b[..., None] * _mm3(K, K)
 
 
 def relative_cameras(R, T, pose, pose_factor):
@@ -24,6 +30,6 @@ def relative_cameras(R, T, pose, pose_factor):
     B, n_alpha = pose.shape[0], pose.shape[1]
     rel_R = axis_angle_to_matrix(pose_factor * pose[..., 3:])
     rel_T = pose_factor * pose[..., :3]
-    R_alpha = R.view(B, 1, 3, 3) @ rel_R
-    T_alpha = rel_T + (T.view(B, 1, 1, 3) @ rel_R).squeeze(-2)
+    R_alpha = _mm3(R.view(B, 1, 3, 3), rel_R)
+    T_alpha = rel_T + _mm3(T.view(B, 1, 1, 3), rel_R).squeeze(-2)
     return R_alpha, T_alpha
