@@ -173,9 +173,10 @@ __global__ void __launch_bounds__(256) view_harmonics_kernel(const float *__rest
 //   phase 1  lane = point: the lane evaluates the reference's binning rule for its own point against the V views in turn
 //            (same view for all lanes: the long dependent chain never diverges) and ORs the bins into a 128-bit mask held in
 //            4 registers;
-//   phase 2  point by point: the mask of point q is broadcast with 4 shuffles, lane l adds the table entries
-//            T[j][2l], T[j][2l+1] of every set bin j (one conflict-free LDS.64 per bin; the loop over the bins is uniform)
-//            and the warp writes the 256-byte output row.
+//   phase 2  two points at a time, one per half-warp: the mask of the point is fetched with 4 shuffles, lane l adds the table
+//            entries T[j][4l..4l+3] of every set bin j (one LDS.128 per bin) and the half-warp writes the 256-byte output row.
+//            (ncu: with one point per warp and 2 coefficients per lane the bit decode -- 10 instructions per set bin,
+//            replicated by all 32 lanes -- was 62 % of the kernel's 52 M warp instructions.)
 // The binning is ~330 issued instructions per ray; 8 CTAs x 8 warps per SM (32 registers) keep the issue slots busy.
 __global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateParams p, const float *__restrict__ base,
                                                                 const float *__restrict__ h_polar, float *__restrict__ out,
@@ -189,15 +190,15 @@ __global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateP
     for (int j = threadIdx.x; j < n_bins; j += blockDim.x) sinp[j] = sinf(h_polar[j]);
     for (int i = threadIdx.x; i < p.V * 3; i += blockDim.x) sviews[i] = p.views[i];
     __syncthreads();
-    for (int i = threadIdx.x; i < n_bins * 64; i += blockDim.x) {   // coalesced read of base (64, n_bins), transposed store
-        const int k = i / n_bins, j = i - k * n_bins;
-        T[j * 64 + k] = __fmul_rn(__fmul_rn(__fmul_rn(base[i], sinp[j]), polar_step), azim_step);
-    }
-    __syncthreads();
     const int lane = threadIdx.x & 31;
+    for (int k = threadIdx.x >> 5; k < 64; k += 8)              // row k of base (64, n_bins): coalesced read, transposed store
+        for (int j = lane; j < n_bins; j += 32)
+            T[j * 64 + k] = __fmul_rn(__fmul_rn(__fmul_rn(base[k * n_bins + j], sinp[j]), polar_step), azim_step);
+    __syncthreads();
     const long long n_tiles = (p.n_pts + 31) / 32;
     const long long warp0 = blockIdx.x * 8ll + (threadIdx.x >> 5), n_warps = gridDim.x * 8ll;
-    const float2 *T2 = reinterpret_cast<const float2 *>(T) + lane;
+    const int half = lane >> 4;                                  // phase 2: each half-warp sums one point, 4 coefficients per lane
+    const float4 *T4 = reinterpret_cast<const float4 *>(T) + (lane & 15);
     for (long long tile = warp0; tile < n_tiles; tile += n_warps) {
         const long long pt = tile * 32 + lane;
         unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
@@ -215,23 +216,24 @@ __global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateP
             }
         }
         const int n = static_cast<int>(p.n_pts - tile * 32 < 32 ? p.n_pts - tile * 32 : 32);
-        float2 *o2 = reinterpret_cast<float2 *>(out + tile * 32 * 64) + lane;
-        for (int q = 0; q < n; ++q) {
-            unsigned mq[4] = {__shfl_sync(0xffffffffu, m0, q), __shfl_sync(0xffffffffu, m1, q),
-                              __shfl_sync(0xffffffffu, m2, q), __shfl_sync(0xffffffffu, m3, q)};
-            float2 acc = make_float2(0.f, 0.f);
+        float4 *o4 = reinterpret_cast<float4 *>(out + tile * 32 * 64) + (lane & 15);
+        for (int q0 = 0; q0 < n; q0 += 2) {
+            const int q = q0 + half;                             // absent points carry an empty mask
+            unsigned mq[4] = {__shfl_sync(0xffffffffu, m0, q & 31), __shfl_sync(0xffffffffu, m1, q & 31),
+                              __shfl_sync(0xffffffffu, m2, q & 31), __shfl_sync(0xffffffffu, m3, q & 31)};
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 unsigned m = mq[w];
-                while (m) {   // ascending bins, uniform across the warp
+                while (m) {   // ascending bins; the two half-warps run their own bit lists under predication
                     const int j = w * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    const float2 t = T2[j * 32];
-                    acc.x = __fadd_rn(acc.x, t.x);
-                    acc.y = __fadd_rn(acc.y, t.y);
+                    const float4 t = T4[j * 16];
+                    acc.x = __fadd_rn(acc.x, t.x), acc.y = __fadd_rn(acc.y, t.y);
+                    acc.z = __fadd_rn(acc.z, t.z), acc.w = __fadd_rn(acc.w, t.w);
                 }
             }
-            o2[q * 32] = acc;
+            if (q < n) o4[q * 16] = acc;
         }
     }
 }

@@ -120,12 +120,12 @@ class SconeOcc(nn.Module):
         (Q_c, 3), `view_harmonics[c]` (Q_c, 64) -> list of (Q_c, 1) outputs, those of `self(clouds[c][None],
         queries[c][None], view_harmonics[c][None])[0]` called in the same order: the random sub-samples of every cell
         are drawn here on the host in exactly that order (`draw_subsamples`), then ONE ragged CUDA forward runs."""
-        if self.training and self.dropout is not None:
-            raise NotImplementedError("the fused SconeOcc forward has no dropout: call .eval() (dropout=%r)" % self.dropout)
-        ops.refuse_grad("SconeOcc.forward_cells", *clouds, *queries, *view_harmonics, module=self)
         n_cells = len(clouds)
         if n_cells == 0:
             return []
+        if self.training and self.dropout is not None:
+            raise NotImplementedError("the fused SconeOcc forward has no dropout: call .eval() (dropout=%r)" % self.dropout)
+        ops.refuse_grad("SconeOcc.forward_cells", *clouds, *queries, *view_harmonics, module=self)
         dev = clouds[0].device
         sizes = [int(c.shape[0]) for c in clouds]
         n_q = [int(q.shape[0]) for q in queries]

@@ -13,4 +13,11 @@ views = synth.sphere_cameras(10, 1.5, torch.Generator().manual_seed(1)).to(dev)
 for _ in range(4):
     out = scone_utils.compute_view_state_harmonics(big, views, base, hp, ha, 7, 14)
 torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(50):
+    out = scone_utils.compute_view_state_harmonics(big, views, base, hp, ha, 7, 14)
+b.record()
+torch.cuda.synchronize()
+print("fused view state + harmonics, 200704 points x 10 views: %.1f us per call (CUDA events, 50 calls)" % (a.elapsed_time(b) * 20))
 print(out.abs().sum().item())
