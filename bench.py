@@ -716,8 +716,8 @@ def run_ours(args, cfg):
                     "staging_probe_ms": [round(v, 3) for v in probe_ms], "staging_kept": keep,
                     "clocks": e2e_clocks,
                     "pinned_h2d_copy_alone_ms": statistics.median(floor_each[2:]) if floor_each else None,
-                    "api": ("mac_covgain_host (C ABI, pinned HOST buffers in, host scores out; 8 H2D slices overlapped with the "
-                            "kernel) + argmax on the host") if world == 1 else
+                    "api": ("mac_covgain_host (C ABI, pinned HOST buffers in, host scores out; cameras + 12 point slices on a copy stream, "
+                            "each slice integrated while the next one crosses PCIe) + argmax on the host") if world == 1 else
                            "pinned host tensors -> each rank uploads its own 1/N of the point rows -> point-partitioned "
                            "scoring step (PeerScoreBoard.step_points: all cameras over the local points, exact int64 partial "
                            "sums exchanged over NVLink inside the kernel, bitwise the scores of `value`) -> scores, argmax "
