@@ -59,39 +59,33 @@ __device__ bool wait_for_ranks(const unsigned int *flags, int world, unsigned in
     return true;
 }
 
-// best[b] = first maximum of scores[b, :] (all NT threads of one CTA)
+// best[b] = first maximum of scores[b, :] (all NT threads of one CTA).  One warp per row, shuffle reduction under the
+// total order of score_better: no block barrier per row (the first version reduced every row through shared memory with
+// 8 barriers; at 32 clouds -- BASELINE config 4 -- that loop alone took ~40 us of the finishing CTA).
 template <int NT>
 __device__ void argmax_rows(const float *scores, int B, int C, long long *best)
 {
-    __shared__ float s_val[NT];
-    __shared__ int s_idx[NT];
-    for (int b = 0; b < B; ++b) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = warp; b < B; b += NT / 32) {
         float v = 0.f;
         int idx = 0x7fffffff;
-        for (int c = threadIdx.x; c < C; c += NT) {
+        for (int c = lane; c < C; c += 32) {
             const float x = __ldcg(scores + static_cast<size_t>(b) * C + c);  // written by peers: skip L1
             if (idx == 0x7fffffff || score_better(x, c, v, idx)) {
                 v = x;
                 idx = c;
             }
         }
-        s_val[threadIdx.x] = v;
-        s_idx[threadIdx.x] = idx;
-        __syncthreads();
-        for (int off = NT / 2; off > 0; off >>= 1) {
-            if (threadIdx.x < off) {
-                const float ov = s_val[threadIdx.x + off];
-                const int oi = s_idx[threadIdx.x + off];
-                if (oi != 0x7fffffff &&
-                    (s_idx[threadIdx.x] == 0x7fffffff || score_better(ov, oi, s_val[threadIdx.x], s_idx[threadIdx.x]))) {
-                    s_val[threadIdx.x] = ov;
-                    s_idx[threadIdx.x] = oi;
-                }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, d);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, d);
+            if (oi != 0x7fffffff && (idx == 0x7fffffff || score_better(ov, oi, v, idx))) {
+                v = ov;
+                idx = oi;
             }
-            __syncthreads();
         }
-        if (threadIdx.x == 0) best[b] = s_idx[0];
-        __syncthreads();
+        if (lane == 0) best[b] = idx;
     }
 }
 
