@@ -350,6 +350,13 @@ int mac_sample_proxy_points_f32(const float *X, const float *preds, const float 
  *      mac_sample_proxy_points_f32 (rows >= counts[2c+1] are left untouched), counts (C, 2) = (points kept, unique
  *      picks), volume (C) = sum of the kept occupancies (`fov_proxy_volume`, :1621; may be null).
  * ------------------------------------------------------------------------------------------- */
+/* The resolution filter of Cell.fill for all cells of one Scene.fill_cells call, /root/reference/macarons/utility/
+ * macarons_utils.py:2556-2561 (`min(cdist(new.double(), stored.double())) > resolution`, one cdist per cell there):
+ * pts (M, 3) new points, slot (M) the cell slot of each, stored (E, 3) the stored points of all slots concatenated,
+ * off (n_slots + 1) their row offsets -> out (M) float64 distance to the nearest stored point of the own cell (+inf if none). */
+int mac_cell_min_dist_f64(const float *pts, const int *slot, const float *stored, const int *off, double *out, int M,
+                          void *stream);
+
 /* Camera.get_points_in_fov for ONE camera, /root/reference/macarons/utility/macarons_utils.py:2400-2435:
  * X (N, 3), cam (36 floats, same layout as a row of `cams` above), ndc_bounds (HOST, 4 floats), fov_range < 0 = no range
  * test -> mask (N) bytes, 1 where the point projects inside the image, lies in front of the camera and within range. */

@@ -129,6 +129,8 @@ SYMBOLS["mac_points_in_fov_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, ctype
                                                    ctypes.c_void_p, ctypes.c_void_p])
 
 
+SYMBOLS["mac_cell_min_dist_f64"] = (ctypes.c_int, [_c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                   ctypes.c_int, ctypes.c_void_p])
 SYMBOLS["mac_unproject_depth_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                      ctypes.c_void_p])
 SYMBOLS["mac_signed_distance_f32"] = (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p, _c_float_p, _c_float_p, ctypes.c_int,

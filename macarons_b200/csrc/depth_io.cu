@@ -108,3 +108,43 @@ extern "C" int mac_signed_distance_f32(const float *pts, const float *depth_maps
     count_launch();
     return MAC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Cell.fill resolution filter for ALL cells of a Scene.fill_cells call at once (reference
+// utility/macarons_utils.py:2556-2561: `torch.min(torch.cdist(new.double(), stored.double()), -1)[0] > resolution`, once per
+// cell): new point i belongs to cell slot[i]; the stored points of slot s are rows [off[s], off[s+1]) of `stored`.
+// out[i] = distance (float64) to the nearest stored point of its own cell, +inf if the cell is empty.
+// ------------------------------------------------------------------------------------------------
+namespace mac {
+namespace {
+__global__ void __launch_bounds__(128) cell_min_dist_kernel(const float *__restrict__ pts, const int *__restrict__ slot,
+                                                            const float *__restrict__ stored, const int *__restrict__ off,
+                                                            double *__restrict__ out, int M)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= M) return;
+    const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    const int s = slot[i];
+    double best = INFINITY;
+    for (int j = off[s]; j < off[s + 1]; ++j) {
+        const double dx = x - static_cast<double>(__ldg(stored + 3 * j)), dy = y - static_cast<double>(__ldg(stored + 3 * j + 1)),
+                     dz = z - static_cast<double>(__ldg(stored + 3 * j + 2));
+        best = fmin(best, dx * dx + dy * dy + dz * dz);
+    }
+    out[i] = sqrt(best);
+}
+}  // namespace
+}  // namespace mac
+
+extern "C" int mac_cell_min_dist_f64(const float *pts, const int *slot, const float *stored, const int *off, double *out, int M,
+                                     void *stream)
+{
+    using namespace mac;
+    MAC_REQUIRE(M >= 0, "M must be non-negative");
+    if (M == 0) return MAC_OK;
+    MAC_REQUIRE(pts && slot && off && out, "null pointer");
+    cell_min_dist_kernel<<<(M + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(pts, slot, stored, off, out, M);
+    MAC_CUDA(cudaGetLastError());
+    count_launch();
+    return MAC_OK;
+}

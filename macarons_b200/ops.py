@@ -567,6 +567,24 @@ def points_in_fov(X_world, cam_row, ndc_bounds, fov_range):
     return mask.bool()
 
 
+def cell_min_dist(pts, slot, stored, off):
+    """pts (M,3) f32, slot (M) int32, stored (E,3) f32, off (n_slots+1) int32 -> (M,) float64 distance of every point to
+    the nearest stored point of its own cell slot (+inf for empty slots)."""
+    _require_cuda_f32("pts", pts)
+    M = pts.shape[0]
+    out = torch.empty((M,), dtype=torch.float64, device=pts.device)
+    if M == 0:
+        return out
+    pts, slot, off = pts.contiguous(), slot.contiguous(), off.contiguous()
+    stored = stored.contiguous() if stored.numel() else torch.zeros((1, 3), dtype=torch.float32, device=pts.device)
+    if slot.dtype != torch.int32 or off.dtype != torch.int32 or stored.dtype != torch.float32:
+        raise TypeError("slot / off must be int32 and stored float32")
+    with torch.cuda.device(pts.device):
+        _lib.check(_lib.load().mac_cell_min_dist_f64(pts.data_ptr(), slot.data_ptr(), stored.data_ptr(), off.data_ptr(),
+                                                     out.data_ptr(), M, _stream_ptr(pts.device)))
+    return out
+
+
 def unproject_depth(depth, cams, H, W):
     """depth (B, H*W) metric depth, cams (B, 18) [inverse full projection | f1 | f2] -> world points (B, H*W, 3)."""
     _require_cuda_f32("depth", depth)
