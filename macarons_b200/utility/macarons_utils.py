@@ -238,21 +238,39 @@ def compute_scene_occupancy_probability_field(params, macarons, camera, surface_
     k_min = 2 * 2 * params.k_for_knn
     max_pass = 20000                       # max_points_per_pass of the reference's per-cell call (:1508)
 
-    # ---- host loop: which proxy points and which surface points belong to every occupied cell ----
+    # ---- which proxy points and which surface points belong to every occupied cell: ONE host synchronisation ----
+    # (the reference does this cell by cell with ~20 small tensor ops and three synchronisations each, :1443-1460)
+    cell_list = proxy_cells.cpu().tolist()                       # sorted cell indices (torch.unique), the loop order
+    grid = (surface_scene.grid_l, surface_scene.grid_w, surface_scene.grid_h)
+    stored = [proxy_scene.cells[str(c)].cell_features.view(-1).long() for c in cell_list]   # proxy indices held by each cell
+    n_stored = [int(t.numel()) for t in stored]
     cell_rows, cell_clouds, cell_centres, cell_diags = [], [], [], []
-    for proxy_cell in proxy_cells:
-        cell = proxy_scene.cells[proxy_scene.get_key_from_idx(proxy_cell)]
-        cloud = surface_scene.get_pt_cloud_from_cells(surface_scene.get_neighboring_cells(proxy_cell), return_features=False)
-        _, indices = proxy_scene.get_pt_cloud_from_cells(proxy_cell, return_features=True)
-        mask = proxy_scene.get_proxy_mask_from_indices(indices)
+    if sum(n_stored) > 0:
+        idx_all = torch.cat(stored)
+        owner = torch.repeat_interleave(torch.arange(len(cell_list), device=idx_all.device),
+                                        torch.tensor(n_stored, device=idx_all.device))
         if use_supervision_occ_mask:
-            mask = mask * occ_mask
-        rows = torch.nonzero(mask).view(-1)                 # ascending proxy index, like boolean-mask indexing
-        if cloud.shape[0] > k_min and rows.numel() > 0:
-            cell_rows.append(rows)
-            cell_clouds.append(cloud)
-            cell_centres.append(cell.center.view(1, 3))
-            cell_diags.append(params.prediction_neighborhood_size * torch.linalg.norm(cell.x_max - cell.x_min))
+            keep = occ_mask[idx_all]
+            idx_all, owner = idx_all[keep], owner[keep]
+        # ascending proxy index inside every cell (what indexing with a boolean mask gives); a cell holds an index once
+        order = torch.argsort(owner * proxy_scene.n_proxy_points + idx_all)
+        idx_all, owner = idx_all[order], owner[order]
+        n_rows = torch.bincount(owner, minlength=len(cell_list)).tolist()                    # the synchronisation
+        row_off = 0
+        for c, n_r in zip(cell_list, n_rows):
+            rows = idx_all[row_off:row_off + n_r]
+            row_off += n_r
+            # surface points of the (up to 27) neighbouring cells, clamped to the grid, in sorted unique order (:2706-2718)
+            neigh = sorted({(min(max(c[0] + a, 0), grid[0] - 1), min(max(c[1] + b, 0), grid[1] - 1),
+                             min(max(c[2] + d, 0), grid[2] - 1)) for a in (-1, 0, 1) for b in (-1, 0, 1) for d in (-1, 0, 1)})
+            parts = [surface_scene.cells[str(list(k))].cell_pts for k in neigh]
+            n_cloud = sum(int(t.shape[0]) for t in parts)
+            if n_cloud > k_min and n_r > 0:
+                cell = proxy_scene.cells[str(c)]
+                cell_rows.append(rows)
+                cell_clouds.append(torch.cat(parts))
+                cell_centres.append(cell.center.view(1, 3))
+                cell_diags.append(params.prediction_neighborhood_size * torch.linalg.norm(cell.x_max - cell.x_min))
 
     n_harm = params.n_harmonics
     if cell_rows:
@@ -290,7 +308,12 @@ def compute_scene_occupancy_probability_field(params, macarons, camera, surface_
                     queries.append(X_norm[q0 + lo:q0 + up])
                     vhs.append(harmonics[q0 + lo:q0 + up])
                 q0, p0 = q0 + n_q, p0 + n_p
-            probs = torch.cat(_scone_occ(macarons, params).forward_cells(clouds, queries, vhs)).view(-1, 1)
+            # groups of cells: while the GPU runs the ragged forward of one group, the host draws the random sub-samples
+            # (three torch.randperm of up to ~27 000 entries per cell, in the reference's order) of the next one
+            occ_net, group, outs = _scone_occ(macarons, params), 12, []
+            for g0 in range(0, len(clouds), group):
+                outs.extend(occ_net.forward_cells(clouds[g0:g0 + group], queries[g0:g0 + group], vhs[g0:g0 + group]))
+            probs = torch.cat(outs).view(-1, 1)
         proxy_scene.proxy_proba[rows_all] = probs
     else:
         X_cells = torch.zeros(0, 3, device=device)
