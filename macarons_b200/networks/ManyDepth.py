@@ -130,14 +130,9 @@ class ManyDepth(nn.Module):
     def forward(self, x, x_alpha, R, T, zfar, device, gt_pose=None):
         """x (B,3,H,W), x_alpha (B,n_alpha,3,H,W), R (B,3,3), T (B,3), zfar (B,), gt_pose (B,n_alpha,6)
         -> (pose, disp1 (B,1,H,W), disp2, disp3, disp4)   [reference ManyDepth.py:719-758]"""
-        # the reference reads zfar[0].item() on every call (a host synchronisation per frame); here the check is repeated
-        # only when the tensor (storage address / version counter) changes
-        zkey = (zfar.data_ptr(), zfar._version, tuple(zfar.shape))
-        if getattr(self, "_zfar_checked", None) != zkey:
-            if self.d_max != zfar[0].item():
-                raise NameError("Model variable d_max is different from the provided zfar.\n"
-                                "Please check that d_min and d_max are respectively equal to parameters znear and zfar.")
-            self.__dict__["_zfar_checked"] = zkey
+        if self.d_max != zfar[0].item():      # (a host synchronisation per frame, as in the reference :728)
+            raise NameError("Model variable d_max is different from the provided zfar.\n"
+                            "Please check that d_min and d_max are respectively equal to parameters znear and zfar.")
         if gt_pose is None:
             raise NameError("Input gt_pose is missing!The parameter 'learn_pose' is set to False. "
                             "Consequently, Model must take ground truth poses as an input.")
