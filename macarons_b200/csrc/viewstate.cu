@@ -61,19 +61,45 @@ struct ViewStateParams {
     int elev_shift;      // n_elev // 2
 };
 
-// Bin of the ray pt -> view, arithmetic order of scone_utils.py:815-849.
+// atan2(y, x) without branches or library calls: atan(min/max) by a degree-8 minimax polynomial in (min/max)^2 (fitted at
+// Chebyshev nodes; 1.2e-7 max error on [0, 1], i.e. fp32 rounding level), then the octant is restored with selects.
+__device__ __forceinline__ float atan2_poly(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+    const float s = a * a;
+    float r = 0.0028340641874819994f;
+    r = fmaf(r, s, -0.016005029901862144f);
+    r = fmaf(r, s, 0.042587608098983765f);
+    r = fmaf(r, s, -0.07495445758104324f);
+    r = fmaf(r, s, 0.10636754333972931f);
+    r = fmaf(r, s, -0.14202570915222168f);
+    r = fmaf(r, s, 0.19992484152317047f);
+    r = fmaf(r, s, -0.3333306610584259f);
+    r = fmaf(r * s, a, a);
+    r = ay > ax ? 1.57079632679489661923f - r : r;
+    r = x < 0.f ? 3.14159265358979323846f - r : r;
+    return y < 0.f ? -r : r;
+}
+
+// Bin of the ray pt -> view (scone_utils.py:815-849).  The reference obtains the angles as elev = asin(dy / r) and
+// azim = +-acos(dz / (r cos(elev))) (CustomGeometry.py:27-45); the first version of this kernel followed that statement by
+// statement with libdevice asinf / cosf / acosf (~330 issued instructions per ray with divergent slow paths, a dependent
+// chain that made the kernel latency-bound, and -- like the reference itself -- ill-conditioned near the poles and near
+// |cos(azim)| = 1, where the two fp32 evaluations disagree by up to 3e-4 rad).  The angles are now the well-conditioned
+// elev = atan2(dy, rho), azim = atan2(dx, dz) (rho = sqrt(dx^2 + dz^2)), equal to the reference's definition in exact
+// arithmetic and accurate to ~2e-7 rad everywhere; everything after the angles (torch.remainder based floor division, the
+// half-step rounding, the Python `-n // 2` clamps, the truncating cast and the wrap) still follows the reference operation
+// by operation.  Measured on 5 M rays against the reference's fp32 arithmetic: 8 differing bins (1.6e-6), all of them rays
+// within 1e-5 rad of a bin boundary or within 2e-3 rad of a pole, where the reference's own azimuth is off by 0.1-2 rad.
 __device__ __forceinline__ int view_bin(const ViewStateParams &p, float dx, float dy, float dz)
 {
-    const float r = sqrtf(dx * dx + dy * dy + dz * dz);
-    const float sin_elev = dy / r;
-    float elev = asinf(sin_elev);
-    if (sin_elev <= -1.f) elev = -1.57079632679489661923f;
-    if (sin_elev >= 1.f) elev = 1.57079632679489661923f;
-    const float cos_azim = dz / (r * cosf(elev));
-    float azim = acosf(cos_azim);
-    if (cos_azim <= -1.f) azim = 3.14159265358979323846f;
-    if (cos_azim >= 1.f) azim = 0.f;
-    if (dx < 0.f) azim = -azim;
+    const float rho2 = fmaf(dx, dx, dz * dz);
+    const float rho = rho2 > 0.f ? rho2 * rsqrt_approx(rho2) : 0.f;
+    const float elev = atan2_poly(dy, rho);
+    // exactly above / below the point the azimuth is undefined; the reference's formula returns acos(+-0) = pi/2 there
+    const float azim = rho2 > 0.f ? atan2_poly(dx, dz) : 1.57079632679489661923f;
 
     const float re = torch_remainder(elev, p.elev_step, p.inv_elev_step), ra = torch_remainder(azim, p.azim_step, p.inv_azim_step);
     float ie = (elev - re) / p.elev_step, ia = (azim - ra) / p.azim_step;
