@@ -31,7 +31,7 @@ WORKLOADS = {
 METRIC = "coverage_gain_evals_per_sec"
 UNIT = "evals/s"
 N_INPUT_SETS = 5          # distinct resident input sets rotated between steps (5 x 54.6 MB > 126 MB L2)
-FMA_CYCLES_PER_PAIR = 74.0  # FMA-pipe cycles per (point, camera) pair: 27 FFMA2 x 2 + 11 FFMA + 9 FADD/FMUL
+FMA_CYCLES_PER_PAIR = 74.0  # FMA-pipe cycles per (point, camera) pair: 65 FFMA + 4 FADD + 4 FMUL + 1 FADD of the tile sum
                             # (SASS of the sweep loop); 1 per cycle per SM sub-partition
 
 

@@ -25,6 +25,7 @@
 
 #include "gather_dev.h"
 #include "mac_common.h"
+#include "sh_eval_mixed.h"
 #include "sh_horner_gen.h"
 
 namespace mac {
@@ -102,13 +103,16 @@ __device__ __forceinline__ void load_coefficients(const float (&h)[64], float (&
     if constexpr (PACKED) mac_sh_pretransform_pq(h, g0, gp, scale);
     else mac_sh_pretransform(h, g, scale);
 }
-template <bool PACKED, int NG, int NG0, int NGP>
+// EVAL: 0 = P + u_x Q form with scalar FFMA (63 per ray; default), 1 = scalar A/B form (75 FFMA per ray),
+// 2 = P + u_x Q form with packed fma.rn.f32x2 (27 FFMA2 + 9 FFMA per ray).  0 and 2 are bitwise identical.
+template <int EVAL, int NG, int NG0, int NGP>
 __device__ __forceinline__ void eval_two_rays(const float (&g)[NG], const float (&g0)[NG0],
                                               const unsigned long long (&gp)[NGP], const Ray a, const Ray b, float &za,
                                               float &zb)
 {
-    if constexpr (PACKED) mac_sh_eval2_pq(g0, gp, a.ux, a.ct, a.uz, b.ux, b.ct, b.uz, za, zb);
-    else mac_sh_eval2(g, a.ux, a.ct, a.uz, b.ux, b.ct, b.uz, za, zb);
+    if constexpr (EVAL == 0) mac_sh_eval2_pq_mixed<0, false>(g0, gp, a.ux, a.ct, a.uz, b.ux, b.ct, b.uz, za, zb);
+    else if constexpr (EVAL == 1) mac_sh_eval2(g, a.ux, a.ct, a.uz, b.ux, b.ct, b.uz, za, zb);
+    else mac_sh_eval2_pq(g0, gp, a.ux, a.ct, a.uz, b.ux, b.ct, b.uz, za, zb);
 }
 
 // The activation is split so that its two MUFU results are consumed one loop iteration apart.
@@ -146,11 +150,11 @@ __device__ __forceinline__ unsigned reduce_batch(const float *red, long long *wa
     return ok ? 0u : (1u << (cb >> 5));
 }
 
-// WARPS x MINB = resident warps per SM (register budget 65536 / (32 * WARPS * MINB)); PACKED selects the
-// fma.rn.f32x2 evaluator.
-template <bool SIGMOID, bool REDUCE, bool PACKED, int WARPS, int MINB>
+// WARPS x MINB = resident warps per SM (register budget 65536 / (32 * WARPS * MINB)); EVAL selects the evaluator.
+template <bool SIGMOID, bool REDUCE, int EVAL, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const CovgainParams prm, const __grid_constant__ CUtensorMap harm_map)
 {
+    constexpr bool PACKED = EVAL != 1;   // coefficients held as 8 floats + 28 (P, Q) register pairs
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) covgain_kernel(const Covgain
                 const float4 nA = ws.cams[2 * jj + 2], nB = ws.cams[2 * jj + 3];  // table has 2 pad entries
                 const Ray qA = make_ray(nA, px, py, pz), qB = make_ray(nB, px, py, pz);
                 float zA, zB;
-                eval_two_rays<PACKED>(g, g0, gp, rA, rB, zA, zB);
+                eval_two_rays<EVAL>(g, g0, gp, rA, rB, zA, zB);
                 const float vA = activation_finish<SIGMOID>(eA), vB = activation_finish<SIGMOID>(eB);
                 // camera (within the chunk) of the pair being finished; at jj == 0 there is none: c = -2 and the
                 // value lands in rows 30/31 of the transpose buffer, which are rewritten before they are summed.
@@ -502,8 +506,9 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
 
     int device = 0;
     MAC_CUDA(cudaGetDevice(&device));
-    // MAC_COVGAIN_VARIANT=1 selects the scalar-FFMA evaluator (ablation knob for tools/bench_covgain.py);
-    // default 0 = packed fma.rn.f32x2 Horner steps.
+    // MAC_COVGAIN_VARIANT (ablation knob for tools/bench_covgain.py): 0 = default, scalar FFMA Horner steps of the
+    // P + u_x Q form; 1 = scalar A/B form; 2 = packed fma.rn.f32x2 Horner steps (bitwise identical to 0, 2.7 % slower:
+    // an FFMA2 holds the issue port for two cycles).
     static const int variant = [] {
         const char *e = getenv("MAC_COVGAIN_VARIANT");
         return e ? atoi(e) : 0;
@@ -549,18 +554,19 @@ int plan_and_launch(bool reduce, const float *pts, int pts_dim, const float *har
     const size_t smem = sizeof(WarpSmem) * warps_per_cta;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-#define MAC_LAUNCH_V(SIG, RED, PACKED, WARPS, MINB)                                                              \
+#define MAC_LAUNCH_V(SIG, RED, EVAL, WARPS, MINB)                                                                \
     do {                                                                                                          \
         static DeviceOnce once;                                                                                   \
-        if (int rc = ensure_dynamic_smem(once, covgain_kernel<SIG, RED, PACKED, WARPS, MINB>, static_cast<int>(smem))) \
+        if (int rc = ensure_dynamic_smem(once, covgain_kernel<SIG, RED, EVAL, WARPS, MINB>, static_cast<int>(smem))) \
             return rc;                                                                                            \
-        covgain_kernel<SIG, RED, PACKED, WARPS, MINB><<<grid, WARPS * 32, smem, st>>>(prm, harm_map);             \
+        covgain_kernel<SIG, RED, EVAL, WARPS, MINB><<<grid, WARPS * 32, smem, st>>>(prm, harm_map);             \
     } while (0)
 #define MAC_LAUNCH(SIG, RED)                                       \
     do {                                                           \
         switch (variant) {                                         \
-        case 1: MAC_LAUNCH_V(SIG, RED, false, 8, 2); break;        \
-        default: MAC_LAUNCH_V(SIG, RED, true, 8, 2); break;        \
+        case 1: MAC_LAUNCH_V(SIG, RED, 1, 8, 2); break;            \
+        case 2: MAC_LAUNCH_V(SIG, RED, 2, 8, 2); break;            \
+        default: MAC_LAUNCH_V(SIG, RED, 0, 8, 2); break;           \
         }                                                          \
     } while (0)
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Kernel-only timing of mac_covgain_f32 for a few shapes (CUDA events, inputs rotated to defeat L2)."""
-import os, sys, json
+import os, sys, json, zlib
 ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
@@ -36,4 +36,6 @@ for B, P, C, rng in shapes:
     byts = B * P * 272 + B * (rng[1] - rng[0]) * 16
     print(json.dumps({"B": B, "P": P, "C_local": rng[1] - rng[0], "median_us": round(med * 1e3, 2), "min_us": round(ts[0] * 1e3, 2),
                       "Gpairs_per_s": round(pairs / med / 1e6, 2), "GBps": round(byts / med / 1e6, 1),
-                      "evals_per_s": round(B * (rng[1] - rng[0]) / med * 1e3)}))
+                      "evals_per_s": round(B * (rng[1] - rng[0]) / med * 1e3),
+                      "variant": os.environ.get("MAC_COVGAIN_VARIANT", "0"),
+                      "out_crc": zlib.crc32(ops.coverage_gain(*sets[0], cams, cam_range=rng, out=out).cpu().numpy().tobytes())}))
