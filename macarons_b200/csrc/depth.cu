@@ -14,6 +14,7 @@
 // and reduces |mean_alpha(warped) - target| over channels with warp shuffles.  The 90 M-float warped tensor, the
 // 96 x H x W x 3 world-point tensor and the per-plane camera batches of the reference are never materialised.
 #include <math.h>
+#include <stdlib.h>
 
 #include "nets.h"
 #include "tc_common.h"
@@ -55,20 +56,22 @@ struct Im2colParams {
 
 // one thread per (output pixel, tap, group of VEC channels): VEC = 4 (128-bit copies) when every channel count and row
 // stride is a multiple of 4, else 1
-template <int VEC>
+// IDX = unsigned when the element count fits 32 bits (the index decomposition is five integer divisions per element;
+// 64-bit divisions made this kernel ALU-bound), long long otherwise
+template <int VEC, typename IDX>
 __global__ void __launch_bounds__(256) im2col_kernel(const Im2colParams p)
 {
     const int taps = p.k * p.k;
     const int C = p.Ca + p.Cb;
     const int groups = C / VEC;
-    const long long total = static_cast<long long>(p.n) * p.Ho * p.Wo * taps * groups;
-    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const IDX total = static_cast<IDX>(p.n) * p.Ho * p.Wo * taps * groups;
+    for (IDX i = blockIdx.x * static_cast<IDX>(256) + threadIdx.x; i < total; i += gridDim.x * static_cast<IDX>(256)) {
         const int c = static_cast<int>(i % groups) * VEC;
-        const long long rt = i / groups;
-        const long long row = rt / taps;
+        const IDX rt = i / groups;
+        const IDX row = rt / taps;
         const int tap = static_cast<int>(rt - row * taps);
         const int ky = tap / p.k, kx = tap - ky * p.k;
-        const long long img = row / (static_cast<long long>(p.Ho) * p.Wo);
+        const IDX img = row / (static_cast<IDX>(p.Ho) * p.Wo);
         const int rem = static_cast<int>(row - img * p.Ho * p.Wo);
         const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
         int y = oy * p.stride - p.pad + ky, x = ox * p.stride - p.pad + kx;
@@ -87,16 +90,16 @@ __global__ void __launch_bounds__(256) im2col_kernel(const Im2colParams p)
                     ya = min(static_cast<int>(floorf(static_cast<float>(y) * p.scale_h)), p.Ha - 1);
                     xa = min(static_cast<int>(floorf(static_cast<float>(x) * p.scale_w)), p.Wa - 1);
                 }
-                src = p.a + ((img * p.Ha + ya) * p.Wa + xa) * p.lda + c;
+                src = p.a + ((static_cast<size_t>(img) * p.Ha + ya) * p.Wa + xa) * p.lda + c;
             } else {
-                src = p.b + ((img * p.H + y) * p.W + x) * p.ldb + (c - p.Ca);
+                src = p.b + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.ldb + (c - p.Ca);
             }
         }
-        float *dst = p.col + row * p.ldc + static_cast<long long>(tap) * C + c;
+        float *dst = p.col + static_cast<size_t>(row) * p.ldc + static_cast<size_t>(tap) * C + c;
         if (VEC == 4) *reinterpret_cast<float4 *>(dst) = src ? *reinterpret_cast<const float4 *>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
         else *dst = src ? *src : 0.f;
         if (tap == taps - 1 && c == 0)   // zero the K padding of this row (K -> ldc)
-            for (int z = taps * C; z < p.ldc; ++z) p.col[row * p.ldc + z] = 0.f;
+            for (int z = taps * C; z < p.ldc; ++z) p.col[static_cast<size_t>(row) * p.ldc + z] = 0.f;
     }
 }
 
@@ -283,9 +286,25 @@ int conv(Ctx &cx, const mac_conv_w_t &w, const Act &a, const Act *b, int H, int 
                               w.lin.K, w.act, res ? res->p : nullptr, res ? res->ld : 0, nullptr, 0, nullptr, nullptr, 0.f, 0,
                               cx.st, res_first);
     }
+    // implicit GEMM: the tcgen05 kernel gathers its A operand from the activations (no im2col matrix); the explicit
+    // im2col below remains for the layers whose channel counts do not tile a 128-byte k-chunk (3, 16 + 3, ...)
+    static const int force_im2col = [] { const char *e = getenv("MAC_DEPTH_IM2COL"); return e ? atoi(e) : 0; }();   // A/B timing knob
+    ConvGather g{};
+    g.a = a.p, g.lda = a.ld, g.Ca = Ca, g.Ha = a.H, g.Wa = a.W;
+    g.b = b ? b->p : nullptr, g.ldb = b ? b->ld : 0, g.Cb = Cb;
+    g.H = H, g.W = W, g.Ho = Ho, g.Wo = Wo, g.k = w.k, g.stride = w.stride, g.pad = w.pad, g.reflect = w.reflect;
+    g.scale_h = p.scale_h, g.scale_w = p.scale_w;
+    if (!force_im2col && w.lin.lo && conv_gather_supported(g))
+        return linear_forward_conv(g, w.lin.hi, w.lin.lo, w.lin.ldw, w.lin.bias, out.p, out.ld, static_cast<int>(rows), w.lin.N,
+                                   w.lin.K, w.act, res ? res->p : nullptr, res ? res->ld : 0, cx.st, res_first, cx.col, cx.col_floats);
     const bool vec = Ca % 4 == 0 && Cb % 4 == 0 && a.ld % 4 == 0 && (!b || b->ld % 4 == 0) && p.ldc % 4 == 0;
-    if (vec) im2col_kernel<4><<<grid_for(rows * w.k * w.k * ((Ca + Cb) / 4), 256, 148 * 32), 256, 0, cx.st>>>(p);
-    else im2col_kernel<1><<<grid_for(rows * w.k * w.k * (Ca + Cb), 256, 148 * 32), 256, 0, cx.st>>>(p);
+    const long long elems = rows * w.k * w.k * ((Ca + Cb) / (vec ? 4 : 1));
+    const int grid = grid_for(elems, 256, 148 * 32);
+    const bool small = elems + 256ll * grid < (1ll << 32);
+    if (vec && small) im2col_kernel<4, unsigned><<<grid, 256, 0, cx.st>>>(p);
+    else if (vec) im2col_kernel<4, long long><<<grid, 256, 0, cx.st>>>(p);
+    else if (small) im2col_kernel<1, unsigned><<<grid, 256, 0, cx.st>>>(p);
+    else im2col_kernel<1, long long><<<grid, 256, 0, cx.st>>>(p);
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return linear_forward(cx.col, p.ldc, w.lin.hi, w.lin.lo, w.lin.ldw, w.lin.bias, out.p, out.ld, static_cast<int>(rows), w.lin.N,

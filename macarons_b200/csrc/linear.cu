@@ -29,6 +29,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include "nets.h"
 #include "tc_common.h"
 
 namespace mac {
@@ -98,7 +99,23 @@ struct LinearParams {
     const float *lnin_stats;   // (M, 2) = (mean, rstd) per row, or null
     const float *lnin_g, *lnin_b;   // (K)
     float *stats_out;          // (M, 2): (mean, rstd) of every output row (for the LayerNorm-on-load of the next layer)
+    ConvGather conv;           // GATHER kernels only: X is the implicit im2col matrix of this convolution
+    // split-K: tile = (m tile, n tile, split); split s contracts the k-chunks [s * chunks_per_split, ...) and writes its raw
+    // fp32 partial tile to out + s * split_stride (bias / activation / residual are then applied by splitk_finish_kernel)
+    int splits, chunks_per_split;
+    long long split_stride;
 };
+
+struct TileCoord {
+    int m0, n0, k0, k1, sp;
+};
+template <int BN>
+__device__ __forceinline__ TileCoord tile_coord(const LinearParams &p, const int tile, const int nk)
+{
+    const int sp = tile % p.splits, mn = tile / p.splits;
+    const int k0 = sp * p.chunks_per_split;
+    return TileCoord{(mn / p.n_tiles_n) * kBM, (mn % p.n_tiles_n) * BN, k0, min(nk, k0 + p.chunks_per_split), sp};
+}
 
 // GELU(x) = x/2 (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, the accuracy class of
 // erff itself): erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z), z >= 0.  14 instructions with two MUFU
@@ -153,7 +170,10 @@ struct Cfg {
 
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA and MMA warps run ahead of the
 // epilogue through a ring of operand stages and two TMEM accumulators.
-template <int BN, bool SPLIT, int ACT>
+// GATHER: X is never materialised; warps 0 and 3 build the X k-chunks of a convolution (ConvGather) straight from the NHWC
+// activations with 16-byte cp.async copies laid out as the SWIZZLE_128B pattern the split warps and the UMMA descriptors
+// expect (zero fill for padding, rows beyond M and columns beyond K), completing on the same full_x barriers.
+template <int BN, bool SPLIT, int ACT, bool GATHER>
 __global__ void __launch_bounds__((Cfg<BN, SPLIT>::kThreads), 1)
 linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
               const __grid_constant__ CUtensorMap mapBlo, const LinearParams p)
@@ -185,14 +205,14 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = (p.K + kBK - 1) / kBK;
-    const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+    const int n_tiles = p.n_tiles_m * p.n_tiles_n * p.splits;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapBhi);
         if (SPLIT) tma_prefetch_desc(&mapBlo);
         for (int s = 0; s < C::kRawSlots; ++s) {
-            mbar_init(&full_x[s], 1);
+            mbar_init(&full_x[s], GATHER ? 64 : 1);   // GATHER: one arrival per lane of the two gather warps
             mbar_init(&empty_x[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -214,13 +234,86 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (GATHER && (warp == 0 || warp == 3)) {
+        // ===== X producer (implicit GEMM): warp 0 gathers rows 0-63 of the tile, warp 3 rows 64-127; a lane owns two
+        // consecutive output pixels and copies their 128-byte k-chunk rows as eight 16-byte pieces =====
+        static_assert(!GATHER || SPLIT, "the gathered operand is consumed by the split warps");
+        const ConvGather &g = p.conv;
+        const int Cin = g.Ca + g.Cb;
+        const int seg_len = Cin < kBK ? Cin : kBK;     // 32, or 16: two taps per k-chunk
+        const int n_seg = kBK / seg_len;
+        const int taps = g.k * g.k;
+        const int r0 = (warp == 0 ? 0 : 64) + 2 * lane;
+        const bool resample = g.Ha != g.H || g.Wa != g.W;
+        int kt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const TileCoord tc = tile_coord<BN>(p, tile, nk);
+            const int m0 = tc.m0;
+            int img[2], iy0[2], ix0[2];
+            bool rok[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = m0 + r0 + i;
+                rok[i] = row < p.M;
+                const int rr = rok[i] ? row : 0;
+                img[i] = rr / (g.Ho * g.Wo);
+                const int rem = rr - img[i] * (g.Ho * g.Wo);
+                const int oy = rem / g.Wo;
+                iy0[i] = oy * g.stride - g.pad;
+                ix0[i] = (rem - oy * g.Wo) * g.stride - g.pad;
+            }
+            for (int kc = tc.k0; kc < tc.k1; ++kc, ++kt) {
+                const int s = kt % C::kRawSlots;
+                const uint32_t ph = (kt / C::kRawSlots) & 1;
+                mbar_wait(&empty_x[s], ph ^ 1);
+                uint8_t *slot = a_hi(s);
+                for (int sg = 0; sg < n_seg; ++sg) {
+                    const int kk = kc * kBK + sg * seg_len;
+                    const int tap = kk / Cin, c = kk - tap * Cin;
+                    const int ky = tap / g.k, kx = tap - ky * g.k;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        int y = iy0[i] + ky, x = ix0[i] + kx;
+                        bool ok = rok[i] && tap < taps;
+                        if (g.reflect) {
+                            y = y < 0 ? -y : (y >= g.H ? 2 * g.H - 2 - y : y);
+                            x = x < 0 ? -x : (x >= g.W ? 2 * g.W - 2 - x : x);
+                        } else {
+                            ok = ok && y >= 0 && y < g.H && x >= 0 && x < g.W;
+                        }
+                        const float *src = g.a;
+                        if (ok) {
+                            if (c < g.Ca) {
+                                int ya = y, xa = x;
+                                if (resample) {
+                                    ya = min(static_cast<int>(floorf(static_cast<float>(y) * g.scale_h)), g.Ha - 1);
+                                    xa = min(static_cast<int>(floorf(static_cast<float>(x) * g.scale_w)), g.Wa - 1);
+                                }
+                                src = g.a + (static_cast<size_t>(img[i] * g.Ha + ya) * g.Wa + xa) * g.lda + c;
+                            } else {
+                                src = g.b + (static_cast<size_t>(img[i] * g.H + y) * g.W + x) * g.ldb + (c - g.Ca);
+                            }
+                        }
+                        const int r = r0 + i;
+                        uint8_t *drow = slot + r * 128;
+                        const uint32_t nbytes = ok ? 16u : 0u;
+                        for (int pc = 0; pc < seg_len / 4; ++pc) {
+                            const int piece = sg * (seg_len / 4) + pc;
+                            cp_async16_zfill(drow + ((piece ^ (r & 7)) << 4), src + pc * 4, nbytes);
+                        }
+                    }
+                }
+                cp_async_mbar_arrive_noinc(&full_x[s]);
+            }
+        }
+    } else if (warp == 0) {
         // ===== X producer (TMA): runs up to kRawSlots k-chunks ahead of the tensor core =====
         if (lane == 0) {
             int kt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.n_tiles_n) * kBM;
-                for (int kc = 0; kc < nk; ++kc, ++kt) {
+                const TileCoord tc = tile_coord<BN>(p, tile, nk);
+                const int m0 = tc.m0;
+                for (int kc = tc.k0; kc < tc.k1; ++kc, ++kt) {
                     const int s = kt % C::kRawSlots;
                     const uint32_t ph = (kt / C::kRawSlots) & 1;
                     mbar_wait(&empty_x[s], ph ^ 1);
@@ -234,8 +327,9 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         if (lane == 0) {
             int kt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int n0 = (tile % p.n_tiles_n) * BN;
-                for (int kc = 0; kc < nk; ++kc, ++kt) {
+                const TileCoord tc = tile_coord<BN>(p, tile, nk);
+                const int n0 = tc.n0;
+                for (int kc = tc.k0; kc < tc.k1; ++kc, ++kt) {
                     const int s = kt & 1;
                     const uint32_t ph = (kt >> 1) & 1;
                     mbar_wait(&empty_w[s], ph ^ 1);
@@ -256,7 +350,8 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 mbar_wait(&acc_empty[ab], aph ^ 1);
                 tc_fence_after_sync();
                 const uint32_t tacc = tmem_base + ab * BN;
-                for (int kc = 0; kc < nk; ++kc, ++kt) {
+                const TileCoord tc = tile_coord<BN>(p, tile, nk);
+                for (int kc = tc.k0; kc < tc.k1; ++kc, ++kt) {
                     const int sx = kt % C::kRawSlots, s2 = kt & 1;
                     const uint32_t phx = (kt / C::kRawSlots) & 1, ph2 = (kt >> 1) & 1;
                     if (SPLIT) mbar_wait(&ready_lo[s2], ph2);
@@ -269,11 +364,11 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         const uint32_t off = k * kUmmaK * 4;
                         if (SPLIT) {
-                            umma_tf32(tacc, umma_desc_k_sw128(al + off), umma_desc_k_sw128(bh + off), idesc, (kc | k) != 0);
+                            umma_tf32(tacc, umma_desc_k_sw128(al + off), umma_desc_k_sw128(bh + off), idesc, kc != tc.k0 || k != 0);
                             umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bl + off), idesc, 1);
                             umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, 1);
                         } else {
-                            umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, (kc | k) != 0);
+                            umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, kc != tc.k0 || k != 0);
                         }
                     }
                     umma_commit(&empty_x[sx]);
@@ -302,8 +397,9 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             int kt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 float mean[8], rstd[8];
+                const TileCoord tc = tile_coord<BN>(p, tile, nk);
                 if (lnin) {
-                    const int m0 = (tile / p.n_tiles_n) * kBM;
+                    const int m0 = tc.m0;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int row = m0 + (t >> 3) + 16 * i;
@@ -312,7 +408,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         mean[i] = st.x, rstd[i] = st.y;
                     }
                 }
-                for (int kc = 0; kc < nk; ++kc, ++kt) {
+                for (int kc = tc.k0; kc < tc.k1; ++kc, ++kt) {
                     const int sx = kt % C::kRawSlots, s2 = kt & 1;
                     const uint32_t phx = (kt / C::kRawSlots) & 1, ph2 = (kt >> 1) & 1;
                     mbar_wait(&full_x[sx], phx);
@@ -360,7 +456,9 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         float v[32];
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int m0 = (tile / p.n_tiles_n) * kBM, n0 = (tile % p.n_tiles_n) * BN;
+            const TileCoord tc = tile_coord<BN>(p, tile, nk);
+            const int m0 = tc.m0, n0 = tc.n0;
+            float *const out_base = p.out ? p.out + tc.sp * p.split_stride : nullptr;   // split-K: this split's partial tile
             const int ab = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int row = m0 + rl;
@@ -473,7 +571,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     }
                     if (p.ln_out || p.stats_out) tmem_st32(taddr + c * 32, v);  // keep y for the LayerNorm passes
                     named_bar_sync(gbar, 128);                   // the 128 x 32 chunk of y is staged
-                    if (p.out) store_chunk(c, p.out, p.ldo);
+                    if (p.out) store_chunk(c, out_base, p.ldo);
                     named_bar_sync(gbar, 128);                   // staging buffer drained
                     if (has_res && c + G < nch) fetch_res(c + G);
                 }
@@ -535,20 +633,21 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
 }
 
-template <int BN, bool SPLIT, int ACT>
+template <int BN, bool SPLIT, int ACT, bool GATHER = false>
 int launch_act(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap &mapBlo, LinearParams &p,
                cudaStream_t stream)
 {
     using C = Cfg<BN, SPLIT>;
     static DeviceOnce once;
-    if (int rc = ensure_dynamic_smem(once, linear_kernel<BN, SPLIT, ACT>, C::kSmemBytes)) return rc;
+    if (int rc = ensure_dynamic_smem(once, linear_kernel<BN, SPLIT, ACT, GATHER>, C::kSmemBytes)) return rc;
     p.n_tiles_m = (p.M + kBM - 1) / kBM;
     p.n_tiles_n = (p.N + BN - 1) / BN;
     int device = 0;
     MAC_CUDA(cudaGetDevice(&device));
-    const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+    if (p.splits < 1) p.splits = 1, p.chunks_per_split = (p.K + kBK - 1) / kBK, p.split_stride = 0;
+    const int n_tiles = p.n_tiles_m * p.n_tiles_n * p.splits;
     const int grid = n_tiles < sm_count(device) ? n_tiles : sm_count(device);
-    linear_kernel<BN, SPLIT, ACT><<<grid, C::kThreads, C::kSmemBytes, stream>>>(mapA, mapBhi, mapBlo, p);
+    linear_kernel<BN, SPLIT, ACT, GATHER><<<grid, C::kThreads, C::kSmemBytes, stream>>>(mapA, mapBhi, mapBlo, p);
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return MAC_OK;
@@ -565,7 +664,120 @@ int launch(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap
     return launch_act<BN, SPLIT, MAC_LIN_NONE>(mapA, mapBhi, mapBlo, p, stream);
 }
 
+// convolution epilogues of the depth network: ReLU (encoder), ELU (decoder), sigmoid (disparity heads), none
+template <int BN>
+int launch_gather(const CUtensorMap &mapBhi, const CUtensorMap &mapBlo, LinearParams &p, cudaStream_t stream)
+{
+    if (p.act == MAC_LIN_RELU) return launch_act<BN, true, MAC_LIN_RELU, true>(mapBhi, mapBhi, mapBlo, p, stream);
+    if (p.act == MAC_LIN_ELU) return launch_act<BN, true, MAC_LIN_ELU, true>(mapBhi, mapBhi, mapBlo, p, stream);
+    if (p.act == MAC_LIN_SIGMOID) return launch_act<BN, true, MAC_LIN_SIGMOID, true>(mapBhi, mapBhi, mapBlo, p, stream);
+    return launch_act<BN, true, MAC_LIN_NONE, true>(mapBhi, mapBhi, mapBlo, p, stream);
+}
+
+// Second pass of a split-K layer: out = epilogue(sum over splits of the raw partial tiles), summed in split order
+// (deterministic).  One thread per 4 columns.
+template <int ACT>
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float *__restrict__ part, int splits, long long stride, int ldp,
+                                                            int M, int N, const float *__restrict__ bias,
+                                                            const float *__restrict__ res, int ldr, int res_first,
+                                                            float *__restrict__ out, int ldo)
+{
+    const int n4 = N / 4;
+    const long long total = static_cast<long long>(M) * n4;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const int row = static_cast<int>(i / n4), col = static_cast<int>(i - static_cast<long long>(row) * n4) * 4;
+        const float *src = part + static_cast<size_t>(row) * ldp + col;
+        float4 a = *reinterpret_cast<const float4 *>(src);
+        for (int sp = 1; sp < splits; ++sp) {
+            const float4 b = *reinterpret_cast<const float4 *>(src + sp * stride);
+            a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+        }
+        if (bias) {
+            const float4 b = *reinterpret_cast<const float4 *>(bias + col);
+            a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+        }
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (res) r = *reinterpret_cast<const float4 *>(res + static_cast<size_t>(row) * ldr + col);
+        const float pre = res_first ? 1.f : 0.f, post = 1.f - pre;
+        float4 y;
+        y.x = apply_act<ACT>(a.x + pre * r.x) + post * r.x;
+        y.y = apply_act<ACT>(a.y + pre * r.y) + post * r.y;
+        y.z = apply_act<ACT>(a.z + pre * r.z) + post * r.z;
+        y.w = apply_act<ACT>(a.w + pre * r.w) + post * r.w;
+        *reinterpret_cast<float4 *>(out + static_cast<size_t>(row) * ldo + col) = y;
+    }
+}
+
 }  // namespace
+
+bool conv_gather_supported(const ConvGather &g)
+{
+    const bool aligned = (reinterpret_cast<uintptr_t>(g.a) & 15u) == 0 && g.lda % 4 == 0 &&
+                         (!g.b || ((reinterpret_cast<uintptr_t>(g.b) & 15u) == 0 && g.ldb % 4 == 0));
+    if (!aligned || g.k < 1 || g.Ca <= 0) return false;
+    if (g.Ca % kBK == 0 && g.Cb % kBK == 0) return true;   // every k-chunk inside one tap of one source
+    return g.Cb == 0 && g.Ca == 16;                        // two taps per k-chunk
+}
+
+int linear_forward_conv(const ConvGather &g, const float *W_hi, const float *W_lo, int ldw, const float *bias, float *out,
+                        int ldo, int M, int N, int K, int act, const float *res, int ldr, cudaStream_t stream, int res_first,
+                        float *ws, size_t ws_floats)
+{
+    MAC_REQUIRE(g.a && W_hi && W_lo && out, "null tensor pointer");
+    MAC_REQUIRE(conv_gather_supported(g), "convolution not supported by the gather producer (Ca=%d Cb=%d)", g.Ca, g.Cb);
+    MAC_REQUIRE(K == g.k * g.k * (g.Ca + g.Cb), "K=%d does not match the convolution", K);
+    MAC_REQUIRE(M > 0 && N > 0 && act >= MAC_LIN_NONE && act <= MAC_LIN_SIGMOID && act != MAC_LIN_GELU, "bad shape or activation");
+    MAC_REQUIRE(ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0, "out must be 16-byte aligned with ldo %% 4 == 0");
+    MAC_REQUIRE(!res || (N % 4 == 0 && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(res) & 15u) == 0),
+                "the residual needs N %% 4 == 0 and a 16-byte aligned base and row stride");
+    const int bn = N <= 64 ? 64 : 128;
+    CUtensorMap mapBhi, mapBlo;
+    if (int rc = make_tensor_map_2d(&mapBhi, W_hi, N, K, ldw, bn)) return rc;
+    if (int rc = make_tensor_map_2d(&mapBlo, W_lo, N, K, ldw, bn)) return rc;
+    LinearParams p{};
+    p.M = M, p.N = N, p.K = K;
+    p.bias = bias;
+    p.out = out, p.ldo = ldo;
+    p.res = res, p.ldr = ldr;
+    p.act = act, p.res_first = res_first;
+    p.conv = g;
+
+    // Split-K for the low-resolution layers: a handful of 128-row tiles with thousands of k-chunks would stream the
+    // (large) weight matrix through 2-8 SMs; with the chunks divided over ~one CTA per SM every SM pulls its own weight columns.
+    int device = 0;
+    MAC_CUDA(cudaGetDevice(&device));
+    const int sms = sm_count(device);
+    const int tiles_mn = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
+    const int nk = (K + kBK - 1) / kBK;
+    static const int no_split = [] { const char *e = getenv("MAC_LINEAR_NO_SPLITK"); return e ? atoi(e) : 0; }();   // A/B timing knob
+    int want = sms / tiles_mn < nk / 4 ? sms / tiles_mn : nk / 4;
+    if (ws && !no_split && N % 4 == 0 && (reinterpret_cast<uintptr_t>(ws) & 15u) == 0 && want >= 2) {
+        const int cps = (nk + want - 1) / want;
+        const int splits = (nk + cps - 1) / cps;        // every split has at least one chunk
+        const size_t need = static_cast<size_t>(splits) * M * N;
+        if (splits >= 2 && need <= ws_floats) {
+            p.splits = splits, p.chunks_per_split = cps, p.split_stride = static_cast<long long>(M) * N;
+            p.out = ws, p.ldo = N;
+            p.bias = nullptr, p.res = nullptr, p.act = MAC_LIN_NONE;
+            if (int rc = bn == 64 ? launch_gather<64>(mapBhi, mapBlo, p, stream) : launch_gather<128>(mapBhi, mapBlo, p, stream))
+                return rc;
+            const long long total = static_cast<long long>(M) * (N / 4);
+            const int grid = static_cast<int>((total + 255) / 256 < 4 * sms ? (total + 255) / 256 : 4 * sms);
+#define MAC_FINISH(ACT)                                                                                                       \
+    splitk_finish_kernel<ACT><<<grid, 256, 0, stream>>>(ws, splits, p.split_stride, N, M, N, bias, res, ldr, res_first, out, ldo)
+            if (act == MAC_LIN_RELU) MAC_FINISH(MAC_LIN_RELU);
+            else if (act == MAC_LIN_ELU) MAC_FINISH(MAC_LIN_ELU);
+            else if (act == MAC_LIN_SIGMOID) MAC_FINISH(MAC_LIN_SIGMOID);
+            else MAC_FINISH(MAC_LIN_NONE);
+#undef MAC_FINISH
+            MAC_CUDA(cudaGetLastError());
+            count_launch();
+            return MAC_OK;
+        }
+    }
+    if (bn == 64) return launch_gather<64>(mapBhi, mapBlo, p, stream);
+    return launch_gather<128>(mapBhi, mapBlo, p, stream);
+}
 
 int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias, float *out,
                    int ldo, int M, int N, int K, int act, const float *res, int ldr, float *ln_out, int ldl,

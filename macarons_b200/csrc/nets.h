@@ -6,6 +6,23 @@
 
 namespace mac {
 
+// Implicit-GEMM A operand of a convolution (linear.cu, depth.cu): row m of the (M, K) matrix is output pixel m of an
+// NHWC convolution, K = k*k*(Ca + Cb) ordered (ky, kx, channel).  Source A (n, Ha, Wa, Ca) is nearest-neighbour
+// up-sampled to the (H, W) input grid when its size differs; source B (n, H, W, Cb), if any, is concatenated behind A's
+// channels.  Zero or reflect padding.
+struct ConvGather {
+    const float *a, *b;
+    int lda, ldb, Ca, Cb, Ha, Wa;
+    int H, W, Ho, Wo, k, stride, pad, reflect;
+    float scale_h, scale_w;   // Ha / H, Wa / W (torch nearest: src = min(floor(dst * scale), size - 1))
+};
+// true if linear_forward_conv can gather this convolution (every 16-byte piece of a k-chunk lies in one tap of one source)
+bool conv_gather_supported(const ConvGather &g);
+// `ws` (optional, 16-byte aligned, ws_floats floats): scratch for the split-K partial tiles of layers with few output tiles
+int linear_forward_conv(const ConvGather &g, const float *W_hi, const float *W_lo, int ldw, const float *bias, float *out,
+                        int ldo, int M, int N, int K, int act, const float *res, int ldr, cudaStream_t stream, int res_first,
+                        float *ws = nullptr, size_t ws_floats = 0);
+
 int knn16(const float *x, const float *pc, int *idx, float *dist, int B, int Q, int N, cudaStream_t stream);
 // ragged batch of cells: queries [q_off[c], q_off[c+1]) against points [n_off[c], n_off[c+1]) of a concatenated cloud;
 // writes GLOBAL point rows (offsets on the device, n_cells + 1 ints each; max_q = largest query count of a cell)
