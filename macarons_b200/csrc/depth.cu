@@ -151,21 +151,31 @@ __device__ __forceinline__ void cubic_weights(float t, float (&w)[4])
     w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
+// A warp owns one feature pixel and a run of kCvDepthsPerWarp depth planes; its two half-warps work on alternate planes.
+// Within a half-warp lane l owns bicubic tap l (un-projection / projection of one full-resolution pixel; the 16 weighted
+// positions are summed with 4 xor-shuffles) and then channels 4l .. 4l+3 of the bilinear gather (one 128-bit load per
+// corner).  Everything that does not depend on the plane (cubic weights, tap pixel, NDC coordinates, target features) is
+// computed once per warp; the per-plane arithmetic is unchanged operation by operation.
+constexpr int kCvDepthsPerWarp = 24;
+
 __global__ void __launch_bounds__(256) cost_volume_kernel(const CostVolumeParams p)
 {
-    const int lane = threadIdx.x & 31;
-    const long long n_warps = static_cast<long long>(p.B) * p.n_depth * p.fh * p.fw;
+    const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
+    const int groups = (p.n_depth + kCvDepthsPerWarp - 1) / kCvDepthsPerWarp;
+    const unsigned n_warps = static_cast<unsigned>(p.B) * p.fh * p.fw * groups;
     const float s = 1.7320508075688772f;  // 1 / tan(fov / 2), fov = 60 degrees (FoVPerspectiveCameras default)
     const int m_full = min(p.W, p.H), m_feat = min(p.fw, p.fh);
-    for (long long wid = blockIdx.x * 8ll + (threadIdx.x >> 5); wid < n_warps; wid += gridDim.x * 8ll) {
-        // consecutive warps share the feature pixel neighbourhood: (b, y, x, d) with d fastest keeps the gathers in L1/L2
-        const int d = static_cast<int>(wid % p.n_depth);
-        long long r = wid / p.n_depth;
+    const int c4 = 4 * l16;
+    const bool has_c = c4 < p.C;
+    for (unsigned wid = blockIdx.x * 8u + (threadIdx.x >> 5); wid < n_warps; wid += gridDim.x * 8u) {
+        // consecutive warps share the feature pixel neighbourhood: (b, y, x, group) with the group fastest keeps the
+        // gathers in L1 / L2
+        const int grp = static_cast<int>(wid % groups);
+        unsigned r = wid / groups;
         const int fx = static_cast<int>(r % p.fw);
         r /= p.fw;
         const int fy = static_cast<int>(r % p.fh);
         const int b = static_cast<int>(r / p.fh);
-        const float depth = p.d_min + (p.d_max - p.d_min) * static_cast<float>(d) / static_cast<float>(p.n_depth - 1);
         const float *cam_t = p.cam + static_cast<size_t>(b) * (1 + p.n_alpha) * 13;
 
         // bicubic taps of the full-resolution grid that feed this feature pixel
@@ -174,63 +184,72 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const CostVolumeParams
         float wy[4], wx[4];
         cubic_weights(sy - static_cast<float>(iy), wy);
         cubic_weights(sx - static_cast<float>(ix), wx);
-        const int ty = (lane & 15) >> 2, tx = lane & 3;       // lanes 0-15 (and 16-31, duplicated) own one tap each
+        const int ty = l16 >> 2, tx = l16 & 3;       // each lane of a half-warp owns one tap
         const int py = min(max(iy - 1 + ty, 0), p.H - 1), px = min(max(ix - 1 + tx, 0), p.W - 1);
-        // un-project pixel (py, px) at this depth: NDC grid of ManyDepth.py:128-129, then view -> world
+        // pixel (py, px) on the NDC grid of ManyDepth.py:128-129
         const float ndc_x = static_cast<float>(p.W) / m_full - (static_cast<float>(px) / (m_full - 1)) * 2.f;
         const float ndc_y = static_cast<float>(p.H) / m_full - (static_cast<float>(py) / (m_full - 1)) * 2.f;
-        const float vx = ndc_x * depth / s - cam_t[9], vy = ndc_y * depth / s - cam_t[10], vz = depth - cam_t[11];
-        const float X = vx * cam_t[0] + vy * cam_t[1] + vz * cam_t[2];   // (X_view - T) R^T
-        const float Y = vx * cam_t[3] + vy * cam_t[4] + vz * cam_t[5];
-        const float Z = vx * cam_t[6] + vy * cam_t[7] + vz * cam_t[8];
         const float wtap = wy[ty] * wx[tx];
+        const size_t pix = (static_cast<size_t>(b) * p.fh + fy) * p.fw + fx;
+        float4 tgt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_c) tgt = *reinterpret_cast<const float4 *>(p.feat_t + pix * p.C + c4);
+        const float inv_a = 1.f / static_cast<float>(p.n_alpha);
 
-        float acc0 = 0.f, acc1 = 0.f;  // sum over source frames of the warped features, channels lane and lane + 32
-        for (int a = 0; a < p.n_alpha; ++a) {
-            const float *cs = cam_t + (1 + a) * 13;
-            // world -> source view -> NDC (w clamped away from 0 like transform_points(eps=1e-8)) -> grid_sample coords
-            const float qx = X * cs[0] + Y * cs[3] + Z * cs[6] + cs[9];
-            const float qy = X * cs[1] + Y * cs[4] + Z * cs[7] + cs[10];
-            float qw = X * cs[2] + Y * cs[5] + Z * cs[8] + cs[11];
-            const float sgn = qw < 0.f ? -1.f : 1.f;
-            qw = sgn * fmaxf(fabsf(qw), 1e-8f);
-            float gx = (-static_cast<float>(m_feat) / p.fw) * (s * qx / qw) * wtap;
-            float gy = (-static_cast<float>(m_feat) / p.fh) * (s * qy / qw) * wtap;
+        const int d_begin = grp * kCvDepthsPerWarp, d_end = min(p.n_depth, d_begin + kCvDepthsPerWarp);
+        for (int dd = d_begin; dd < d_end; dd += 2) {   // warp-uniform trip count (full-mask shuffles inside)
+            const bool active = dd + half < d_end;
+            const int d = active ? dd + half : dd;      // an odd run: the second half-warp repeats the last plane, result dropped
+            const float depth = p.d_min + (p.d_max - p.d_min) * static_cast<float>(d) / static_cast<float>(p.n_depth - 1);
+            // un-project the tap pixel at this depth, then view -> world: (X_view - T) R^T
+            const float vx = ndc_x * depth / s - cam_t[9], vy = ndc_y * depth / s - cam_t[10], vz = depth - cam_t[11];
+            const float X = vx * cam_t[0] + vy * cam_t[1] + vz * cam_t[2];
+            const float Y = vx * cam_t[3] + vy * cam_t[4] + vz * cam_t[5];
+            const float Z = vx * cam_t[6] + vy * cam_t[7] + vz * cam_t[8];
+
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);   // sum over source frames of the warped features
+            for (int a = 0; a < p.n_alpha; ++a) {
+                const float *cs = cam_t + (1 + a) * 13;
+                // world -> source view -> NDC (w clamped away from 0 like transform_points(eps=1e-8)) -> grid_sample coords
+                const float qx = X * cs[0] + Y * cs[3] + Z * cs[6] + cs[9];
+                const float qy = X * cs[1] + Y * cs[4] + Z * cs[7] + cs[10];
+                float qw = X * cs[2] + Y * cs[5] + Z * cs[8] + cs[11];
+                const float sgn = qw < 0.f ? -1.f : 1.f;
+                qw = sgn * fmaxf(fabsf(qw), 1e-8f);
+                float gx = (-static_cast<float>(m_feat) / p.fw) * (s * qx / qw) * wtap;
+                float gy = (-static_cast<float>(m_feat) / p.fh) * (s * qy / qw) * wtap;
 #pragma unroll
-            for (int o = 8; o >= 1; o >>= 1) {
-                gx += __shfl_xor_sync(0xffffffffu, gx, o);
-                gy += __shfl_xor_sync(0xffffffffu, gy, o);
-            }
-            // bilinear gather, zeros padding, align_corners = False
-            const float fxp = ((gx + 1.f) * p.fw - 1.f) * 0.5f, fyp = ((gy + 1.f) * p.fh - 1.f) * 0.5f;
-            const float x0f = floorf(fxp), y0f = floorf(fyp);
-            const float ax = fxp - x0f, ay = fyp - y0f;
-            const float *src = p.feat_s + (static_cast<size_t>(b) * p.n_alpha + a) * p.fh * p.fw * p.C;
-            float v0 = 0.f, v1 = 0.f;
-            // (coordinates far outside the image, inf or NaN contribute nothing, as in grid_sample)
-            if (fxp > -2.f && fxp < p.fw + 1.f && fyp > -2.f && fyp < p.fh + 1.f) {
-                const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f);
+                for (int o = 8; o >= 1; o >>= 1) {   // stays inside the half-warp
+                    gx += __shfl_xor_sync(0xffffffffu, gx, o);
+                    gy += __shfl_xor_sync(0xffffffffu, gy, o);
+                }
+                // bilinear gather, zeros padding, align_corners = False
+                const float fxp = ((gx + 1.f) * p.fw - 1.f) * 0.5f, fyp = ((gy + 1.f) * p.fh - 1.f) * 0.5f;
+                const float x0f = floorf(fxp), y0f = floorf(fyp);
+                const float ax = fxp - x0f, ay = fyp - y0f;
+                const float *src = p.feat_s + (static_cast<size_t>(b) * p.n_alpha + a) * p.fh * p.fw * p.C + c4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                // (coordinates far outside the image, inf or NaN contribute nothing, as in grid_sample)
+                if (has_c && fxp > -2.f && fxp < p.fw + 1.f && fyp > -2.f && fyp < p.fh + 1.f) {
+                    const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
-                    const float wgt = ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay);
-                    if (xx >= 0 && xx < p.fw && yy >= 0 && yy < p.fh) {
-                        const float *px_ = src + (static_cast<size_t>(yy) * p.fw + xx) * p.C;
-                        v0 = fmaf(wgt, px_[lane], v0);
-                        if (lane + 32 < p.C) v1 = fmaf(wgt, px_[lane + 32], v1);
+                    for (int t = 0; t < 4; ++t) {
+                        const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+                        const float wgt = ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay);
+                        if (xx >= 0 && xx < p.fw && yy >= 0 && yy < p.fh) {
+                            const float4 f = *reinterpret_cast<const float4 *>(src + (yy * p.fw + xx) * p.C);
+                            v.x = fmaf(wgt, f.x, v.x), v.y = fmaf(wgt, f.y, v.y), v.z = fmaf(wgt, f.z, v.z), v.w = fmaf(wgt, f.w, v.w);
+                        }
                     }
                 }
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
             }
-            acc0 += v0;
-            acc1 += v1;
-        }
-        const float inv_a = 1.f / static_cast<float>(p.n_alpha);
-        const float *tgt = p.feat_t + ((static_cast<size_t>(b) * p.fh + fy) * p.fw + fx) * p.C;
-        float cost = fabsf(acc0 * inv_a - tgt[lane]);
-        if (lane + 32 < p.C) cost += fabsf(acc1 * inv_a - tgt[lane + 32]);
+            float cost = 0.f;
+            if (has_c)
+                cost = (fabsf(acc.x * inv_a - tgt.x) + fabsf(acc.y * inv_a - tgt.y)) + (fabsf(acc.z * inv_a - tgt.z) + fabsf(acc.w * inv_a - tgt.w));
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
-        if (lane == 0) p.cv[((static_cast<size_t>(b) * p.fh + fy) * p.fw + fx) * p.n_depth + d] = cost / static_cast<float>(p.C);
+            for (int o = 8; o >= 1; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+            if (l16 == 0 && active) p.cv[pix * p.n_depth + d] = cost / static_cast<float>(p.C);
+        }
     }
 }
 
@@ -380,7 +399,9 @@ int forward_impl(Ctx &cx, const mac_manydepth_w_t *w, const float *x, const floa
         p.B = B, p.n_alpha = n_alpha, p.H = H, p.W = W, p.fh = fh, p.fw = fw, p.C = l1.C, p.n_depth = w->n_depth;
         p.d_min = w->d_min, p.d_max = w->d_max;
         p.scale_h = static_cast<float>(H) / static_cast<float>(fh), p.scale_w = static_cast<float>(W) / static_cast<float>(fw);
-        cost_volume_kernel<<<grid_for(static_cast<long long>(B) * w->n_depth * fh * fw, 8, 148 * 32), 256, 0, cx.st>>>(p);
+        const long long cv_warps = static_cast<long long>(B) * fh * fw * ((w->n_depth + kCvDepthsPerWarp - 1) / kCvDepthsPerWarp);
+        MAC_REQUIRE(l1.C % 4 == 0 && l1.C <= 64 && l1.ld == l1.C && cv_warps < (1ll << 31), "cost volume: unsupported feature layout");
+        cost_volume_kernel<<<grid_for(cv_warps, 8, 148 * 32), 256, 0, cx.st>>>(p);
         MAC_CUDA(cudaGetLastError());
         count_launch();
     }
