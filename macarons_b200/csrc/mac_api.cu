@@ -32,6 +32,7 @@ void set_error(const char *fmt, ...)
 }
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void uncount_launch(unsigned n) { g_launches.fetch_sub(n, std::memory_order_relaxed); }
 
 int sm_count(int device)
 {

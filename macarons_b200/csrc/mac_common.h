@@ -12,6 +12,7 @@ namespace mac {
 
 void set_error(const char *fmt, ...);
 void count_launch(unsigned n = 1);
+void uncount_launch(unsigned n);   // launches recorded into a CUDA graph are counted when the graph runs
 int sm_count(int device);
 // covgain.cu: accumulate one slice of the points of a single cloud (see mac_covgain_host)
 int covgain_accumulate(const float *pts, int pts_dim, const float *harmonics, const float *cams, float *out, int P, int C,
