@@ -23,6 +23,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra flags for debug builds, e.g. MAC_EXTRA_NVCC_FLAGS=-DMAC_LINEAR_PROFILE (then run with --force)
+NVCC_FLAGS += os.environ.get("MAC_EXTRA_NVCC_FLAGS", "").split()
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 

@@ -106,6 +106,12 @@ struct LinearParams {
     long long split_stride;
 };
 
+#ifdef MAC_LINEAR_PROFILE
+// debug build only (MAC_EXTRA_NVCC_FLAGS=-DMAC_LINEAR_PROFILE): cycles the UMMA-issuing thread spends waiting on each
+// barrier class, summed over CTAs: [0] accumulator free, [1] X (hi / lo) ready, [2] W ready, [3] whole role, [4] tiles
+__device__ unsigned long long g_linear_prof[8];
+#endif
+
 struct TileCoord {
     int m0, n0, k0, k1, sp;
 };
@@ -344,19 +350,25 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
             int kt = 0, it = 0;
+#ifdef MAC_LINEAR_PROFILE
+            long long w_acc = 0, w_x = 0, w_w = 0, t_role = clock64(), t_;
+#define MAC_PROF_WAIT(ACC, STMT) t_ = clock64(); STMT; ACC += clock64() - t_
+#else
+#define MAC_PROF_WAIT(ACC, STMT) STMT
+#endif
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const int ab = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
-                mbar_wait(&acc_empty[ab], aph ^ 1);
+                MAC_PROF_WAIT(w_acc, mbar_wait(&acc_empty[ab], aph ^ 1));
                 tc_fence_after_sync();
                 const uint32_t tacc = tmem_base + ab * BN;
                 const TileCoord tc = tile_coord<BN>(p, tile, nk);
                 for (int kc = tc.k0; kc < tc.k1; ++kc, ++kt) {
                     const int sx = kt % C::kRawSlots, s2 = kt & 1;
                     const uint32_t phx = (kt / C::kRawSlots) & 1, ph2 = (kt >> 1) & 1;
-                    if (SPLIT) mbar_wait(&ready_lo[s2], ph2);
-                    else mbar_wait(&full_x[sx], phx);
-                    mbar_wait(&full_w[s2], ph2);
+                    if (SPLIT) { MAC_PROF_WAIT(w_x, mbar_wait(&ready_lo[s2], ph2)); }
+                    else { MAC_PROF_WAIT(w_x, mbar_wait(&full_x[sx], phx)); }
+                    MAC_PROF_WAIT(w_w, mbar_wait(&full_w[s2], ph2));
                     tc_fence_after_sync();
                     const uint32_t ah = smem_u32(a_hi(sx)), bh = smem_u32(b_hi(s2));
                     const uint32_t al = smem_u32(a_lo(s2)), bl = smem_u32(b_lo(s2));
@@ -377,6 +389,14 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 }
                 umma_commit(&acc_full[ab]);
             }
+#ifdef MAC_LINEAR_PROFILE
+            atomicAdd(&g_linear_prof[0], static_cast<unsigned long long>(w_acc));
+            atomicAdd(&g_linear_prof[1], static_cast<unsigned long long>(w_x));
+            atomicAdd(&g_linear_prof[2], static_cast<unsigned long long>(w_w));
+            atomicAdd(&g_linear_prof[3], static_cast<unsigned long long>(clock64() - t_role));
+            atomicAdd(&g_linear_prof[4], static_cast<unsigned long long>(it));
+#endif
+#undef MAC_PROF_WAIT
         }
     } else if (warp >= 4 && warp < 8) {
         // ===== X split: x -> (tf32(x), tf32(x - tf32(x))), element-wise in shared memory =====
@@ -841,6 +861,18 @@ int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo
 }
 
 }  // namespace mac
+
+#ifdef MAC_LINEAR_PROFILE
+// debug build only: read and clear the wait counters of the UMMA thread (see g_linear_prof)
+extern "C" int mac_linear_profile_read(unsigned long long *out8)
+{
+    MAC_CUDA(cudaDeviceSynchronize());
+    MAC_CUDA(cudaMemcpyFromSymbol(out8, mac::g_linear_prof, sizeof(unsigned long long) * 8));
+    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    MAC_CUDA(cudaMemcpyToSymbol(mac::g_linear_prof, zero, sizeof(zero)));
+    return MAC_OK;
+}
+#endif
 
 extern "C" int mac_linear_f32(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias,
                               float *out, int ldo, int M, int N, int K, int act, const float *res, int ldr,

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) embed_first_kernel(const EmbedParams p)
         float v[IN];
         if (GATHER) {
             const long long bq = t >> 4;            // b*Q + q
-            const int b = static_cast<int>(bq / p.Q);
+            const int b = static_cast<int>(static_cast<unsigned>(bq) / static_cast<unsigned>(p.Q));   // bq < 2^32 (checked by the launcher): no 64-bit division
             const int n = p.idx[t];
             const float *pp = p.pc + (static_cast<size_t>(b) * p.N + n) * 3;
             const float *xx = p.x + bq * 3;
@@ -631,6 +631,7 @@ int embed_first(const float *in, int ld_in, int in_dim, const float *pc, const f
                 "embedding width %d does not fit the 128-column staging row (ldo=%d)", inner, ldo);
     const bool gather = idx != nullptr;
     MAC_REQUIRE(gather ? (pc && x && in_dim == 3) : (in != nullptr), "embedding input missing");
+    MAC_REQUIRE((T >> 4) < (1ll << 32), "too many tokens for one launch");
     EmbedParams p{};
     p.in = in, p.ld_in = ld_in, p.pc = pc, p.x = x, p.idx = idx, p.Q = Q, p.N = N;
     p.w = w, p.b = b, p.inner = inner, p.append = append, p.out = out, p.ldo = ldo, p.T = T;
