@@ -155,17 +155,27 @@ __device__ __forceinline__ float apply_act(float y)
 //   raw X ring   kRawSlots x 16 KB   TMA destination; the split rewrites each slot in place with tf32(x)
 //   lo  X ring   kLoSlots  x 16 KB   tf32(x - tf32(x)), produced by the split warps            [SPLIT only]
 //   W ring       kWSlots x (1 or 2) x BN x 128 B   W_hi (and W_lo) k-chunks
+//
+// A operand in tensor memory (kATmem: SPLIT layers with BN <= 192).  Per k-chunk the operands of the 12 UMMAs are read
+// 3 times: with A in shared memory that is 96 KB of operand reads on top of the 48 KB TMA writes and the 16 KB read +
+// 32 KB written by the split -- 192 KB per chunk against a shared-memory port of 128 B / clock = 1536 clocks, MORE than the
+// tensor pipe needs (~800): the layers were shared-memory-bandwidth bound (measured 7.5 k clocks per K = 128 tile, floor
+// 6.1 k).  The split warps now hold a row per thread and write tf32(x) / tf32(x - tf32(x)) to TENSOR memory with tcgen05.st
+// (2 x 64 columns behind the accumulators); the UMMAs read A from there ("ts" form) and only W from shared memory: 112 KB
+// per chunk, no lo ring (two more X slots in flight), and the raw X slot is recycled as soon as the split has read it.
 template <int BN, bool SPLIT>
 struct Cfg {
+    static constexpr bool kATmem = SPLIT && (2 * BN + 128 <= 512);
     static constexpr int kBTileBytes = BN * kBK * 4;
     static constexpr int kWSlotBytes = (SPLIT ? 2 : 1) * kBTileBytes;
-    static constexpr int kEpiBufs = (BN <= 128) ? 2 : 1;
+    static constexpr int kEpiGroups2 = BN <= 128 || (kATmem && BN <= 192);   // room for a second staging buffer (no lo ring)
+    static constexpr int kEpiBufs = kEpiGroups2 ? 2 : 1;
     static constexpr int kWSlots = 2;
-    static constexpr int kLoSlots = SPLIT ? 2 : 0;
+    static constexpr int kLoSlots = (SPLIT && !kATmem) ? 2 : 0;
     static constexpr int kLnInMaxK = 512;
     static constexpr int kVecBytes = 3 * BN * 4 + 2 * 128 * 4 +   // bias | gamma | beta of the tile's columns, LayerNorm partials
                                      (SPLIT ? 2 * kLnInMaxK * 4 : 0);   // gamma | beta (K) of the LayerNorm applied on load
-    static constexpr int kThreads = kBaseThreads + 128 * ((BN <= 128) ? 2 : 1);
+    static constexpr int kThreads = kBaseThreads + 128 * kEpiBufs;
     static constexpr int kBudget = 226 * 1024 - 1024 - 512 - kVecBytes - kEpiBufs * kEpiBufBytes - kWSlots * kWSlotBytes - kLoSlots * kATileBytes;
     static constexpr int kRawSlots = (kBudget / kATileBytes) < kMaxStages ? (kBudget / kATileBytes) : kMaxStages;
     static constexpr int kOperandBytes = kRawSlots * kATileBytes + kLoSlots * kATileBytes + kWSlots * kWSlotBytes;
@@ -219,7 +229,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         if (SPLIT) tma_prefetch_desc(&mapBlo);
         for (int s = 0; s < C::kRawSlots; ++s) {
             mbar_init(&full_x[s], GATHER ? 64 : 1);   // GATHER: one arrival per lane of the two gather warps
-            mbar_init(&empty_x[s], 1);
+            mbar_init(&empty_x[s], C::kATmem ? 128 : 1);   // A in TMEM: released by the 128 split threads, else by the UMMAs
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&ready_lo[s], 128);
@@ -233,7 +243,8 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         }
         fence_mbar_init();
     }
-    constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128u : (2 * BN <= 256 ? 256u : 512u);   // power of two >= 2 BN
+    constexpr int kTmemNeed = 2 * BN + (C::kATmem ? 128 : 0);   // two accumulators (+ two A slots of hi | lo, 32 columns each)
+    constexpr uint32_t kTmemCols = kTmemNeed <= 128 ? 128u : (kTmemNeed <= 256 ? 256u : 512u);   // power of two
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before_sync();
     __syncthreads();
@@ -372,10 +383,15 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     tc_fence_after_sync();
                     const uint32_t ah = smem_u32(a_hi(sx)), bh = smem_u32(b_hi(s2));
                     const uint32_t al = smem_u32(a_lo(s2)), bl = smem_u32(b_lo(s2));
+                    const uint32_t ta_hi = tmem_base + 2 * BN + s2 * 64, ta_lo = ta_hi + 32;   // A slot s2 in tensor memory
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         const uint32_t off = k * kUmmaK * 4;
-                        if (SPLIT) {
+                        if (C::kATmem) {
+                            umma_tf32_ts(tacc, ta_lo + k * kUmmaK, umma_desc_k_sw128(bh + off), idesc, kc != tc.k0 || k != 0);
+                            umma_tf32_ts(tacc, ta_hi + k * kUmmaK, umma_desc_k_sw128(bl + off), idesc, 1);
+                            umma_tf32_ts(tacc, ta_hi + k * kUmmaK, umma_desc_k_sw128(bh + off), idesc, 1);
+                        } else if (SPLIT) {
                             umma_tf32(tacc, umma_desc_k_sw128(al + off), umma_desc_k_sw128(bh + off), idesc, kc != tc.k0 || k != 0);
                             umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bl + off), idesc, 1);
                             umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, 1);
@@ -383,7 +399,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                             umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, kc != tc.k0 || k != 0);
                         }
                     }
-                    umma_commit(&empty_x[sx]);
+                    if (!C::kATmem) umma_commit(&empty_x[sx]);
                     umma_commit(&empty_w[s2]);
                     if (SPLIT) umma_commit(&empty_lo[s2]);
                 }
@@ -399,8 +415,70 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 #undef MAC_PROF_WAIT
         }
     } else if (warp >= 4 && warp < 8) {
-        // ===== X split: x -> (tf32(x), tf32(x - tf32(x))), element-wise in shared memory =====
-        if (SPLIT) {
+        // ===== X split: x -> (tf32(x), tf32(x - tf32(x))) =====
+        if (C::kATmem) {
+            // one row of the tile per thread (warp q of the four owns TMEM lanes 32 q .. 32 q + 31): 8 conflict-free LDS.128
+            // un-swizzle the row, the halves go to tensor memory, the raw slot is released at once
+            const int r = threadIdx.x - 128;   // 0..127 = tile row = TMEM lane
+            const uint32_t lane_addr = static_cast<uint32_t>(r & ~31) << 16;
+            const bool lnin = p.lnin_stats != nullptr;
+            float *kvec = svec + 3 * BN + 2 * 128;   // [2][kLnInMaxK]: gamma | beta over K
+            if (lnin) {
+                for (int c = r; c < C::kLnInMaxK; c += 128) {
+                    kvec[c] = c < p.K ? p.lnin_g[c] : 0.f;
+                    kvec[C::kLnInMaxK + c] = c < p.K ? p.lnin_b[c] : 0.f;
+                }
+                named_bar_sync(8, 128);   // the 4 split warps only (ids 1-3 belong to the epilogue groups)
+            }
+            int kt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord<BN>(p, tile, nk);
+                float mean = 0.f, rstd = 0.f;
+                if (lnin && tc.m0 + r < p.M) {
+                    const float2 st = __ldg(reinterpret_cast<const float2 *>(p.lnin_stats) + tc.m0 + r);
+                    mean = st.x, rstd = st.y;
+                }
+                for (int kc = tc.k0; kc < tc.k1; ++kc, ++kt) {
+                    const int sx = kt % C::kRawSlots, s2 = kt & 1;
+                    const uint32_t phx = (kt / C::kRawSlots) & 1, ph2 = (kt >> 1) & 1;
+                    mbar_wait(&full_x[sx], phx);
+                    float v[32], h[32];
+                    const uint8_t *row = a_hi(sx) + r * 128;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 x4 = *reinterpret_cast<const float4 *>(row + ((q ^ (r & 7)) << 4));
+                        v[4 * q] = x4.x, v[4 * q + 1] = x4.y, v[4 * q + 2] = x4.z, v[4 * q + 3] = x4.w;
+                    }
+                    if (lnin) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 g4 = *reinterpret_cast<const float4 *>(kvec + kc * kBK + 4 * q);
+                            const float4 b4 = *reinterpret_cast<const float4 *>(kvec + C::kLnInMaxK + kc * kBK + 4 * q);
+                            v[4 * q] = fmaf((v[4 * q] - mean) * rstd, g4.x, b4.x);
+                            v[4 * q + 1] = fmaf((v[4 * q + 1] - mean) * rstd, g4.y, b4.y);
+                            v[4 * q + 2] = fmaf((v[4 * q + 2] - mean) * rstd, g4.z, b4.z);
+                            v[4 * q + 3] = fmaf((v[4 * q + 3] - mean) * rstd, g4.w, b4.w);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        h[j] = tf32_hi(v[j]);
+                        v[j] = tf32_lo(v[j], h[j]);
+                    }
+                    mbar_wait(&empty_lo[s2], ph2 ^ 1);   // the UMMAs that read A slot s2 two chunks ago have completed
+                    tc_fence_after_sync();
+                    const uint32_t ta = tmem_base + 2 * BN + s2 * 64 + lane_addr;
+                    tmem_st32(ta, h);
+                    tmem_st32(ta + 32, v);
+                    // every value read from the raw slot has been consumed by the two stores above (volatile, in program
+                    // order), so the loads have completed: order them before the async-proxy refill and release the slot
+                    fence_proxy_async_smem();
+                    mbar_arrive(&empty_x[sx]);
+                    tc_fence_before_sync();
+                    mbar_arrive(&ready_lo[s2]);
+                }
+            }
+        } else if (SPLIT) {
             const int t = threadIdx.x - 128;  // 0..127
             // LayerNorm on load: thread t always owns the same 4 logical columns of a k-chunk (16-byte piece t & 7 of a
             // 128-byte row, un-swizzled with the row's low bits, which are those of t >> 3) and rows (t >> 3) + 16 i.
