@@ -77,7 +77,8 @@ constexpr int kATileBytes = kBM * kBK * 4;
 constexpr int kBaseThreads = 256;   // warp 0 X TMA, warp 1 MMA, warp 2 W TMA, warps 4-7 X split; then 4 warps per epilogue group
 constexpr int kMaxStages = 8;
 constexpr int kEpiLd = 36;          // epilogue staging row stride (floats): 32 columns + 4 pad, conflict-free float4 rows
-constexpr int kEpiBufBytes = kBM * kEpiLd * 4;
+constexpr int kEpiPadBytes = kBM * kEpiLd * 4;   // plain-store path: one padded 128 x 36 staging tile per epilogue group
+constexpr int kEpiTmaBytes = 2 * kBM * 128;      // TMA-store path: two swizzled 128 x 32 staging tiles per epilogue group
 constexpr int kEpiBar = 1;          // named barrier of the 128 epilogue threads
 
 struct LinearParams {
@@ -104,12 +105,13 @@ struct LinearParams {
     // fp32 partial tile to out + s * split_stride (bias / activation / residual are then applied by splitk_finish_kernel)
     int splits, chunks_per_split;
     long long split_stride;
+    int tma_out;               // 1: `out` leaves through TMA stores (mapOut) from swizzled, double-buffered staging tiles
 };
 
 #ifdef MAC_LINEAR_PROFILE
 // debug build only (MAC_EXTRA_NVCC_FLAGS=-DMAC_LINEAR_PROFILE): cycles the UMMA-issuing thread spends waiting on each
 // barrier class, summed over CTAs: [0] accumulator free, [1] X (hi / lo) ready, [2] W ready, [3] whole role, [4] tiles
-__device__ unsigned long long g_linear_prof[8];
+__device__ unsigned long long g_linear_prof[12];
 #endif
 
 struct TileCoord {
@@ -170,6 +172,8 @@ struct Cfg {
     static constexpr int kWSlotBytes = (SPLIT ? 2 : 1) * kBTileBytes;
     static constexpr int kEpiGroups2 = BN <= 128 || (kATmem && BN <= 192);   // room for a second staging buffer (no lo ring)
     static constexpr int kEpiBufs = kEpiGroups2 ? 2 : 1;
+    static constexpr bool kTmaOut = kATmem;   // (the kernels with the lo ring have no room for the second staging tile)
+    static constexpr int kEpiBufBytes = kTmaOut ? kEpiTmaBytes : kEpiPadBytes;
     static constexpr int kWSlots = 2;
     static constexpr int kLoSlots = (SPLIT && !kATmem) ? 2 : 0;
     static constexpr int kLnInMaxK = 512;
@@ -192,7 +196,7 @@ struct Cfg {
 template <int BN, bool SPLIT, int ACT, bool GATHER>
 __global__ void __launch_bounds__((Cfg<BN, SPLIT>::kThreads), 1)
 linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
-              const __grid_constant__ CUtensorMap mapBlo, const LinearParams p)
+              const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapOut, const LinearParams p)
 {
     using C = Cfg<BN, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
@@ -202,8 +206,8 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     uint8_t *lo_base = raw_base + C::kRawSlots * kATileBytes;
     uint8_t *w_base = lo_base + C::kLoSlots * kATileBytes;
     float *ebuf = reinterpret_cast<float *>(smem + C::kOperandBytes);
-    float *svec = ebuf + C::kEpiBufs * (kBM * kEpiLd);   // [3][BN]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kOperandBytes + C::kEpiBufs * kEpiBufBytes + C::kVecBytes);
+    float *svec = ebuf + C::kEpiBufs * (C::kEpiBufBytes / 4);   // [3][BN]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kOperandBytes + C::kEpiBufs * C::kEpiBufBytes + C::kVecBytes);
     uint64_t *full_x = bars;                      // [kRawSlots] X chunk landed
     uint64_t *empty_x = bars + kMaxStages;        // [kRawSlots] MMAs that read the raw slot have completed
     uint64_t *ready_lo = bars + 2 * kMaxStages;   // [2] split done: hi rewritten in the raw slot, lo written
@@ -549,11 +553,47 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int rl = q * 32 + lane;           // row of the tile owned by this thread
         const int gbar = kEpiBar + g;           // named barrier of this group
-        float *mybuf = ebuf + g * (kBM * kEpiLd);
+        float *mybuf = ebuf + g * (C::kEpiBufBytes / 4);
         float *red = svec + 3 * BN;             // [G][128] cross-group LayerNorm partials
         float v[32];
         int it = 0;
+        // TMA-store path: staging tile (cb & 1) of this group holds chunk number cb of the group's chunk sequence; the
+        // residual of the NEXT chunk is copied into the other tile while the current one is computed (res_inflight)
+        const bool tma_out = C::kTmaOut && p.tma_out != 0;
+        const bool fixed_cols = p.n_tiles_n == 1;   // the column vectors (bias, gamma, beta) are the same for every tile
+        uint8_t *const stage = reinterpret_cast<uint8_t *>(mybuf);
+        int cb = 0;
+        bool res_inflight = false;
+        // residual chunk c of the tile at (rm0, rn0) -> swizzled staging tile, 16-byte async copies, coalesced
+        auto fetch_res_sw = [&](int rm0, int rn0, int c, uint8_t *dst) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int piece = t + i * 128, r = piece >> 3, sg = piece & 7;
+                const int col = rn0 + c * 32 + sg * 4;
+                if (rm0 + r < p.M && col < p.N)
+                    cp_async16(dst + r * 128 + ((sg ^ (r & 7)) << 4), p.res + static_cast<size_t>(rm0 + r) * p.ldr + col);
+            }
+            cp_async_commit();
+        };
+        if (tma_out && p.res && blockIdx.x < n_tiles) {
+            const TileCoord t0 = tile_coord<BN>(p, blockIdx.x, nk);
+            if (g < (min(BN, p.N - t0.n0) + 31) / 32) {
+                fetch_res_sw(t0.m0, t0.n0, g, stage);
+                res_inflight = true;
+            }
+        }
+#ifdef MAC_LINEAR_PROFILE
+        // epilogue phases of group 0 (thread 0): [5] tile prologue (syncs + column vectors), [6] wait for the accumulator,
+        // [7] chunk loop (residual wait, TMEM load, math, staging, stores), [8] row statistics / LayerNorm passes
+        long long e_pro = 0, e_acc = 0, e_chunks = 0, e_stats = 0, e_t = 0;
+#define MAC_EPI_MARK(ACC) if (g == 0 && t == 0) { const long long now_ = clock64(); ACC += now_ - e_t; e_t = now_; }
+#else
+#define MAC_EPI_MARK(ACC)
+#endif
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+#ifdef MAC_LINEAR_PROFILE
+            if (g == 0 && t == 0) e_t = clock64();
+#endif
             const TileCoord tc = tile_coord<BN>(p, tile, nk);
             const int m0 = tc.m0, n0 = tc.n0;
             float *const out_base = p.out ? p.out + tc.sp * p.split_stride : nullptr;   // split-K: this split's partial tile
@@ -598,16 +638,20 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 
             // per-column vectors of this tile -> shared memory (broadcast float4 reads instead of one LDG per element)
             all_groups_sync();  // previous tile: staging buffers drained, vectors and partials no longer read
-            for (int c = t + g * 128; c < BN; c += 128 * G) {
-                const bool ok = c < ncols;
-                svec[c] = (ok && p.bias) ? p.bias[n0 + c] : 0.f;
-                svec[BN + c] = (ok && p.ln_out) ? p.ln_g[n0 + c] : 0.f;
-                svec[2 * BN + c] = (ok && p.ln_out) ? p.ln_b[n0 + c] : 0.f;
+            if (!fixed_cols || it == 0) {
+                for (int c = t + g * 128; c < BN; c += 128 * G) {
+                    const bool ok = c < ncols;
+                    svec[c] = (ok && p.bias) ? p.bias[n0 + c] : 0.f;
+                    svec[BN + c] = (ok && p.ln_out) ? p.ln_g[n0 + c] : 0.f;
+                    svec[2 * BN + c] = (ok && p.ln_out) ? p.ln_b[n0 + c] : 0.f;
+                }
             }
-            if (p.res && g < nch) fetch_res(g);   // overlaps with the main loop of this tile
-            all_groups_sync();
+            if (!tma_out && p.res && g < nch) fetch_res(g);   // overlaps with the main loop of this tile
+            if (!fixed_cols || it == 0) all_groups_sync();
+            MAC_EPI_MARK(e_pro);
             mbar_wait(&acc_full[ab], aph);
             tc_fence_after_sync();
+            MAC_EPI_MARK(e_acc);
             if (p.pool) {
                 // groups of 16 consecutive rows -> out[row/16, col] = max, out[row/16, N + col] = mean
                 const int grp = row >> 4, gl = lane & 15;
@@ -641,7 +685,56 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 const bool has_res = p.res != nullptr;
                 const float pre = p.res_first ? 1.f : 0.f, post = 1.f - pre;   // where the residual enters
                 float sum = 0.f;
-                for (int c = g; c < nch; c += G) {
+                for (int c = g; tma_out && c < nch; c += G, ++cb) {
+                    uint8_t *const sb = stage + (cb & 1) * (kBM * 128);
+                    tmem_ld32(taddr + c * 32, v);
+                    if (has_res && !res_inflight) fetch_res_sw(m0, n0, c, sb);   // (only after a tile this group had no chunk of)
+                    if (t == 0) bulk_wait_read_all();   // the store of the previous chunk has read the OTHER staging tile
+                    if (has_res) cp_async_wait_all();
+                    named_bar_sync(gbar, 128);          // residual chunk visible to the group; the other tile is free
+                    res_inflight = false;
+                    if (has_res) {                      // residual of the group's next chunk -> the other tile, while this one is computed
+                        int c2 = c + G, tile2 = tile;
+                        if (c2 >= nch) c2 = g, tile2 = tile + gridDim.x;
+                        if (tile2 < n_tiles) {
+                            const TileCoord t2 = tile_coord<BN>(p, tile2, nk);
+                            if (c2 < (min(BN, p.N - t2.n0) + 31) / 32) {
+                                fetch_res_sw(t2.m0, t2.n0, c2, stage + ((cb + 1) & 1) * (kBM * 128));
+                                res_inflight = true;
+                            }
+                        }
+                    }
+                    uint8_t *const rowp = sb + rl * 128;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 *const ptr = reinterpret_cast<float4 *>(rowp + (((j >> 2) ^ (rl & 7)) << 4));
+                        const float4 b4 = *reinterpret_cast<const float4 *>(svec + c * 32 + j);
+                        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (has_res) r4 = *ptr;
+                        float4 y4;
+                        y4.x = apply_act<ACT>(v[j] + b4.x + pre * r4.x) + post * r4.x;
+                        y4.y = apply_act<ACT>(v[j + 1] + b4.y + pre * r4.y) + post * r4.y;
+                        y4.z = apply_act<ACT>(v[j + 2] + b4.z + pre * r4.z) + post * r4.z;
+                        y4.w = apply_act<ACT>(v[j + 3] + b4.w + pre * r4.w) + post * r4.w;
+                        if (c * 32 + j + 3 >= ncols) {  // ragged right edge: columns >= N contribute nothing
+                            if (c * 32 + j >= ncols) y4.x = 0.f;
+                            if (c * 32 + j + 1 >= ncols) y4.y = 0.f;
+                            if (c * 32 + j + 2 >= ncols) y4.z = 0.f;
+                            y4.w = 0.f;
+                        }
+                        v[j] = y4.x, v[j + 1] = y4.y, v[j + 2] = y4.z, v[j + 3] = y4.w;
+                        sum += (y4.x + y4.y) + (y4.z + y4.w);
+                        *ptr = y4;
+                    }
+                    if (p.stats_out) tmem_st32(taddr + c * 32, v);   // keep y for the row statistics
+                    fence_proxy_async_smem();           // generic writes of the tile -> visible to the TMA engine
+                    named_bar_sync(gbar, 128);          // the 128 x 32 chunk of y is staged
+                    if (t == 0) {
+                        tma_store_2d(&mapOut, sb, n0 + c * 32, m0);   // rows >= M / columns >= N are dropped by the TMA unit
+                        bulk_commit_group();
+                    }
+                }
+                for (int c = g; !tma_out && c < nch; c += G) {
                     if (has_res) {
                         cp_async_wait_all();
                         named_bar_sync(gbar, 128);  // residual chunk c visible to the whole group
@@ -673,6 +766,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     named_bar_sync(gbar, 128);                   // staging buffer drained
                     if (has_res && c + G < nch) fetch_res(c + G);
                 }
+                MAC_EPI_MARK(e_chunks);
                 if (p.ln_out || p.stats_out) {
                     // LayerNorm over the N columns of this row (the tile spans all of N): mean, then centred variance;
                     // the groups hold disjoint column chunks and combine their partial sums through shared memory
@@ -719,9 +813,20 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     }
                 }
             }
+            MAC_EPI_MARK(e_stats);
             tc_fence_before_sync();
             mbar_arrive(&acc_empty[ab]);
         }
+        if (tma_out && t == 0) bulk_wait_read_all();   // the staging tiles must outlive the last stores' reads
+#ifdef MAC_LINEAR_PROFILE
+        if (g == 0 && t == 0) {
+            atomicAdd(&g_linear_prof[5], static_cast<unsigned long long>(e_pro));
+            atomicAdd(&g_linear_prof[6], static_cast<unsigned long long>(e_acc));
+            atomicAdd(&g_linear_prof[7], static_cast<unsigned long long>(e_chunks));
+            atomicAdd(&g_linear_prof[8], static_cast<unsigned long long>(e_stats));
+        }
+#endif
+#undef MAC_EPI_MARK
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -735,6 +840,16 @@ template <int BN, bool SPLIT, int ACT, bool GATHER = false>
 int launch_act(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtensorMap &mapBlo, LinearParams &p,
                cudaStream_t stream)
 {
+    // `out` through TMA stores whenever it is a plain (M, N) matrix written once: not pooled, not a split-K partial, no
+    // second (LayerNorm-ed) output
+    static const int no_tma_out = [] { const char *e = getenv("MAC_LINEAR_NO_TMA_STORE"); return e ? atoi(e) : 0; }();   // A/B knob
+    CUtensorMap mapOut = mapBhi;   // placeholder when unused
+    p.tma_out = 0;
+    if (Cfg<BN, SPLIT>::kTmaOut && !no_tma_out && p.out && !p.pool && !p.ln_out && p.splits <= 1 && p.ldo % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) {
+        if (int rc = make_tensor_map_2d(&mapOut, p.out, p.M, p.N, p.ldo, kBM)) return rc;
+        p.tma_out = 1;
+    }
     using C = Cfg<BN, SPLIT>;
     static DeviceOnce once;
     if (int rc = ensure_dynamic_smem(once, linear_kernel<BN, SPLIT, ACT, GATHER>, C::kSmemBytes)) return rc;
@@ -745,7 +860,7 @@ int launch_act(const CUtensorMap &mapA, const CUtensorMap &mapBhi, const CUtenso
     if (p.splits < 1) p.splits = 1, p.chunks_per_split = (p.K + kBK - 1) / kBK, p.split_stride = 0;
     const int n_tiles = p.n_tiles_m * p.n_tiles_n * p.splits;
     const int grid = n_tiles < sm_count(device) ? n_tiles : sm_count(device);
-    linear_kernel<BN, SPLIT, ACT, GATHER><<<grid, C::kThreads, C::kSmemBytes, stream>>>(mapA, mapBhi, mapBlo, p);
+    linear_kernel<BN, SPLIT, ACT, GATHER><<<grid, C::kThreads, C::kSmemBytes, stream>>>(mapA, mapBhi, mapBlo, mapOut, p);
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return MAC_OK;
@@ -942,11 +1057,11 @@ int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo
 
 #ifdef MAC_LINEAR_PROFILE
 // debug build only: read and clear the wait counters of the UMMA thread (see g_linear_prof)
-extern "C" int mac_linear_profile_read(unsigned long long *out8)
+extern "C" int mac_linear_profile_read(unsigned long long *out12)
 {
     MAC_CUDA(cudaDeviceSynchronize());
-    MAC_CUDA(cudaMemcpyFromSymbol(out8, mac::g_linear_prof, sizeof(unsigned long long) * 8));
-    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    MAC_CUDA(cudaMemcpyFromSymbol(out12, mac::g_linear_prof, sizeof(unsigned long long) * 12));
+    unsigned long long zero[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     MAC_CUDA(cudaMemcpyToSymbol(mac::g_linear_prof, zero, sizeof(zero)));
     return MAC_OK;
 }

@@ -24,6 +24,16 @@ __device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *tensor_m
         "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// TMA tiled store of one box shared -> global (bulk async-group completion); rows / columns outside the tensor are dropped
+__device__ __forceinline__ void tma_store_2d(const void *tensor_map, const void *src_smem, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tensor_map), "r"(c0), "r"(c1),
+                 "r"(smem_u32(src_smem))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores committed by this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const void *tensor_map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tensor_map) : "memory");

@@ -26,7 +26,7 @@ def layer(K, N):
 def run(name, fn, nbytes):
     for _ in range(2):
         fn()
-    buf = (ctypes.c_ulonglong * 8)()
+    buf = (ctypes.c_ulonglong * 12)()
     if prof is not None:
         prof(buf)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -41,7 +41,9 @@ def run(name, fn, nbytes):
         prof(buf)
         tot = max(1, buf[3])
         rec.update({"wait_acc": round(buf[0] / tot, 3), "wait_x": round(buf[1] / tot, 3), "wait_w": round(buf[2] / tot, 3),
-                    "cycles_per_tile": round(buf[3] / max(1, buf[4]))})
+                    "cycles_per_tile": round(buf[3] / max(1, buf[4])),
+                    "epi_cycles_per_tile": {k: round(buf[i] / max(1, buf[4])) for k, i in
+                                            (("prologue", 5), ("wait_acc", 6), ("chunks", 7), ("stats", 8))}})
     print(json.dumps(rec))
 
 
