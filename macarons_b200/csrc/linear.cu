@@ -167,13 +167,18 @@ __device__ __forceinline__ float apply_act(float y)
 // per chunk, no lo ring (two more X slots in flight), and the raw X slot is recycled as soon as the split has read it.
 template <int BN, bool SPLIT>
 struct Cfg {
-    static constexpr bool kATmem = SPLIT && (2 * BN + 128 <= 512);
+    static constexpr bool kATmem = SPLIT;
+    // 512 TMEM columns: two accumulators + the A slots up to BN = 192; at BN = 256 ONE accumulator (the UMMAs of tile t+1 then
+    // wait for the epilogue of tile t; with A in shared memory and one epilogue group that tile shape ran at 1.5 TB/s)
+    static constexpr int kAccBufs = (!kATmem || 2 * BN + 128 <= 512) ? 2 : 1;
+    static constexpr int kStageTiles = BN <= 192 ? 2 : 1;   // staging tiles per epilogue group (TMA-store path)
     static constexpr int kBTileBytes = BN * kBK * 4;
     static constexpr int kWSlotBytes = (SPLIT ? 2 : 1) * kBTileBytes;
-    static constexpr int kEpiGroups2 = BN <= 128 || (kATmem && BN <= 192);   // room for a second staging buffer (no lo ring)
+    static constexpr int kEpiGroups2 = BN <= 128 || kATmem;   // room for a second epilogue group (no lo ring)
     static constexpr int kEpiBufs = kEpiGroups2 ? 2 : 1;
     static constexpr bool kTmaOut = kATmem;   // (the kernels with the lo ring have no room for the second staging tile)
-    static constexpr int kEpiBufBytes = kTmaOut ? kEpiTmaBytes : kEpiPadBytes;
+    // (the plain-store path of the same kernel -- LayerNorm-ed second output, pooling, split-K partials -- needs the padded tile)
+    static constexpr int kEpiBufBytes = (kTmaOut && kStageTiles * kBM * 128 > kEpiPadBytes) ? kStageTiles * kBM * 128 : kEpiPadBytes;
     static constexpr int kWSlots = 2;
     static constexpr int kLoSlots = (SPLIT && !kATmem) ? 2 : 0;
     static constexpr int kLnInMaxK = 512;
@@ -247,7 +252,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         }
         fence_mbar_init();
     }
-    constexpr int kTmemNeed = 2 * BN + (C::kATmem ? 128 : 0);   // two accumulators (+ two A slots of hi | lo, 32 columns each)
+    constexpr int kTmemNeed = C::kAccBufs * BN + (C::kATmem ? 128 : 0);   // accumulators (+ two A slots of hi | lo, 32 columns each)
     constexpr uint32_t kTmemCols = kTmemNeed <= 128 ? 128u : (kTmemNeed <= 256 ? 256u : 512u);   // power of two
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before_sync();
@@ -372,8 +377,8 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 #define MAC_PROF_WAIT(ACC, STMT) STMT
 #endif
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int ab = it & 1;
-                const uint32_t aph = (it >> 1) & 1;
+                const int ab = C::kAccBufs == 2 ? (it & 1) : 0;
+                const uint32_t aph = C::kAccBufs == 2 ? ((it >> 1) & 1) : (it & 1);
                 MAC_PROF_WAIT(w_acc, mbar_wait(&acc_empty[ab], aph ^ 1));
                 tc_fence_after_sync();
                 const uint32_t tacc = tmem_base + ab * BN;
@@ -387,7 +392,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     tc_fence_after_sync();
                     const uint32_t ah = smem_u32(a_hi(sx)), bh = smem_u32(b_hi(s2));
                     const uint32_t al = smem_u32(a_lo(s2)), bl = smem_u32(b_lo(s2));
-                    const uint32_t ta_hi = tmem_base + 2 * BN + s2 * 64, ta_lo = ta_hi + 32;   // A slot s2 in tensor memory
+                    const uint32_t ta_hi = tmem_base + C::kAccBufs * BN + s2 * 64, ta_lo = ta_hi + 32;   // A slot s2 in tensor memory
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         const uint32_t off = k * kUmmaK * 4;
@@ -471,7 +476,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     }
                     mbar_wait(&empty_lo[s2], ph2 ^ 1);   // the UMMAs that read A slot s2 two chunks ago have completed
                     tc_fence_after_sync();
-                    const uint32_t ta = tmem_base + 2 * BN + s2 * 64 + lane_addr;
+                    const uint32_t ta = tmem_base + C::kAccBufs * BN + s2 * 64 + lane_addr;
                     tmem_st32(ta, h);
                     tmem_st32(ta + 32, v);
                     // every value read from the raw slot has been consumed by the two stores above (volatile, in program
@@ -597,8 +602,8 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const TileCoord tc = tile_coord<BN>(p, tile, nk);
             const int m0 = tc.m0, n0 = tc.n0;
             float *const out_base = p.out ? p.out + tc.sp * p.split_stride : nullptr;   // split-K: this split's partial tile
-            const int ab = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
+            const int ab = C::kAccBufs == 2 ? (it & 1) : 0;
+            const uint32_t aph = C::kAccBufs == 2 ? ((it >> 1) & 1) : (it & 1);
             const int row = m0 + rl;
             const bool row_ok = row < p.M;
             const int ncols = min(BN, p.N - n0);          // valid columns of this tile
@@ -686,14 +691,17 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 const float pre = p.res_first ? 1.f : 0.f, post = 1.f - pre;   // where the residual enters
                 float sum = 0.f;
                 for (int c = g; tma_out && c < nch; c += G, ++cb) {
-                    uint8_t *const sb = stage + (cb & 1) * (kBM * 128);
+                    uint8_t *const sb = stage + (cb % C::kStageTiles) * (kBM * 128);
                     tmem_ld32(taddr + c * 32, v);
-                    if (has_res && !res_inflight) fetch_res_sw(m0, n0, c, sb);   // (only after a tile this group had no chunk of)
-                    if (t == 0) bulk_wait_read_all();   // the store of the previous chunk has read the OTHER staging tile
+                    if (t == 0) bulk_wait_read_all();   // the store of the previous chunk has read its staging tile
+                    if (has_res && !res_inflight) {     // one staging tile, or after a tile this group had no chunk of
+                        if (C::kStageTiles == 1) named_bar_sync(gbar, 128);   // the tile is this chunk's own: wait for its last store
+                        fetch_res_sw(m0, n0, c, sb);
+                    }
                     if (has_res) cp_async_wait_all();
                     named_bar_sync(gbar, 128);          // residual chunk visible to the group; the other tile is free
                     res_inflight = false;
-                    if (has_res) {                      // residual of the group's next chunk -> the other tile, while this one is computed
+                    if (has_res && C::kStageTiles == 2) {   // residual of the group's next chunk -> the other tile, while this one is computed
                         int c2 = c + G, tile2 = tile;
                         if (c2 >= nch) c2 = g, tile2 = tile + gridDim.x;
                         if (tile2 < n_tiles) {

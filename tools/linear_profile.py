@@ -57,4 +57,7 @@ run("qkv   K128 N192 ln-on-load", lambda: ops.linear_lnio(x128, l_qkv, ln_in=(st
 run("out   K128 N128 +res +stats", lambda: ops.linear_lnio(x128, l_out, residual=res, stats_out=True), M * (128 * 3) * 4)
 run("ff1   K128 N256 gelu ln-on-load", lambda: ops.linear_lnio(x128, l_ff1, act=ops.ACT_GELU, ln_in=(stats, gam, bet)), M * (128 + 256) * 4)
 run("ff2   K256 N128 +res +stats", lambda: ops.linear_lnio(x256, l_ff2, residual=res, stats_out=True), M * (256 + 256) * 4)
+l_d256 = layer(256, 256)
+res256 = torch.randn(M // 4, 256, generator=g).to(dev)
+run("d256  K256 N256 +res +stats (M/4)", lambda: ops.linear_lnio(x256[:M // 4], l_d256, residual=res256, stats_out=True), (M // 4) * (256 * 3) * 4)
 run("plain K128 N128", lambda: ops.linear(x128, l_out), M * 256 * 4)
