@@ -105,6 +105,7 @@ struct LinearParams {
     // fp32 partial tile to out + s * split_stride (bias / activation / residual are then applied by splitk_finish_kernel)
     int splits, chunks_per_split;
     long long split_stride;
+    int act_in;                // MAC_LIN_GELU: the exact GELU is applied to X on load (by the split warps), else MAC_LIN_NONE
     int tma_out;               // 1: `out` leaves through TMA stores (mapOut) from swizzled, double-buffered staging tiles
 };
 
@@ -152,19 +153,19 @@ __device__ __forceinline__ float apply_act(float y)
     return y;
 }
 
-// Shared-memory plan.  Three independent rings so that the number of X bytes in flight from HBM is not tied to the
-// (large, L2-resident) weight tiles:
-//   raw X ring   kRawSlots x 16 KB   TMA destination; the split rewrites each slot in place with tf32(x)
-//   lo  X ring   kLoSlots  x 16 KB   tf32(x - tf32(x)), produced by the split warps            [SPLIT only]
+// Shared-memory plan.  Independent rings so that the number of X bytes in flight from HBM is not tied to the (large,
+// L2-resident) weight tiles:
+//   raw X ring   kRawSlots x 16 KB   TMA / gather destination, read once by the split warps (SPLIT) or by the UMMAs
 //   W ring       kWSlots x (1 or 2) x BN x 128 B   W_hi (and W_lo) k-chunks
+//   staging      per epilogue group: two (one at BN = 256) swizzled 128 x 32 tiles for the TMA stores
 //
-// A operand in tensor memory (kATmem: SPLIT layers with BN <= 192).  Per k-chunk the operands of the 12 UMMAs are read
-// 3 times: with A in shared memory that is 96 KB of operand reads on top of the 48 KB TMA writes and the 16 KB read +
+// A operand in tensor memory (kATmem = every SPLIT layer).  Per k-chunk the operands of the 12 UMMAs are read 3 times: with
+// A in shared memory (first version) that was 96 KB of operand reads on top of the 48 KB TMA writes and the 16 KB read +
 // 32 KB written by the split -- 192 KB per chunk against a shared-memory port of 128 B / clock = 1536 clocks, MORE than the
-// tensor pipe needs (~800): the layers were shared-memory-bandwidth bound (measured 7.5 k clocks per K = 128 tile, floor
-// 6.1 k).  The split warps now hold a row per thread and write tf32(x) / tf32(x - tf32(x)) to TENSOR memory with tcgen05.st
-// (2 x 64 columns behind the accumulators); the UMMAs read A from there ("ts" form) and only W from shared memory: 112 KB
-// per chunk, no lo ring (two more X slots in flight), and the raw X slot is recycled as soon as the split has read it.
+// tensor pipe needs: the layers were shared-memory-bandwidth bound (measured 7.5 k clocks per K = 128 tile, floor 6.1 k).
+// The split warps hold a row per thread and write tf32(x) / tf32(x - tf32(x)) to TENSOR memory with tcgen05.st (2 x 64
+// columns behind the accumulators); the UMMAs read A from there ("ts" form) and only W from shared memory: 112 KB per
+// chunk, no lo ring, and the raw X slot is recycled as soon as the split has read it.
 template <int BN, bool SPLIT>
 struct Cfg {
     static constexpr bool kATmem = SPLIT;
@@ -180,14 +181,13 @@ struct Cfg {
     // (the plain-store path of the same kernel -- LayerNorm-ed second output, pooling, split-K partials -- needs the padded tile)
     static constexpr int kEpiBufBytes = (kTmaOut && kStageTiles * kBM * 128 > kEpiPadBytes) ? kStageTiles * kBM * 128 : kEpiPadBytes;
     static constexpr int kWSlots = 2;
-    static constexpr int kLoSlots = (SPLIT && !kATmem) ? 2 : 0;
     static constexpr int kLnInMaxK = 512;
     static constexpr int kVecBytes = 3 * BN * 4 + 2 * 128 * 4 +   // bias | gamma | beta of the tile's columns, LayerNorm partials
                                      (SPLIT ? 2 * kLnInMaxK * 4 : 0);   // gamma | beta (K) of the LayerNorm applied on load
     static constexpr int kThreads = kBaseThreads + 128 * kEpiBufs;
-    static constexpr int kBudget = 226 * 1024 - 1024 - 512 - kVecBytes - kEpiBufs * kEpiBufBytes - kWSlots * kWSlotBytes - kLoSlots * kATileBytes;
+    static constexpr int kBudget = 226 * 1024 - 1024 - 512 - kVecBytes - kEpiBufs * kEpiBufBytes - kWSlots * kWSlotBytes;
     static constexpr int kRawSlots = (kBudget / kATileBytes) < kMaxStages ? (kBudget / kATileBytes) : kMaxStages;
-    static constexpr int kOperandBytes = kRawSlots * kATileBytes + kLoSlots * kATileBytes + kWSlots * kWSlotBytes;
+    static constexpr int kOperandBytes = kRawSlots * kATileBytes + kWSlots * kWSlotBytes;
     static constexpr int kSmemBytes = kOperandBytes + kEpiBufs * kEpiBufBytes + kVecBytes + 1024 /*alignment*/ + 512 /*barriers*/;
     static constexpr uint32_t kWTxBytes = kWSlotBytes;
     static_assert(kRawSlots >= 2, "need at least a double-buffered X pipeline");
@@ -208,15 +208,14 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t *raw_base = smem;
-    uint8_t *lo_base = raw_base + C::kRawSlots * kATileBytes;
-    uint8_t *w_base = lo_base + C::kLoSlots * kATileBytes;
+    uint8_t *w_base = raw_base + C::kRawSlots * kATileBytes;
     float *ebuf = reinterpret_cast<float *>(smem + C::kOperandBytes);
     float *svec = ebuf + C::kEpiBufs * (C::kEpiBufBytes / 4);   // [3][BN]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kOperandBytes + C::kEpiBufs * C::kEpiBufBytes + C::kVecBytes);
     uint64_t *full_x = bars;                      // [kRawSlots] X chunk landed
     uint64_t *empty_x = bars + kMaxStages;        // [kRawSlots] MMAs that read the raw slot have completed
-    uint64_t *ready_lo = bars + 2 * kMaxStages;   // [2] split done: hi rewritten in the raw slot, lo written
-    uint64_t *empty_lo = ready_lo + 2;            // [2] MMAs that read the lo slot have completed
+    uint64_t *ready_lo = bars + 2 * kMaxStages;   // [2] split done: tf32 hi / lo of the chunk written to A slot s of tensor memory
+    uint64_t *empty_lo = ready_lo + 2;            // [2] UMMAs that read A slot s have completed
     uint64_t *full_w = empty_lo + 2;              // [2] W chunk landed
     uint64_t *empty_w = full_w + 2;               // [2]
     uint64_t *acc_full = empty_w + 2;             // [2] accumulator complete
@@ -224,7 +223,6 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     auto a_hi = [&](int s) { return raw_base + s * kATileBytes; };
-    auto a_lo = [&](int s) { return lo_base + s * kATileBytes; };
     auto b_hi = [&](int s) { return w_base + s * C::kWSlotBytes; };
     auto b_lo = [&](int s) { return w_base + s * C::kWSlotBytes + C::kBTileBytes; };
 
@@ -391,7 +389,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     MAC_PROF_WAIT(w_w, mbar_wait(&full_w[s2], ph2));
                     tc_fence_after_sync();
                     const uint32_t ah = smem_u32(a_hi(sx)), bh = smem_u32(b_hi(s2));
-                    const uint32_t al = smem_u32(a_lo(s2)), bl = smem_u32(b_lo(s2));
+                    const uint32_t bl = smem_u32(b_lo(s2));
                     const uint32_t ta_hi = tmem_base + C::kAccBufs * BN + s2 * 64, ta_lo = ta_hi + 32;   // A slot s2 in tensor memory
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
@@ -400,10 +398,6 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                             umma_tf32_ts(tacc, ta_lo + k * kUmmaK, umma_desc_k_sw128(bh + off), idesc, kc != tc.k0 || k != 0);
                             umma_tf32_ts(tacc, ta_hi + k * kUmmaK, umma_desc_k_sw128(bl + off), idesc, 1);
                             umma_tf32_ts(tacc, ta_hi + k * kUmmaK, umma_desc_k_sw128(bh + off), idesc, 1);
-                        } else if (SPLIT) {
-                            umma_tf32(tacc, umma_desc_k_sw128(al + off), umma_desc_k_sw128(bh + off), idesc, kc != tc.k0 || k != 0);
-                            umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bl + off), idesc, 1);
-                            umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, 1);
                         } else {
                             umma_tf32(tacc, umma_desc_k_sw128(ah + off), umma_desc_k_sw128(bh + off), idesc, kc != tc.k0 || k != 0);
                         }
@@ -469,6 +463,10 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                             v[4 * q + 3] = fmaf((v[4 * q + 3] - mean) * rstd, g4.w, b4.w);
                         }
                     }
+                    if (p.act_in == MAC_LIN_GELU) {   // the producer layer stored its pre-activation (its epilogue was GELU-bound)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_exact(v[j]);
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         h[j] = tf32_hi(v[j]);
@@ -484,65 +482,6 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     fence_proxy_async_smem();
                     mbar_arrive(&empty_x[sx]);
                     tc_fence_before_sync();
-                    mbar_arrive(&ready_lo[s2]);
-                }
-            }
-        } else if (SPLIT) {
-            const int t = threadIdx.x - 128;  // 0..127
-            // LayerNorm on load: thread t always owns the same 4 logical columns of a k-chunk (16-byte piece t & 7 of a
-            // 128-byte row, un-swizzled with the row's low bits, which are those of t >> 3) and rows (t >> 3) + 16 i.
-            const bool lnin = p.lnin_stats != nullptr;
-            float *kvec = svec + 3 * BN + 2 * 128;   // [2][kLnInMaxK]: gamma | beta over K
-            const int col4 = (((t & 7) ^ ((t >> 3) & 7)) << 2);
-            if (lnin) {
-                for (int c = t; c < C::kLnInMaxK; c += 128) {
-                    kvec[c] = c < p.K ? p.lnin_g[c] : 0.f;
-                    kvec[C::kLnInMaxK + c] = c < p.K ? p.lnin_b[c] : 0.f;
-                }
-                named_bar_sync(8, 128);   // the 4 split warps only (ids 1-3 belong to the epilogue groups)
-            }
-            int kt = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                float mean[8], rstd[8];
-                const TileCoord tc = tile_coord<BN>(p, tile, nk);
-                if (lnin) {
-                    const int m0 = tc.m0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = m0 + (t >> 3) + 16 * i;
-                        float2 st = make_float2(0.f, 0.f);
-                        if (row < p.M) st = __ldg(reinterpret_cast<const float2 *>(p.lnin_stats) + row);
-                        mean[i] = st.x, rstd[i] = st.y;
-                    }
-                }
-                for (int kc = tc.k0; kc < tc.k1; ++kc, ++kt) {
-                    const int sx = kt % C::kRawSlots, s2 = kt & 1;
-                    const uint32_t phx = (kt / C::kRawSlots) & 1, ph2 = (kt >> 1) & 1;
-                    mbar_wait(&full_x[sx], phx);
-                    mbar_wait(&empty_lo[s2], ph2 ^ 1);
-                    float4 *hi = reinterpret_cast<float4 *>(a_hi(sx));
-                    float4 *lo = reinterpret_cast<float4 *>(a_lo(s2));
-                    float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (lnin) {
-                        g4 = *reinterpret_cast<const float4 *>(kvec + kc * kBK + col4);
-                        b4 = *reinterpret_cast<const float4 *>(kvec + C::kLnInMaxK + kc * kBK + col4);
-                    }
-#pragma unroll
-                    for (int i = 0; i < kATileBytes / 16 / 128; ++i) {
-                        float4 v = hi[t + i * 128];
-                        if (lnin) {
-                            v.x = fmaf((v.x - mean[i]) * rstd[i], g4.x, b4.x);
-                            v.y = fmaf((v.y - mean[i]) * rstd[i], g4.y, b4.y);
-                            v.z = fmaf((v.z - mean[i]) * rstd[i], g4.z, b4.z);
-                            v.w = fmaf((v.w - mean[i]) * rstd[i], g4.w, b4.w);
-                        }
-                        float4 h, l;
-                        h.x = tf32_hi(v.x), h.y = tf32_hi(v.y), h.z = tf32_hi(v.z), h.w = tf32_hi(v.w);
-                        l.x = tf32_lo(v.x, h.x), l.y = tf32_lo(v.y, h.y), l.z = tf32_lo(v.z, h.z), l.w = tf32_lo(v.w, h.w);
-                        hi[t + i * 128] = h;
-                        lo[t + i * 128] = l;
-                    }
-                    fence_proxy_async_smem();
                     mbar_arrive(&ready_lo[s2]);
                 }
             }
@@ -1003,9 +942,11 @@ int linear_forward_conv(const ConvGather &g, const float *W_hi, const float *W_l
 int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo, int ldw, const float *bias, float *out,
                    int ldo, int M, int N, int K, int act, const float *res, int ldr, float *ln_out, int ldl,
                    const float *ln_g, const float *ln_b, float ln_eps, int pool, cudaStream_t stream, int res_first,
-                   const float *lnin_stats, const float *lnin_g, const float *lnin_b, float *stats_out)
+                   const float *lnin_stats, const float *lnin_g, const float *lnin_b, float *stats_out, int act_in)
 {
     MAC_REQUIRE(X && W_hi && (out || ln_out), "null tensor pointer");
+    MAC_REQUIRE(act_in == MAC_LIN_NONE || (act_in == MAC_LIN_GELU && W_lo && !lnin_stats),
+                "an activation on load needs split weights and no LayerNorm on load");
     MAC_REQUIRE(!lnin_stats || (W_lo && lnin_g && lnin_b && K <= 512 && K % 4 == 0 &&
                                 (reinterpret_cast<uintptr_t>(lnin_stats) & 7u) == 0),
                 "LayerNorm on load needs split weights, gamma / beta and K <= 512");
@@ -1047,6 +988,7 @@ int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo
     p.ln_out = ln_out, p.ldl = ldl, p.ln_g = ln_g, p.ln_b = ln_b, p.ln_eps = ln_eps;
     p.act = act, p.pool = pool, p.res_first = res_first;
     p.lnin_stats = lnin_stats, p.lnin_g = lnin_g, p.lnin_b = lnin_b, p.stats_out = stats_out;
+    p.act_in = act_in;
     if (stats_out && !ln_out) p.ln_eps = ln_eps;
 
     if (split) {

@@ -33,10 +33,10 @@ struct LnIn {
 };
 int lin(const float *X, int ldx, const mac_linear_w_t &w, const float *bias, float *out, int ldo, long long M, int act,
         const float *res, int ldr, float *ln_out, int ldl, const float *g, const float *b, int pool, cudaStream_t st,
-        LnIn lnin = LnIn(), float *stats_out = nullptr)
+        LnIn lnin = LnIn(), float *stats_out = nullptr, int act_in = MAC_LIN_NONE)
 {
     return linear_forward(X, ldx, w.hi, w.lo, w.ldw, bias, out, ldo, static_cast<int>(M), w.N, w.K, act, res, ldr, ln_out, ldl,
-                          g, b, kLnEps, pool, st, 0, lnin.stats, lnin.g, lnin.b, stats_out);
+                          g, b, kLnEps, pool, st, 0, lnin.stats, lnin.g, lnin.b, stats_out, act_in);
 }
 
 // Buffers of one encoder stack over T tokens of width D.
@@ -100,11 +100,16 @@ int encoder_stack(const mac_encoder_w_t *enc, int n_enc, EncBufs &e, long long T
             return rc;
         LnIn n2;
         n2.stats = e.stats, n2.g = w.ln2_g, n2.b = w.ln2_b;
-        if (int rc = lin(e.x2, D, w.ff1, w.ff1.bias, e.ff, 2 * D, T, MAC_LIN_GELU, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, st, n2))
+        // The GELU between ff1 and ff2 is applied by ff2 ON LOAD (its split warps have slack; the 2 MUFU + 13 FP instructions per
+        // element made ff1's epilogue the slowest stage of the block): e.ff holds the pre-activation.  Same function on the same
+        // fp32 values, so the result is unchanged bit for bit.  MAC_FF_GELU_IN_EPILOGUE=1 restores the first form (A/B timing).
+        static const int gelu_in_epilogue = [] { const char *v = getenv("MAC_FF_GELU_IN_EPILOGUE"); return v ? atoi(v) : 0; }();
+        if (int rc = lin(e.x2, D, w.ff1, w.ff1.bias, e.ff, 2 * D, T, gelu_in_epilogue ? MAC_LIN_GELU : MAC_LIN_NONE, nullptr, 0, nullptr,
+                         0, nullptr, nullptr, 0, st, n2))
             return rc;
-        // x = x2 + ff2(ff), statistics of x for the next norm1 (or the final norm)
+        // x = x2 + ff2(gelu(ff)), statistics of x for the next norm1 (or the final norm)
         if (int rc = lin(e.ff, 2 * D, w.ff2, w.ff2.bias, e.x, D, T, MAC_LIN_NONE, e.x2, D, nullptr, 0, nullptr, nullptr, 0, st, LnIn(),
-                         e.stats))
+                         e.stats, gelu_in_epilogue ? MAC_LIN_NONE : MAC_LIN_GELU))
             return rc;
     }
     return MAC_OK;

@@ -190,5 +190,5 @@ int linear_forward(const float *X, int ldx, const float *W_hi, const float *W_lo
                    int ldo, int M, int N, int K, int act, const float *res, int ldr, float *ln_out, int ldl,
                    const float *ln_g, const float *ln_b, float ln_eps, int pool, cudaStream_t stream, int res_first = 0,
                    const float *lnin_stats = nullptr, const float *lnin_g = nullptr, const float *lnin_b = nullptr,
-                   float *stats_out = nullptr);
+                   float *stats_out = nullptr, int act_in = 0 /* MAC_LIN_NONE; MAC_LIN_GELU: exact GELU applied to X on load */);
 }  // namespace mac
