@@ -78,7 +78,6 @@ constexpr int kBaseThreads = 256;   // warp 0 X TMA, warp 1 MMA, warp 2 W TMA, w
 constexpr int kMaxStages = 8;
 constexpr int kEpiLd = 36;          // epilogue staging row stride (floats): 32 columns + 4 pad, conflict-free float4 rows
 constexpr int kEpiPadBytes = kBM * kEpiLd * 4;   // plain-store path: one padded 128 x 36 staging tile per epilogue group
-constexpr int kEpiTmaBytes = 2 * kBM * 128;      // TMA-store path: two swizzled 128 x 32 staging tiles per epilogue group
 constexpr int kEpiBar = 1;          // named barrier of the 128 epilogue threads
 
 struct LinearParams {
@@ -421,7 +420,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         // ===== X split: x -> (tf32(x), tf32(x - tf32(x))) =====
         if (C::kATmem) {
             // one row of the tile per thread (warp q of the four owns TMEM lanes 32 q .. 32 q + 31): 8 conflict-free LDS.128
-            // un-swizzle the row, the halves go to tensor memory, the raw slot is released at once
+            // un-swizzle the row, the halves go to tensor memory, then the raw slot returns to the producer
             const int r = threadIdx.x - 128;   // 0..127 = tile row = TMEM lane
             const uint32_t lane_addr = static_cast<uint32_t>(r & ~31) << 16;
             const bool lnin = p.lnin_stats != nullptr;
