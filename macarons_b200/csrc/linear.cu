@@ -181,7 +181,7 @@ struct Cfg {
     static constexpr int kEpiBufBytes = (kTmaOut && kStageTiles * kBM * 128 > kEpiPadBytes) ? kStageTiles * kBM * 128 : kEpiPadBytes;
     static constexpr int kWSlots = 2;
     static constexpr int kLnInMaxK = 512;
-    static constexpr int kVecBytes = 3 * BN * 4 + 2 * 128 * 4 +   // bias | gamma | beta of the tile's columns, LayerNorm partials
+    static constexpr int kVecBytes = 3 * BN * 4 + 4 * 128 * 4 +   // bias | gamma | beta of the tile's columns, LayerNorm partials (sum | variance)
                                      (SPLIT ? 2 * kLnInMaxK * 4 : 0);   // gamma | beta (K) of the LayerNorm applied on load
     static constexpr int kThreads = kBaseThreads + 128 * kEpiBufs;
     static constexpr int kBudget = 226 * 1024 - 1024 - 512 - kVecBytes - kEpiBufs * kEpiBufBytes - kWSlots * kWSlotBytes;
@@ -424,7 +424,7 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const int r = threadIdx.x - 128;   // 0..127 = tile row = TMEM lane
             const uint32_t lane_addr = static_cast<uint32_t>(r & ~31) << 16;
             const bool lnin = p.lnin_stats != nullptr;
-            float *kvec = svec + 3 * BN + 2 * 128;   // [2][kLnInMaxK]: gamma | beta over K
+            float *kvec = svec + 3 * BN + 4 * 128;   // [2][kLnInMaxK]: gamma | beta over K
             if (lnin) {
                 for (int c = r; c < C::kLnInMaxK; c += 128) {
                     kvec[c] = c < p.K ? p.lnin_g[c] : 0.f;
@@ -497,7 +497,8 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const int rl = q * 32 + lane;           // row of the tile owned by this thread
         const int gbar = kEpiBar + g;           // named barrier of this group
         float *mybuf = ebuf + g * (C::kEpiBufBytes / 4);
-        float *red = svec + 3 * BN;             // [G][128] cross-group LayerNorm partials
+        float *red = svec + 3 * BN;             // [G][128] cross-group partial row sums, then [G][128] partial centred squares: separate
+        float *red_var = red + 2 * 128;         // arrays, so that neither needs a barrier before it is rewritten for the next tile
         float v[32];
         int it = 0;
         // TMA-store path: staging tile (cb & 1) of this group holds chunk number cb of the group's chunk sequence; the
@@ -580,7 +581,9 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             auto all_groups_sync = [&]() { named_bar_sync(kEpiBar + G, 128 * G); };
 
             // per-column vectors of this tile -> shared memory (broadcast float4 reads instead of one LDG per element)
-            all_groups_sync();  // previous tile: staging buffers drained, vectors and partials no longer read
+            // (with fixed column vectors the groups run decoupled: their staging tiles are their own, the partial-sum arrays
+            // are ordered by the barriers of the statistics passes, the accumulator hand-over counts both groups' arrivals)
+            if (!fixed_cols || it == 0) all_groups_sync();  // previous tile: vectors no longer read
             if (!fixed_cols || it == 0) {
                 for (int c = t + g * 128; c < BN; c += 128 * G) {
                     const bool ok = c < ncols;
@@ -720,7 +723,6 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         red[g * 128 + rl] = sum;
                         all_groups_sync();
                         sum = red[rl] + red[128 + rl];
-                        all_groups_sync();
                     }
                     const float mean = sum / static_cast<float>(p.N);
                     float var = 0.f;
@@ -733,9 +735,9 @@ linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         }
                     }
                     if (G > 1) {
-                        red[g * 128 + rl] = var;
+                        red_var[g * 128 + rl] = var;
                         all_groups_sync();
-                        var = red[rl] + red[128 + rl];
+                        var = red_var[rl] + red_var[128 + rl];
                     }
                     const float rstd = 1.0f / sqrtf(var / static_cast<float>(p.N) + p.ln_eps);
                     if (p.stats_out && g == 0 && row_ok)   // the next layer normalises on load: 8 bytes instead of a row
