@@ -244,6 +244,7 @@ def path_stages(dev):
 
     def timed(fn, iters=3):
         fn()
+        fn()   # two warm-up calls: the depth forward captures its CUDA graph on the second call with a given shape
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
