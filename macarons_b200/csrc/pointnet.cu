@@ -188,10 +188,21 @@ __global__ void __launch_bounds__(256) embed_first_kernel(const EmbedParams p)
     const float *sb = sw + p.inner * IN;
     const int groups = (p.inner + (p.append ? IN : 0) + 3) / 4;  // float4 groups per token
     const long long total = p.T * 32;                              // 32 lanes per token (ldo <= 128)
+    // the block size and the grid stride are multiples of 32, so a thread serves the same 4 output columns for every token:
+    // its 4 x IN weights and 4 biases live in registers (read from shared memory inside the loop, the stride-4 / stride-12
+    // accesses were 4-way bank conflicts: ~60 wavefronts per token made the kernel LSU-bound at 2 TB/s)
+    const int c4 = static_cast<int>(threadIdx.x & 31);
+    float wr[4][IN], br[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int c = c4 * 4 + e;
+        br[e] = c < p.inner ? sb[c] : 0.f;
+#pragma unroll
+        for (int k = 0; k < IN; ++k) wr[e][k] = c < p.inner ? sw[c * IN + k] : 0.f;
+    }
     for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < total;
          g += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long t = g >> 5;
-        const int c4 = static_cast<int>(g & 31);
         if (c4 >= groups) continue;
         float v[IN];
         if (GATHER) {
@@ -213,9 +224,9 @@ __global__ void __launch_bounds__(256) embed_first_kernel(const EmbedParams p)
             const int c = c4 * 4 + e;
             float y = 0.f;
             if (c < p.inner) {
-                y = sb[c];
+                y = br[e];
 #pragma unroll
-                for (int k = 0; k < IN; ++k) y = fmaf(sw[c * IN + k], v[k], y);
+                for (int k = 0; k < IN; ++k) y = fmaf(wr[e][k], v[k], y);
                 y = gelu_exact(y);
             } else if (p.append && c < p.inner + IN) {
                 y = v[c - p.inner];
