@@ -257,10 +257,15 @@ __global__ void __launch_bounds__(256) attn16_kernel(const float *__restrict__ q
     for (long long s = blockIdx.x * 8ll + warp; s < n_seq; s += gridDim.x * 8ll) {
         const float *src = qkv + s * 16 * ldq;
         __syncwarp();
+        // the whole 16 x 192 tile as 16-byte async copies: all 24 per lane in flight at once (through registers the compiler
+        // kept 4 loads in flight, i.e. 32 KB per SM: the kernel was latency-bound at 63 % of the HBM roofline)
+#pragma unroll
         for (int e = lane; e < 16 * (W / 4); e += 32) {
             const int r = e / (W / 4), c = e % (W / 4);
-            *reinterpret_cast<float4 *>(t + r * LD + c * 4) = *reinterpret_cast<const float4 *>(src + r * ldq + c * 4);
+            cp_async16(t + r * LD + c * 4, src + r * ldq + c * 4);
         }
+        cp_async_commit();
+        cp_async_wait_all();
         __syncwarp();
         float o[2][DV];
 #pragma unroll
@@ -661,7 +666,8 @@ int attn16(const float *qkv, int ldq, float *out, int ldo, long long n_seq, int 
 {
     MAC_REQUIRE(qkv && out && n_seq > 0, "null tensor pointer");
     MAC_REQUIRE(dqk == 8 && dv == 32, "attn16 is built for 4 heads of (8, 32) dims");
-    MAC_REQUIRE(ldq % 4 == 0 && ldo % 4 == 0, "attention rows must be 16-byte aligned");
+    MAC_REQUIRE(ldq % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
+                "attention rows must be 16-byte aligned");
     constexpr int LD = 2 * 4 * 8 + 4 * 32 + 4;
     const size_t smem = 8 * 16 * LD * sizeof(float);
     static DeviceOnce once;
