@@ -187,7 +187,6 @@ __global__ void __launch_bounds__(256) embed_first_kernel(const EmbedParams p)
     __syncthreads();
     const float *sb = sw + p.inner * IN;
     const int groups = (p.inner + (p.append ? IN : 0) + 3) / 4;  // float4 groups per token
-    const long long total = p.T * 32;                              // 32 lanes per token (ldo <= 128)
     // the block size and the grid stride are multiples of 32, so a thread serves the same 4 output columns for every token:
     // its 4 x IN weights and 4 biases live in registers (read from shared memory inside the loop, the stride-4 / stride-12
     // accesses were 4-way bank conflicts: ~60 wavefronts per token made the kernel LSU-bound at 2 TB/s)
@@ -200,40 +199,54 @@ __global__ void __launch_bounds__(256) embed_first_kernel(const EmbedParams p)
 #pragma unroll
         for (int k = 0; k < IN; ++k) wr[e][k] = c < p.inner ? sw[c * IN + k] : 0.f;
     }
-    for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < total;
-         g += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long t = g >> 5;
-        if (c4 >= groups) continue;
-        float v[IN];
-        if (GATHER) {
-            const long long bq = t >> 4;            // b*Q + q
-            const int b = static_cast<int>(static_cast<unsigned>(bq) / static_cast<unsigned>(p.Q));   // bq < 2^32 (checked by the launcher): no 64-bit division
-            const int n = p.idx[t];
-            const float *pp = p.pc + (static_cast<size_t>(b) * p.N + n) * 3;
-            const float *xx = p.x + bq * 3;
+    // four tokens per warp and trip, all their loads issued before the first use: with one token per trip the dependent
+    // index -> point loads left ~0.5 KB per warp in flight and the kernel was latency-bound (2 TB/s)
+    constexpr int UNR = 4;
+    const long long warp_stride = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    if (c4 >= groups) return;
+    for (long long t0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; t0 < p.T; t0 += UNR * warp_stride) {
+        float v[UNR][IN];
+        const float *pp[UNR], *xx[UNR];
 #pragma unroll
-            for (int e = 0; e < IN; ++e) v[e] = pp[e] - xx[e];
-        } else {
-            const float *pp = p.in + t * p.ld_in;
-#pragma unroll
-            for (int e = 0; e < IN; ++e) v[e] = pp[e];
-        }
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int c = c4 * 4 + e;
-            float y = 0.f;
-            if (c < p.inner) {
-                y = br[e];
-#pragma unroll
-                for (int k = 0; k < IN; ++k) y = fmaf(wr[e][k], v[k], y);
-                y = gelu_exact(y);
-            } else if (p.append && c < p.inner + IN) {
-                y = v[c - p.inner];
+        for (int u = 0; u < UNR; ++u) {
+            const long long t = t0 + u * warp_stride;
+            const long long tc = t < p.T ? t : t0;   // a trip past the end repeats token t0 (result dropped)
+            if (GATHER) {
+                const long long bq = tc >> 4;            // b*Q + q
+                const int b = static_cast<int>(static_cast<unsigned>(bq) / static_cast<unsigned>(p.Q));   // bq < 2^32 (launcher)
+                pp[u] = p.pc + (static_cast<size_t>(b) * p.N + __ldg(p.idx + tc)) * 3;
+                xx[u] = p.x + bq * 3;
+            } else {
+                pp[u] = p.in + tc * p.ld_in;
+                xx[u] = nullptr;
             }
-            o[e] = y;
         }
-        *reinterpret_cast<float4 *>(p.out + t * p.ldo + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+            for (int e = 0; e < IN; ++e) v[u][e] = GATHER ? __ldg(pp[u] + e) - __ldg(xx[u] + e) : __ldg(pp[u] + e);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const long long t = t0 + u * warp_stride;
+            if (t >= p.T) break;
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = c4 * 4 + e;
+                float y = 0.f;
+                if (c < p.inner) {
+                    y = br[e];
+#pragma unroll
+                    for (int k = 0; k < IN; ++k) y = fmaf(wr[e][k], v[u][k], y);
+                    y = gelu_exact(y);
+                } else if (p.append && c < p.inner + IN) {
+                    y = v[u][c - p.inner];
+                }
+                o[e] = y;
+            }
+            *reinterpret_cast<float4 *>(p.out + t * p.ldo + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
