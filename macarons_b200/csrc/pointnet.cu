@@ -199,37 +199,39 @@ __global__ void __launch_bounds__(256) embed_first_kernel(const EmbedParams p)
 #pragma unroll
         for (int k = 0; k < IN; ++k) wr[e][k] = c < p.inner ? sw[c * IN + k] : 0.f;
     }
-    // four tokens per warp and trip, all their loads issued before the first use: with one token per trip the dependent
-    // index -> point loads left ~0.5 KB per warp in flight and the kernel was latency-bound (2 TB/s)
-    constexpr int UNR = 4;
-    const long long warp_stride = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-    if (c4 >= groups) return;
-    for (long long t0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; t0 < p.T; t0 += UNR * warp_stride) {
-        float v[UNR][IN];
-        const float *pp[UNR], *xx[UNR];
+    // A warp takes 32 consecutive tokens: lane l fetches the input of token l once (index, point, query: with one token per
+    // warp-trip every lane repeated that address arithmetic and those loads -- 228 warp instructions per token, issue-bound at
+    // 76 % issue-active), then the 32 inputs are broadcast one after the other with shuffles and lane l produces its 4 columns.
+    const int lane = threadIdx.x & 31;
+    const bool has_cols = c4 < groups;
+    const long long n_tiles = (p.T + 31) >> 5;
+    const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long tile = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; tile < n_tiles; tile += n_warps) {
+        const long long t = tile * 32 + lane;
+        float v[IN];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const long long t = t0 + u * warp_stride;
-            const long long tc = t < p.T ? t : t0;   // a trip past the end repeats token t0 (result dropped)
+        for (int e = 0; e < IN; ++e) v[e] = 0.f;
+        if (t < p.T) {
             if (GATHER) {
-                const long long bq = tc >> 4;            // b*Q + q
+                const long long bq = t >> 4;            // b*Q + q
                 const int b = static_cast<int>(static_cast<unsigned>(bq) / static_cast<unsigned>(p.Q));   // bq < 2^32 (launcher)
-                pp[u] = p.pc + (static_cast<size_t>(b) * p.N + __ldg(p.idx + tc)) * 3;
-                xx[u] = p.x + bq * 3;
+                const float *pp = p.pc + (static_cast<size_t>(b) * p.N + __ldg(p.idx + t)) * 3;
+                const float *xx = p.x + bq * 3;
+#pragma unroll
+                for (int e = 0; e < IN; ++e) v[e] = __ldg(pp + e) - __ldg(xx + e);
             } else {
-                pp[u] = p.in + tc * p.ld_in;
-                xx[u] = nullptr;
+                const float *pp = p.in + t * p.ld_in;
+#pragma unroll
+                for (int e = 0; e < IN; ++e) v[e] = __ldg(pp + e);
             }
         }
+        const int n = static_cast<int>(p.T - tile * 32 < 32 ? p.T - tile * 32 : 32);
+        float *orow = p.out + tile * 32 * p.ldo + c4 * 4;
+        for (int j = 0; j < n; ++j, orow += p.ldo) {
+            float a[IN];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-#pragma unroll
-            for (int e = 0; e < IN; ++e) v[u][e] = GATHER ? __ldg(pp[u] + e) - __ldg(xx[u] + e) : __ldg(pp[u] + e);
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const long long t = t0 + u * warp_stride;
-            if (t >= p.T) break;
+            for (int e = 0; e < IN; ++e) a[e] = __shfl_sync(0xffffffffu, v[e], j);
+            if (!has_cols) continue;
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -238,14 +240,14 @@ __global__ void __launch_bounds__(256) embed_first_kernel(const EmbedParams p)
                 if (c < p.inner) {
                     y = br[e];
 #pragma unroll
-                    for (int k = 0; k < IN; ++k) y = fmaf(wr[e][k], v[u][k], y);
+                    for (int k = 0; k < IN; ++k) y = fmaf(wr[e][k], a[k], y);
                     y = gelu_exact(y);
                 } else if (p.append && c < p.inner + IN) {
-                    y = v[u][c - p.inner];
+                    y = a[c - p.inner];
                 }
                 o[e] = y;
             }
-            *reinterpret_cast<float4 *>(p.out + t * p.ldo + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4 *>(orow) = make_float4(o[0], o[1], o[2], o[3]);
         }
     }
 }
@@ -665,11 +667,14 @@ int embed_first(const float *in, int ld_in, int in_dim, const float *pc, const f
     p.in = in, p.ld_in = ld_in, p.pc = pc, p.x = x, p.idx = idx, p.Q = Q, p.N = N;
     p.w = w, p.b = b, p.inner = inner, p.append = append, p.out = out, p.ldo = ldo, p.T = T;
     const size_t smem = static_cast<size_t>(inner) * (in_dim + 1) * sizeof(float);
-    const long long want = (T * 32 + 255) / 256;
+    // one 32-token tile per warp; 8 warps per CTA, or one when there are too few tiles to fill the machine that way
+    const long long n_tiles = (T + 31) / 32;
+    const int block = n_tiles < 148 * 8 ? 32 : 256;
+    const long long want = (n_tiles * 32 + block - 1) / block;
     const int grid = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
-    if (gather) embed_first_kernel<3, true><<<grid, 256, smem, stream>>>(p);
-    else if (in_dim == 3) embed_first_kernel<3, false><<<grid, 256, smem, stream>>>(p);
-    else embed_first_kernel<4, false><<<grid, 256, smem, stream>>>(p);
+    if (gather) embed_first_kernel<3, true><<<grid, block, smem, stream>>>(p);
+    else if (in_dim == 3) embed_first_kernel<3, false><<<grid, block, smem, stream>>>(p);
+    else embed_first_kernel<4, false><<<grid, block, smem, stream>>>(p);
     MAC_CUDA(cudaGetLastError());
     count_launch();
     return MAC_OK;
