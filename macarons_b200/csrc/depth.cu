@@ -500,7 +500,8 @@ struct DepthGraph {
     void *workspace = nullptr;
     size_t workspace_bytes = 0;
     int B = 0, n_alpha = 0, H = 0, W = 0, device = -1;
-    int calls = 0;
+    long long calls = 0;     // 0: free entry
+    bool failed = false;     // the capture failed once: this key keeps the plain launches
     cudaGraphExec_t exec = nullptr;
     unsigned launches = 0;
     Ctx::Out outs[4] = {};
@@ -589,7 +590,7 @@ extern "C" int mac_manydepth_forward_f32(const mac_manydepth_w_t *w, const float
         victim->calls = 1;
         return MAC_OK;
     }
-    if (!g->exec) {
+    if (!g->exec && !g->failed) {
         // second call: capture the body on a private stream
         cudaStream_t cap = nullptr;
         MAC_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
@@ -609,8 +610,9 @@ extern "C" int mac_manydepth_forward_f32(const mac_manydepth_w_t *w, const float
         if (rc != MAC_OK) {
             // capture is an optimisation: fall back to plain launches (and stop trying for this key)
             cudaGetLastError();
+            uncount_launch(static_cast<unsigned>(mac_launch_count() - n0));   // nothing of the capture ran
             g->exec = nullptr;
-            g->calls = 1 << 30;
+            g->failed = true;
             Ctx direct = make_ctx(st, false);
             return run_direct(direct);
         }
@@ -619,11 +621,11 @@ extern "C" int mac_manydepth_forward_f32(const mac_manydepth_w_t *w, const float
         for (int i = 0; i < 4; ++i) g->outs[i] = cx.outs[i];
         g->img_ws = cx.img_ws, g->cam_ws = cx.cam_ws;
     }
-    if (g->calls >= (1 << 30)) {
+    ++g->calls;
+    if (g->failed) {
         Ctx cx = make_ctx(st, false);
         return run_direct(cx);
     }
-    ++g->calls;
     if (int rc = load_inputs(st, x, x_alpha, cam, g->img_ws, g->cam_ws, B, n_alpha, H, W)) return rc;
     MAC_CUDA(cudaGraphLaunch(g->exec, st));
     count_launch(g->launches);
