@@ -210,8 +210,12 @@ __global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateP
 {
     extern __shared__ float sm[];
     const int n_bins = p.n_elev * p.n_azim;
-    float *T = sm;                         // [n_bins][64]
-    float *sinp = T + n_bins * 64;         // [n_bins]
+    // table rows padded to kTS = 68 floats: in the transposed build below lane j writes T[j][k], and with a stride of 64 all
+    // 32 lanes hit one bank (a 32-way conflict on every one of the 196 stores of each CTA, 8 CTAs per SM); 68 makes it 4-way
+    // and keeps the rows 16-byte aligned for the LDS.128 of phase 2
+    constexpr int kTS = 68;
+    float *T = sm;                         // [n_bins][kTS]
+    float *sinp = T + n_bins * kTS;        // [n_bins]
     float *sviews = sinp + kMaxBins;       // [V][3]
     for (int j = threadIdx.x; j < n_bins; j += blockDim.x) sinp[j] = sinf(h_polar[j]);
     for (int i = threadIdx.x; i < p.V * 3; i += blockDim.x) sviews[i] = p.views[i];
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateP
     const int lane = threadIdx.x & 31;
     for (int k = threadIdx.x >> 5; k < 64; k += 8)              // row k of base (64, n_bins): coalesced read, transposed store
         for (int j = lane; j < n_bins; j += 32)
-            T[j * 64 + k] = __fmul_rn(__fmul_rn(__fmul_rn(base[k * n_bins + j], sinp[j]), polar_step), azim_step);
+            T[j * kTS + k] = __fmul_rn(__fmul_rn(__fmul_rn(base[k * n_bins + j], sinp[j]), polar_step), azim_step);
     __syncthreads();
     const long long n_tiles = (p.n_pts + 31) / 32;
     const long long warp0 = blockIdx.x * 8ll + (threadIdx.x >> 5), n_warps = gridDim.x * 8ll;
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(256, 8) viewstate_harm_kernel(const ViewStateP
                 while (m) {   // ascending bins; the two half-warps run their own bit lists under predication
                     const int j = w * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    const float4 t = T4[j * 16];
+                    const float4 t = T4[j * (kTS / 4)];
                     acc.x = __fadd_rn(acc.x, t.x), acc.y = __fadd_rn(acc.y, t.y);
                     acc.z = __fadd_rn(acc.z, t.z), acc.w = __fadd_rn(acc.w, t.w);
                 }
@@ -359,7 +363,7 @@ extern "C" int mac_viewstate_harm_f32(const float *pts, int pts_dim, const float
     p.azim_wrap = -((n_azim + 1) / 2);
     p.elev_shift = n_elev / 2;
     const int n_bins = n_elev * n_azim;
-    const size_t smem = (64 * static_cast<size_t>(n_bins) + kMaxBins + 3 * static_cast<size_t>(V)) * sizeof(float);
+    const size_t smem = (68 * static_cast<size_t>(n_bins) + kMaxBins + 3 * static_cast<size_t>(V)) * sizeof(float);   // kTS = 68
     static DeviceOnce once;
     if (int rc = ensure_dynamic_smem(once, viewstate_harm_kernel, 96 * 1024)) return rc;
     const long long want = ((p.n_pts + 31) / 32 + 7) / 8;   // one 32-point tile per warp, 8 warps per CTA
